@@ -1,0 +1,185 @@
+// alignmentstoreadset_b200.cpp — drop-in body for the reference's
+//     void alignmentsToReadset(AlignmentReader&, Graph&, unordered_map<int, unordered_map<int,
+//          vector<vector<int>>>>& pathToAlleles, string readsetfile, bool shell_logging,
+//          vector<pair<int,int>>& size_sorting, std::mutex&)
+// (reference src/alignmentstoreadset.cpp:55, called at src/polyassembly.cpp:171).
+//
+// It is compiled against the reference's own headers (graph.hpp, alignmentreader.hpp), does
+// three things and nothing else:
+//   1. flatten  alignmentreader.alignments / pathToAlleles / size_sorting  into the CSR batch
+//      of include/ahsoka_b200.h  (SURVEY §8b);
+//   2. call ahs_phase_batch() — the sm_100a CUDA path; there is no CPU path behind it;
+//   3. write <prefix>-result.txt, <prefix>-chain<id>-result.txt and the stdout "hap:" lines with
+//      the semantics of src/alignmentstoreadset.cpp:70-83 and :411-486.
+// Not reproduced: ./logfile.log and the -readset*.txt debugging dumps (third-party
+// ReadSet::toString() text), see INTEGRATION.md.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <mutex>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "alignmentreader.hpp"   // reference header, found through -I<reference>/src
+#include "graph.hpp"             // reference header
+#include "ahsoka_b200.h"
+
+namespace ahs_host {
+
+struct FlatBatch {
+    std::vector<int32_t> chain_id, anode, stage_a_order, enode, entry_read;
+    std::vector<int64_t> bubble_off{0}, allele_off{0}, anode_off{0}, read_off{0}, entry_off{0}, enode_off{0};
+    std::vector<float> entry_identity;
+    std::vector<std::vector<std::string>> read_names;   // per chain: chain-local read index -> name
+    ahs_batch_in view;
+};
+
+static bool same_entry(AlignmentPath& a, AlignmentPath& b) {
+    return a.name == b.name && a.id == b.id && a.startpos == b.startpos && a.endpos == b.endpos && a.nodes == b.nodes;
+}
+
+// the containers of reference src/alignmentreader.hpp:38 and
+// src/polyassembly.cpp:126-140, flattened CSR-by-chain in size_sorting order.
+void flatten(AlignmentReader& reader, std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
+             std::vector<std::pair<int, int>>& size_sorting, int ploidy, FlatBatch& fb) {
+    for (auto& size : size_sorting) {
+        const int chainid = size.second;
+        // same copy the reference takes (alignmentstoreadset.cpp:76): its iteration order is stage A's
+        auto chainmap = std::make_pair(chainid, pathToAlleles[chainid]);
+        fb.chain_id.push_back(chainid);
+        int B = 0;
+        if (chainmap.second.size() > 1) for (auto& kv : chainmap.second) B = std::max(B, kv.first + 1);
+        std::vector<char> seen(B, 0);
+        for (auto& kv : chainmap.second) if (kv.first >= 0 && kv.first < B) { fb.stage_a_order.push_back(kv.first); seen[kv.first] = 1; }
+        for (int b = 0; b < B; b++) if (!seen[b]) fb.stage_a_order.push_back(b);
+        for (int b = 0; b < B; b++) {
+            auto it = chainmap.second.find(b);
+            if (it != chainmap.second.end()) for (auto& path : it->second) {
+                fb.anode.insert(fb.anode.end(), path.begin(), path.end());
+                fb.anode_off.push_back((int64_t)fb.anode.size());
+            }
+            fb.allele_off.push_back((int64_t)fb.anode_off.size() - 1);
+        }
+        fb.bubble_off.push_back((int64_t)fb.allele_off.size() - 1);
+        fb.read_names.emplace_back();
+        std::vector<std::string>& names = fb.read_names.back();
+        if (B > 1) {
+            std::unordered_map<std::string, int> intern;
+            auto it = reader.alignments.find(chainid);
+            if (it != reader.alignments.end()) {
+                std::vector<AlignmentPath>& v = it->second;
+                for (size_t e = 0; e < v.size(); e++) {
+                    if (e > 0 && same_entry(v[e], v[e - 1])) continue;       // per-node duplicates, alignmentreader.cpp:176-183
+                    auto ins = intern.emplace(v[e].name, (int)names.size());
+                    if (ins.second) names.push_back(v[e].name);
+                    std::vector<int> raw = v[e].getRawIds();
+                    fb.enode.insert(fb.enode.end(), raw.begin(), raw.end());
+                    fb.enode_off.push_back((int64_t)fb.enode.size());
+                    fb.entry_read.push_back(ins.first->second);
+                    fb.entry_identity.push_back(v[e].id);
+                }
+            }
+        }
+        fb.read_off.push_back(fb.read_off.back() + (int64_t)names.size());
+        fb.entry_off.push_back((int64_t)fb.entry_read.size());
+    }
+    ahs_batch_in& v = fb.view;
+    v.n_chains = (int32_t)fb.chain_id.size(); v.ploidy = ploidy; v.chain_id = fb.chain_id.data();
+    v.bubble_off = fb.bubble_off.data(); v.allele_off = fb.allele_off.data(); v.anode_off = fb.anode_off.data();
+    v.anode = fb.anode.data(); v.stage_a_order = fb.stage_a_order.data(); v.read_off = fb.read_off.data();
+    v.entry_off = fb.entry_off.data(); v.enode_off = fb.enode_off.data(); v.enode = fb.enode.data();
+    v.entry_read = fb.entry_read.data(); v.entry_identity = fb.entry_identity.data();
+}
+
+// Emission, semantics of reference src/alignmentstoreadset.cpp:70-83 and :411-486.
+void emit(const ahs_batch_out& out, Graph& graph,
+          std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
+          std::vector<std::pair<int, int>>& size_sorting, const std::string& prefix) {
+    std::ofstream full_output(prefix + "-result.txt", std::ios_base::app);        // append, :72
+    const int ploidy = out.ploidy;
+    for (size_t c = 0; c < size_sorting.size(); c++) {
+        const int chainid = size_sorting[c].second;
+        full_output << "chain id: " << chainid << std::endl;
+        full_output << "size of chain: " << pathToAlleles[chainid].size() << std::endl;
+        if (out.status[c] != AHS_CHAIN_OK) {
+            if (out.status[c] >= AHS_CHAIN_TOO_LARGE)
+                std::cerr << "ahsoka_b200: chain " << chainid << " not phased (status " << out.status[c] << ")" << std::endl;
+            continue;
+        }
+        std::ofstream resfile(prefix + "-chain" + std::to_string(chainid) + "-result.txt");
+        const int64_t p0 = out.pos_off[c], n_pos = out.pos_off[c + 1] - p0;
+        auto& alleles_of = pathToAlleles[chainid];
+        for (int i = 0; i < ploidy; i++) {
+            std::set<int> usednodes;
+            full_output << "haplotype " << i << ":" << std::endl;
+            for (int64_t j = 0; j < n_pos; j++) {
+                const uint32_t cons = out.hap_allele[(p0 + j) * ploidy + i];
+                const std::vector<int>& ap = alleles_of[out.pos[p0 + j]].at(cons);
+                for (size_t ind = 0; ind + 1 < ap.size(); ind++) {
+                    const int single = ap[ind], next = ap[ind + 1];
+                    if (usednodes.count(single)) continue;
+                    Node first = graph.nodes.find(single)->second;       // Graph::getNode without the linear scan (f2)
+                    Node sec = graph.nodes.find(next)->second;
+                    std::pair<DirectedNode, DirectedNode> tup = graph.getEdge(first, sec);
+                    const char dir = tup.first.end == 1 ? '+' : '-';
+                    resfile << single << '(' << dir << ')' << ",";
+                    full_output << single << '(' << dir << ')' << ",";
+                    usednodes.insert(single);
+                }
+            }
+            resfile << std::endl;
+            full_output << std::endl;
+        }
+        resfile.close();
+        for (int i = 0; i < ploidy; i++) {                                           // :479-486
+            std::cout << "hap: " << std::endl;
+            for (int64_t j = 0; j < n_pos; j++) std::cout << (uint32_t)out.hap_allele[(p0 + j) * ploidy + i] << "(" << out.pos[p0 + j] << ")" << ",";
+            std::cout << std::endl;
+        }
+    }
+    full_output.close();
+}
+
+}  // namespace ahs_host
+
+void alignmentsToReadset(AlignmentReader& alignmentreader, Graph& graph,
+                         std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
+                         std::string readsetfile, bool shell_logging, std::vector<std::pair<int, int>>& size_sorting,
+                         std::mutex& g_display_mutex) {
+    std::lock_guard<std::mutex> guard(g_display_mutex);
+    (void)shell_logging;
+    const char* pl = getenv("AHSOKA_PLOIDY");                 // reference: hard-coded 2 (:306)
+    const int ploidy = pl ? atoi(pl) : 2;
+    ahs_host::FlatBatch fb;
+    ahs_host::flatten(alignmentreader, pathToAlleles, size_sorting, ploidy, fb);
+    if (const char* dump = getenv("AHSOKA_DUMP_BATCH")) {
+        // raw little-endian dump of the flattened batch, for the Python tests
+        FILE* f = fopen(dump, "wb");
+        if (f) {
+            auto w64 = [&](int64_t v) { fwrite(&v, 8, 1, f); };
+            auto wv = [&](const void* p, size_t bytes) { fwrite(p, 1, bytes, f); };
+            w64(fb.view.n_chains); w64(ploidy); w64(fb.bubble_off.back()); w64((int64_t)fb.anode_off.size() - 1); w64((int64_t)fb.anode.size());
+            w64((int64_t)fb.entry_read.size()); w64((int64_t)fb.enode.size());
+            wv(fb.chain_id.data(), 4 * fb.chain_id.size()); wv(fb.bubble_off.data(), 8 * fb.bubble_off.size());
+            wv(fb.allele_off.data(), 8 * fb.allele_off.size()); wv(fb.anode_off.data(), 8 * fb.anode_off.size());
+            wv(fb.anode.data(), 4 * fb.anode.size()); wv(fb.stage_a_order.data(), 4 * fb.stage_a_order.size());
+            wv(fb.read_off.data(), 8 * fb.read_off.size()); wv(fb.entry_off.data(), 8 * fb.entry_off.size());
+            wv(fb.enode_off.data(), 8 * fb.enode_off.size()); wv(fb.enode.data(), 4 * fb.enode.size());
+            wv(fb.entry_read.data(), 4 * fb.entry_read.size()); wv(fb.entry_identity.data(), 4 * fb.entry_identity.size());
+            fclose(f);
+        }
+    }
+    ahs_batch_out out;
+    const char* dv = getenv("AHSOKA_DEVICE");
+    int rc = ahs_phase_batch(&fb.view, &out, dv ? atoi(dv) : 0);
+    if (rc != AHS_OK) {
+        std::cerr << "ahsoka_b200: phasing failed (" << rc << "): " << ahs_last_error() << std::endl;
+        exit(70);                                             // fail loudly: no CPU path behind the ABI
+    }
+    ahs_host::emit(out, graph, pathToAlleles, size_sorting, readsetfile);
+    ahs_free_out(&out);
+}

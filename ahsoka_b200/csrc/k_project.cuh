@@ -1,0 +1,401 @@
+// k_project.cuh — projection of alignment entries onto bubbles -> read x bubble allele matrix.
+//
+// Replaces reference src/alignmentstoreadset.cpp:90-136 (stage A), :146-209 (filter, boundary
+// set), :210-254 (stage B), :262-297 (filter, ReadSet::sort()) and is_subset (:495-548).
+//
+// Layout in HBM (per chain c, R_c distinct read names, B_c bubbles):
+//   mask[mrow_off[c] + r*B_c + b]  u16: bit a (a<15) = some entry of read r with identity*100 > 90
+//                                  contains the INNER nodes of allele a of bubble b (stage B test);
+//                                  bit 15 = some entry contains a FULL allele path of b (stage A).
+//   Set with atomicOr, so the result does not depend on scheduling.  The few order-dependent
+//   facts of the reference (which entry creates a read -> its mapq; first matching allele) are
+//   recovered from 64-bit atomicMin keys (position | allele | entry index), i.e. the minimum in
+//   the reference's own loop order (position asc, allele asc, entry asc).
+//
+// Finding matches: every allele path has one TRIGGER node (its first inner node; path[0] if it
+// has no inner node).  A path can only be contained in an entry that contains its trigger, so a
+// hash table trigger node -> alleles turns the reference's bubbles x alleles x entries scan into
+// one lookup per entry node.  Paths without inner nodes match EVERY entry in stage B
+// (std::includes of an empty range, SURVEY A#9): they are kept per bubble as `bubble_univ`.
+#pragma once
+#include "common.cuh"
+#include "device_batch.cuh"
+
+namespace ahs {
+
+// ---------------------------------------------------------------- generic helpers
+__global__ void k_owner(const int64_t* __restrict__ off, int n_owner, int64_t n_elem, int32_t* __restrict__ out) {
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n_elem; x += (int64_t)gridDim.x * blockDim.x)
+        out[x] = owner_of(off, n_owner, x);
+}
+
+__global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) p[x] = v;
+}
+__global__ void k_fill_i32(int32_t* p, int32_t v, int64_t n) {
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) p[x] = v;
+}
+
+// stage-A visit rank of each bubble (inverse of stage_a_order, alignmentstoreadset.cpp:90)
+__global__ void k_rank_a(DB d) {
+    for (int64_t gb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gb < d.NB; gb += (int64_t)gridDim.x * blockDim.x) {
+        int c = d.bubble_chain[gb];
+        int64_t b0 = d.bubble_off[c];
+        if (d.stage_a_order) d.rankA[b0 + d.stage_a_order[gb]] = (int32_t)(gb - b0);
+        else d.rankA[gb] = (int32_t)(d.bubble_off[c + 1] - 1 - gb);
+    }
+}
+
+// ---------------------------------------------------------------- K0: trigger table
+__global__ void k_build_triggers(DB d) {
+    for (int64_t ga = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ga < d.NA; ga += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t gb = d.allele_bubble[ga];
+        const int c = d.bubble_chain[gb];
+        const int64_t o = d.anode_off[ga];
+        const int len = (int)(d.anode_off[ga + 1] - o);
+        d.inc_next[ga] = -1;
+        if (len <= 0) { atomicOr(d.err_flags, 1); continue; }
+        if (d.bubble_off[c + 1] - d.bubble_off[c] <= 1) continue;          // trivial chain: never phased (:86)
+        const int a = (int)(ga - d.allele_off[gb]);
+        if (a >= MAX_ALLELES) { atomicOr(d.err_flags, 2); continue; }
+        if (len <= 2) atomicMin(&d.bubble_univ[gb], (uint32_t)a);          // no inner node: matches every entry (A#9)
+        const int32_t trig = len >= 3 ? d.anode[o + 1] : d.anode[o];
+        const uint64_t key = ((uint64_t)(uint32_t)c << 32) | (uint32_t)trig;
+        uint32_t slot = hash64(key) & d.hmask;
+        while (true) {
+            unsigned long long prev = atomicCAS((unsigned long long*)&d.hkeys[slot], (unsigned long long)KEY_NONE, (unsigned long long)key);
+            if (prev == KEY_NONE || prev == key) break;
+            slot = (slot + 1) & d.hmask;
+        }
+        d.inc_next[ga] = atomicExch(&d.hhead[slot], (int32_t)ga);
+    }
+}
+
+// ---------------------------------------------------------------- K1: project entries
+__device__ __forceinline__ bool entry_has(const int32_t* __restrict__ nodes, int L, int32_t v) {
+    for (int x = 0; x < L; x++) if (__ldg(nodes + x) == v) return true;
+    return false;
+}
+
+// one warp per alignment entry; lanes stride over the entry's nodes
+__global__ void __launch_bounds__(256) k_project(DB d) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = lane_id();
+    for (int64_t ge = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); ge < d.NE; ge += (int64_t)gridDim.x * warps_per_block) {
+        const int c = d.entry_chain[ge];
+        const int64_t b0 = d.bubble_off[c];
+        const int B = (int)(d.bubble_off[c + 1] - b0);
+        if (B <= 1) continue;
+        const int rl = d.entry_read[ge];
+        const int64_t r = d.read_off[c] + rl;
+        const uint32_t el = (uint32_t)(ge - d.entry_off[c]);
+        const float ident = d.entry_identity[ge];
+        const bool good = good_identity(ident);
+        if (lane == 0) { atomicMin(&d.first_entry[r], el); if (good) d.has_good[r] = 1; }
+        uint16_t* mrow = d.mask + d.mrow_off[c] + (int64_t)rl * B;
+        const int32_t* nodes = d.enode + d.enode_off[ge];
+        const int L = (int)(d.enode_off[ge + 1] - d.enode_off[ge]);
+        for (int x = lane; x < L; x += 32) {
+            const int32_t v = __ldg(nodes + x);
+            const uint64_t key = ((uint64_t)(uint32_t)c << 32) | (uint32_t)v;
+            uint32_t slot = hash64(key) & d.hmask;
+            int32_t ga = -1;
+            while (true) {
+                const uint64_t k = d.hkeys[slot];
+                if (k == key) { ga = d.hhead[slot]; break; }
+                if (k == KEY_NONE) break;
+                slot = (slot + 1) & d.hmask;
+            }
+            for (; ga >= 0; ga = d.inc_next[ga]) {
+                const int64_t gb = d.allele_bubble[ga];
+                const int b = (int)(gb - b0);
+                const int a = (int)(ga - d.allele_off[gb]);
+                const int64_t o = d.anode_off[ga];
+                const int len = (int)(d.anode_off[ga + 1] - o);
+                bool inner_ok = len >= 3;                      // len <= 2: universal, handled in k_read_rows
+                for (int y = 2; inner_ok && y < len - 1; y++) inner_ok = entry_has(nodes, L, d.anode[o + y]);
+                bool full_ok;
+                if (len >= 3) full_ok = inner_ok && entry_has(nodes, L, d.anode[o]) && entry_has(nodes, L, d.anode[o + len - 1]);
+                else full_ok = (len == 1) || entry_has(nodes, L, d.anode[o + 1]);
+                if (inner_ok) {
+                    if (good) atomic_or_u16(&mrow[b], (uint16_t)(1u << a));
+                    atomicMin((unsigned long long*)&d.create_key[r], (unsigned long long)make_key((uint32_t)b, (uint32_t)a, el));
+                }
+                if (full_ok) {
+                    atomic_or_u16(&mrow[b], (uint16_t)0x8000u);
+                    atomicMin((unsigned long long*)&d.createA_key[r], (unsigned long long)make_key((uint32_t)d.rankA[gb], (uint32_t)a, el));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K1b: stage-A statistics per read
+// count / first / last fully contained bubble and the stage-A mapq (:146-165, :173-182)
+__global__ void __launch_bounds__(256) k_read_stage_a(DB d) {
+    const int wpb = blockDim.x >> 5, lane = lane_id();
+    for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < d.NR; r += (int64_t)gridDim.x * wpb) {
+        const int c = d.read_chain[r];
+        const int B = (int)(d.bubble_off[c + 1] - d.bubble_off[c]);
+        if (B <= 1) continue;
+        const uint16_t* mrow = d.mask + d.mrow_off[c] + (r - d.read_off[c]) * B;
+        int cnt = 0, first = INT32_MAX, last = -1;
+        for (int b = lane; b < B; b += 32) if (mrow[b] & 0x8000u) { cnt++; first = min(first, b); last = max(last, b); }
+        cnt = warp_sum_i32(cnt); first = warp_min_i32(first); last = warp_max_i32(last);
+        if (lane == 0) {
+            int mapq = 0;
+            if (cnt > 0) {
+                const uint32_t el = (uint32_t)(d.createA_key[r] & 0xffffffffu);
+                mapq = mapq_of(d.entry_identity[d.entry_off[c] + el]);
+                atomicMax(&d.ch_maxpos[c], last);
+            }
+            d.rdA_cnt[r] = cnt; d.rdA_first[r] = first; d.rdA_last[r] = last; d.rdA_mapq[r] = mapq;
+        }
+    }
+}
+
+// boundary flags: which of maxpos-1 / maxpos are last / first positions of filtered stage-A reads (:173-189)
+__global__ void k_chain_flags(DB d) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < d.NR; r += (int64_t)gridDim.x * blockDim.x) {
+        const int c = d.read_chain[r];
+        if (d.bubble_off[c + 1] - d.bubble_off[c] <= 1) continue;
+        if (!(d.rdA_cnt[r] > 1 && d.rdA_mapq[r] >= 93)) continue;
+        const int mp = d.ch_maxpos[c];
+        int f = 0;
+        if (d.rdA_last[r] == mp) f |= 1;
+        if (d.rdA_last[r] == mp - 1) f |= 2;
+        if (d.rdA_first[r] == mp) f |= 4;
+        if (d.rdA_first[r] == mp - 1) f |= 8;
+        if (f) atomicOr(&d.ch_flags[c], f);
+    }
+}
+
+// to_be_added = [0,maxpos) U {e, e+1 : e in last \ first} = [0, T)  (:173-209, SURVEY A#10)
+__global__ void k_chain_T(DB d) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.C; c += gridDim.x * blockDim.x) {
+        const int B = (int)(d.bubble_off[c + 1] - d.bubble_off[c]);
+        if (B <= 1) { d.ch_status[c] = AHS_CHAIN_TRIVIAL; d.ch_T[c] = 0; continue; }
+        const int mp = d.ch_maxpos[c];
+        if (mp < 0) { d.ch_status[c] = AHS_CHAIN_EMPTY; d.ch_T[c] = 0; continue; }   // reference: UB (:193)
+        const int f = d.ch_flags[c];
+        const bool e_max = (f & 1) && !(f & 4);          // maxpos   in last \ first  -> adds maxpos, maxpos+1
+        const bool e_m1  = (f & 2) && !(f & 8);          // maxpos-1 in last \ first  -> adds maxpos-1, maxpos
+        int T = mp;
+        if (e_max) T = mp + 2; else if (e_m1) T = mp + 1;
+        d.ch_T[c] = min(T, B);                             // bubble ids >= B have no alleles (:216 default-insert)
+        d.ch_status[c] = AHS_CHAIN_OK;
+    }
+}
+
+// ---------------------------------------------------------------- K1d: final rows per read (stage B + filter)
+__global__ void __launch_bounds__(256) k_read_rows(DB d) {
+    const int wpb = blockDim.x >> 5, lane = lane_id();
+    for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < d.NR; r += (int64_t)gridDim.x * wpb) {
+        const int c = d.read_chain[r];
+        if (lane == 0) d.rd_pass[r] = 0;
+        if (d.ch_status[c] != AHS_CHAIN_OK) continue;
+        const int64_t b0g = d.bubble_off[c];
+        const int B = (int)(d.bubble_off[c + 1] - b0g);
+        const int T = d.ch_T[c];
+        uint16_t* mrow = d.mask + d.mrow_off[c] + (r - d.read_off[c]) * B;
+        const uint32_t fe = d.first_entry[r];
+        const bool has_entry = fe != 0xffffffffu;
+        const bool hg = d.has_good[r] != 0;
+        // creation triple: minimum (position, allele, entry) over all matches, universal alleles included
+        uint64_t ck = d.create_key[r];
+        if (has_entry) for (int b = lane; b < T; b += 32) {
+            const uint32_t u = d.bubble_univ[b0g + b];
+            if (u != 0xffffffffu) { uint64_t k = make_key((uint32_t)b, u, fe); ck = k < ck ? k : ck; }
+        }
+        ck = warp_min_u64(ck);
+        const int bc = (ck == KEY_NONE) ? INT32_MAX : (int)(ck >> 40);
+        int nv = 0, last = -1;
+        if (bc < T) {
+            const int ac = (int)((ck >> 32) & 0xff);
+            for (int b = lane; b < B; b += 32) {
+                uint32_t code = 0;
+                if (b < T) {
+                    uint32_t m = mrow[b] & 0x7fffu;
+                    const uint32_t u = d.bubble_univ[b0g + b];
+                    if (u != 0xffffffffu && hg) m |= 1u << u;
+                    if (b == bc) code = (uint32_t)ac + 1u;
+                    else if (m) code = (uint32_t)__ffs((int)m);             // lowest set bit = first matching allele
+                }
+                mrow[b] = (uint16_t)code;
+                if (code) { nv++; last = max(last, b); }
+            }
+            nv = warp_sum_i32(nv); last = warp_max_i32(last);
+        }
+        int mapq = 0; bool pass = false;
+        if (bc < T) {
+            mapq = mapq_of(d.entry_identity[d.entry_off[c] + (uint32_t)(ck & 0xffffffffu)]);
+            pass = nv > 1 && mapq >= 93;                                    // :270
+        }
+        if (pass) for (int b = lane; b < T; b += 32) if (mrow[b]) d.poscov[b0g + b] = 1;
+        if (lane == 0) {
+            d.rd_nv[r] = nv; d.rd_first[r] = bc; d.rd_last[r] = last; d.rd_mapq[r] = mapq; d.rd_pass[r] = pass ? 1 : 0;
+            d.create_key[r] = ck;
+            if (pass) { atomicAdd(&d.ch_nfinal[c], 1); atomicAdd((unsigned long long*)d.tot_cells, (unsigned long long)nv); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K1e: read order
+// Insertion order of the stage-B read set = order of the creation triples; rank by counting.
+__global__ void k_read_rank(DB d) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < d.NR; r += (int64_t)gridDim.x * blockDim.x) {
+        if (!d.rd_pass[r]) continue;
+        const int c = d.read_chain[r];
+        const int64_t r0 = d.read_off[c], r1 = d.read_off[c + 1];
+        const uint64_t key = d.create_key[r];
+        int rank = 0;
+        for (int64_t x = r0; x < r1; x++) rank += (d.rd_pass[x] && d.create_key[x] < key) ? 1 : 0;
+        d.ord[r0 + rank] = (int32_t)(r - r0);
+        d.okey[r0 + rank] = d.rd_first[r];
+    }
+}
+
+// libstdc++ std::sort (introsort + final insertion sort) replayed move for move on (key, value)
+// pairs with a comparator that looks at the key only: ReadSet::sort() at alignmentstoreadset.cpp:297
+// (comparator on firstPosition()), and the cluster sort at :720.  SURVEY A#11, A#22.
+struct KV { int32_t* k; int32_t* v; };
+__device__ __forceinline__ void kv_swap(KV a, int x, int y) {
+    int32_t t = a.k[x]; a.k[x] = a.k[y]; a.k[y] = t; t = a.v[x]; a.v[x] = a.v[y]; a.v[y] = t;
+}
+template <bool DESC> __device__ __forceinline__ bool kv_less(int32_t x, int32_t y) { return DESC ? x > y : x < y; }
+
+template <bool DESC>
+__device__ void kv_unguarded_linear_insert(KV a, int last) {
+    int32_t vk = a.k[last], vv = a.v[last];
+    int next = last - 1;
+    while (kv_less<DESC>(vk, a.k[next])) { a.k[last] = a.k[next]; a.v[last] = a.v[next]; last = next; --next; }
+    a.k[last] = vk; a.v[last] = vv;
+}
+template <bool DESC>
+__device__ void kv_insertion_sort(KV a, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (kv_less<DESC>(a.k[i], a.k[first])) {
+            int32_t vk = a.k[i], vv = a.v[i];
+            for (int x = i; x > first; --x) { a.k[x] = a.k[x - 1]; a.v[x] = a.v[x - 1]; }
+            a.k[first] = vk; a.v[first] = vv;
+        } else kv_unguarded_linear_insert<DESC>(a, i);
+    }
+}
+// returns false if the depth limit was reached (libstdc++ switches to heapsort: not replayed)
+template <bool DESC>
+__device__ bool kv_std_sort(KV a, int n) {
+    if (n <= 1) return true;
+    int depth0 = 0; for (int m = n; m > 1; m >>= 1) depth0++;
+    depth0 *= 2;
+    int stk_first[64], stk_last[64], stk_depth[64]; int sp = 0;
+    stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = depth0; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) return false;
+            --depth;
+            // __move_median_to_first(first, first+1, mid, last-1)
+            int mid = first + (last - first) / 2, A = first + 1, Bm = mid, Cc = last - 1;
+            if (kv_less<DESC>(a.k[A], a.k[Bm])) {
+                if (kv_less<DESC>(a.k[Bm], a.k[Cc])) kv_swap(a, first, Bm);
+                else if (kv_less<DESC>(a.k[A], a.k[Cc])) kv_swap(a, first, Cc);
+                else kv_swap(a, first, A);
+            } else if (kv_less<DESC>(a.k[A], a.k[Cc])) kv_swap(a, first, A);
+            else if (kv_less<DESC>(a.k[Bm], a.k[Cc])) kv_swap(a, first, Cc);
+            else kv_swap(a, first, Bm);
+            // __unguarded_partition(first+1, last, pivot=first)
+            int lo = first + 1, hi = last;
+            const int32_t pk = a.k[first];
+            while (true) {
+                while (kv_less<DESC>(a.k[lo], pk)) ++lo;
+                --hi;
+                while (kv_less<DESC>(pk, a.k[hi])) --hi;
+                if (!(lo < hi)) break;
+                kv_swap(a, lo, hi);
+                ++lo;
+            }
+            // recurse on [cut,last), loop on [first,cut): the right part is sorted first, but the
+            // parts are disjoint, so the order of processing does not change the result
+            if (sp < 64) { stk_first[sp] = lo; stk_last[sp] = last; stk_depth[sp] = depth; ++sp; }
+            last = lo;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        kv_insertion_sort<DESC>(a, 0, 16);
+        for (int i = 16; i < n; ++i) kv_unguarded_linear_insert<DESC>(a, i);
+    } else kv_insertion_sort<DESC>(a, 0, n);
+    return true;
+}
+
+__global__ void k_chain_sort(DB d) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.C; c += gridDim.x * blockDim.x) {
+        if (d.ch_status[c] != AHS_CHAIN_OK) continue;
+        const int n = d.ch_nfinal[c];
+        if (n == 0) { d.ch_status[c] = AHS_CHAIN_EMPTY; continue; }            // :279-282
+        KV a; a.k = d.okey + d.read_off[c]; a.v = d.ord + d.read_off[c];
+        if (!kv_std_sort<false>(a, n)) d.ch_status[c] = AHS_CHAIN_SORT_FALLBACK;
+        // covered positions (ReadSet::get_positions, :317)
+    }
+}
+
+// covered positions per chain: count, then (after the host has the offsets) the compact list
+__global__ void k_count_pos(DB d) {
+    const int wpb = blockDim.x >> 5, lane = lane_id();
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < d.C; c += gridDim.x * wpb) {
+        const int64_t b0 = d.bubble_off[c];
+        const int B = (int)(d.bubble_off[c + 1] - b0);
+        int n = 0;
+        for (int b = lane; b < B; b += 32) n += d.poscov[b0 + b] ? 1 : 0;
+        n = warp_sum_i32(n);
+        if (lane == 0) d.ch_npos[c] = n;
+    }
+}
+
+__global__ void k_compact_pos(DB d) {
+    const int wpb = blockDim.x >> 5, lane = lane_id();
+    for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < d.C; c += gridDim.x * wpb) {
+        const int64_t b0 = d.bubble_off[c];
+        const int B = (int)(d.bubble_off[c + 1] - b0);
+        const bool live = d.ch_status[c] == AHS_CHAIN_OK;
+        int base = 0;
+        for (int bb = 0; bb < B; bb += 32) {
+            const int b = bb + lane;
+            const bool cov = live && b < B && d.poscov[b0 + b];
+            const unsigned m = __ballot_sync(0xffffffffu, cov);
+            if (b < B) d.pos_compact[b0 + b] = cov ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+            if (cov) d.pos[d.pos_off[c] + base + __popc(m & ((1u << lane) - 1u))] = b;
+            base += __popc(m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K1f: pack final rows
+// one warp per final read: mask row (u16 codes) -> packed 2/4-bit codes, dense by bubble id
+__global__ void __launch_bounds__(256) k_pack_rows(DB d) {
+    const int wpb = blockDim.x >> 5, lane = lane_id();
+    const int bits = d.bits, per_word = 32 / bits;
+    for (int64_t f = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); f < d.NF; f += (int64_t)gridDim.x * wpb) {
+        const int c = d.fr_chain[f];
+        const int B = (int)(d.bubble_off[c + 1] - d.bubble_off[c]);
+        const int i = (int)(f - d.frow_off[c]);
+        const int rl = d.ord[d.read_off[c] + i];
+        const int64_t r = d.read_off[c] + rl;
+        const uint16_t* mrow = d.mask + d.mrow_off[c] + (int64_t)rl * B;
+        uint32_t* row = d.codes + d.code_off[c] + (int64_t)i * d.ch_words[c];
+        const int first = d.rd_first[r], last = d.rd_last[r];
+        for (int w = first / per_word + lane; w <= last / per_word; w += 32) {
+            uint32_t word = 0;
+            for (int x = 0; x < per_word; x++) { int b = w * per_word + x; if (b < B) word |= (uint32_t)mrow[b] << (x * bits); }
+            row[w] = word;
+        }
+        if (lane == 0) {
+            d.fr_first[f] = first; d.fr_last[f] = last; d.fr_mapq[f] = d.rd_mapq[r]; d.fr_id[f] = rl; d.fr_nv[f] = d.rd_nv[r];
+            atomicMax(&d.ch_maxspan[c], last - first);
+        }
+    }
+}
+
+}  // namespace ahs

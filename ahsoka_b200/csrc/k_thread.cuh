@@ -1,0 +1,265 @@
+// k_thread.cuh — per-position cluster coverage / consensus (K3), haplotype threading DP (K4) and
+// the CSR result writers.
+//
+// K3 replaces get_coverage (:660-697), get_pos_to_clusters_map (:751-779),
+// get_local_cluster_consensus / get_single_cluster_consensus_frac (:550-655) and the re-packing at
+// :378-404 of reference src/alignmentstoreadset.cpp — including the fact that the coverage and
+// consensus vectors handed to the threader are in ascending-cluster-id order while covMap is in
+// descending-coverage order (SURVEY A#12).  Coverage is kept as (count, total): every comparison
+// the reference makes on count/total doubles is decided identically by the integer cross product.
+//
+// K4 replaces HaploThreader(2,32.0,8.0,false,0).computePaths (:320,:408; algorithm:
+// oracle/core/phase_core.hpp rule R3).  The transition cost 32*(#switched haplotypes) is separable
+// over haplotypes, so the min over predecessors is taken one tuple coordinate at a time (least
+// significant first, ties -> smallest predecessor digit), which yields exactly the minimum and
+// the lowest-code argmin of the all-pairs definition; the affine 8 is applied afterwards against
+// the unique zero-switch predecessor.  Costs are integers.
+#pragma once
+#include "common.cuh"
+#include "device_batch.cuh"
+#include "k_project.cuh"
+
+namespace ahs {
+
+constexpr int K3_CAP = 128;      // clusters per position held in shared memory
+
+template <int BITS>
+__global__ void __launch_bounds__(128) k_consensus(DB d) {
+    __shared__ int32_t s_id[4][K3_CAP], s_cnt[4][K3_CAP], s_key[4][K3_CAP], s_idx[4][K3_CAP];
+    __shared__ uint8_t s_cons[4][K3_CAP];
+    const int wpb = blockDim.x >> 5, lane = lane_id(), wib = threadIdx.x >> 5;
+    const int p = d.ploidy;
+    for (int64_t gp = blockIdx.x * (int64_t)wpb + wib; gp < d.NP; gp += (int64_t)gridDim.x * wpb) {
+        const int c = d.pos_chain[gp];
+        const int b = d.pos[gp];
+        const int64_t f0 = d.frow_off[c];
+        const int n_c = (int)(d.frow_off[c + 1] - f0);
+        const int32_t* first = d.fr_first + f0; const int32_t* lastp = d.fr_last + f0; const int32_t* cl = d.fr_cluster + f0;
+        const int words = d.ch_words[c];
+        const uint32_t* rows = d.codes + d.code_off[c];
+        const int64_t gb = d.bubble_off[c] + b;
+        const int K = (int)(d.allele_off[gb + 1] - d.allele_off[gb]);
+        // candidate band: first <= b and first >= b - maxspan
+        int lo, hi;
+        { int x = -1, y = n_c; while (x + 1 < y) { int m = (x + y) >> 1; if (first[m] <= b) x = m; else y = m; } hi = x;
+          const int bound = b - d.ch_maxspan[c]; x = -1; y = n_c; while (x + 1 < y) { int m = (x + y) >> 1; if (first[m] >= bound) y = m; else x = m; } lo = y; }
+        int cur = -1, ncl = 0; uint32_t total = 0; bool overflow = false;
+        while (true) {
+            int nxt = INT32_MAX;
+            for (int i = lo + lane; i <= hi; i += 32)
+                if (lastp[i] >= b && cl[i] > cur && get_code(rows + (int64_t)i * words, b, BITS)) nxt = min(nxt, cl[i]);
+            nxt = warp_min_i32(nxt);
+            if (nxt == INT32_MAX) break;
+            uint32_t ac[MAX_ALLELES];
+#pragma unroll
+            for (int a = 0; a < MAX_ALLELES; a++) ac[a] = 0;
+            for (int i = lo + lane; i <= hi; i += 32)
+                if (lastp[i] >= b && cl[i] == nxt) {
+                    const uint32_t code = get_code(rows + (int64_t)i * words, b, BITS);
+#pragma unroll
+                    for (int a = 0; a < MAX_ALLELES; a++) ac[a] += (code == (uint32_t)(a + 1)) ? 1u : 0u;
+                }
+            uint32_t cnt = 0, best = 0; int cons = 0;
+#pragma unroll
+            for (int a = 0; a < MAX_ALLELES; a++) if (a < K) {
+                const uint32_t v = (uint32_t)warp_sum_i32((int)ac[a]);
+                cnt += v;
+                if (v > best) { best = v; cons = a; }               // ties -> smallest allele (:633-649, A#13)
+            }
+            if (ncl < K3_CAP) { if (lane == 0) { s_id[wib][ncl] = nxt; s_cnt[wib][ncl] = (int32_t)cnt; s_cons[wib][ncl] = (uint8_t)cons; } }
+            else overflow = true;
+            ncl++; total += cnt; cur = nxt;
+        }
+        __syncwarp();
+        if (overflow) { if (lane == 0) atomicMax(&d.ch_status[c], AHS_CHAIN_TOO_LARGE); continue; }
+        if (lane == 0) {
+            PosRec r;
+            r.total = total; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+            for (int x = 0; x < ncl; x++) { s_key[wib][x] = s_cnt[wib][x]; s_idx[wib][x] = x; }
+            KV kv; kv.k = s_key[wib]; kv.v = s_idx[wib];
+            kv_std_sort<true>(kv, ncl);                            // std::sort(A, cmp) on coverage, descending (:720)
+            int k = min(ncl, 2 * p);
+            for (int i = p; i < min(ncl, 2 * p); i++)
+                if ((uint64_t)s_cnt[wib][s_idx[wib][i]] * (uint64_t)(8 * p) < (uint64_t)total) { k = i; break; }   // cov < 1/(8p), :768
+            r.k = (uint8_t)k;
+            int sel[MAX_K];
+            for (int l = 0; l < MAX_K; l++) { r.gid[l] = -1; r.cnt_asc[l] = 0; r.cons_asc[l] = 0; r.cons_cm[l] = 0; }
+            for (int l = 0; l < k; l++) { sel[l] = s_idx[wib][l]; r.gid[l] = s_id[wib][sel[l]]; r.cons_cm[l] = s_cons[wib][sel[l]]; r.cnt_asc[l] = (uint32_t)s_cnt[wib][l]; }
+            for (int x = 1; x < k; x++) { int v = sel[x], y = x - 1; while (y >= 0 && sel[y] > v) { sel[y + 1] = sel[y]; y--; } sel[y + 1] = v; }
+            for (int l = 0; l < k; l++) r.cons_asc[l] = s_cons[wib][sel[l]];
+            d.rec[gp] = r;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- K4: threading DP, one block per chain
+constexpr int DP_THREADS = 128;
+
+__device__ __forceinline__ int ipow(int b, int e) { int r = 1; for (int i = 0; i < e; i++) r *= b; return r; }
+
+__global__ void __launch_bounds__(DP_THREADS) k_thread(DB d, int32_t* __restrict__ work_counter) {
+    extern __shared__ int32_t smem[];
+    const int SM = d.S_max, p = d.ploidy;
+    int32_t* Dprev = smem; int32_t* Dcur = smem + SM; int32_t* Xa = smem + 2 * SM; int32_t* Xb = smem + 3 * SM;
+    uint16_t* Aa = (uint16_t*)(smem + 4 * SM); uint16_t* Ab = Aa + SM;
+    int8_t* cc = (int8_t*)(Ab + SM);                    // covcost, -1 = not genotype conform
+    __shared__ PosRec s_rec[2];
+    __shared__ int s_chain;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    while (true) {
+        if (tid == 0) s_chain = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int c = s_chain;
+        __syncthreads();
+        if (c >= d.C) break;
+        if (d.ch_status[c] != AHS_CHAIN_OK) continue;
+        const int64_t p0 = d.pos_off[c];
+        const int n_pos = (int)(d.pos_off[c + 1] - p0);
+        if (n_pos == 0) continue;
+        uint16_t* back = d.back + d.back_off[c];
+        int kp = 0;
+        for (int q = 0; q < n_pos; q++) {
+            if (tid == 0) s_rec[q & 1] = d.rec[p0 + q];
+            __syncthreads();
+            const PosRec& R = s_rec[q & 1];
+            const PosRec& Rp = s_rec[(q & 1) ^ 1];
+            const int kc = R.k;
+            const int S = ipow(kc, p);
+            // ---- per-tuple genotype conformity and coverage cost
+            int any = 0;
+            for (int t = tid; t < S; t += nt) {
+                int dig[MAX_PLOIDY]; { int x = t; for (int h = p - 1; h >= 0; h--) { dig[h] = x % kc; x /= kc; } }
+                bool conform;
+                if (p == 2) { const int a0 = R.cons_asc[dig[0]], a1 = R.cons_asc[dig[1]]; conform = (a0 == 0 && a1 == 1) || (a0 == 1 && a1 == 0); }
+                else { conform = false; for (int h = 1; h < p; h++) conform |= R.cons_asc[dig[h]] != R.cons_asc[dig[0]]; }
+                int cost = 0;
+                for (int h = 0; h < p; h++) {
+                    int m = 0; for (int g = 0; g < p; g++) m += dig[g] == dig[h];
+                    const uint64_t lhs = (uint64_t)R.cnt_asc[dig[h]] * (uint64_t)(2 * p);
+                    if (lhs < (uint64_t)(2 * m - 1) * R.total || lhs > (uint64_t)(2 * m + 1) * R.total) cost++;
+                }
+                cc[t] = conform ? (int8_t)cost : (int8_t)(-1 - cost);
+                any |= conform;
+            }
+            any = __syncthreads_or(any);
+            if (q == 0) {
+                for (int t = tid; t < S; t += nt) { const int v = cc[t]; Dcur[t] = (v >= 0) ? v : (any ? DP_INF : (-1 - v)); }
+            } else {
+                // ---- factorised min over predecessors
+                const int Sp = ipow(kp, p);
+                for (int t = tid; t < Sp; t += nt) { Xa[t] = Dprev[t]; Aa[t] = 0; }
+                __syncthreads();
+                int32_t* Xin = Xa; int32_t* Xout = Xb; uint16_t* Ain = Aa; uint16_t* Aout = Ab;
+                for (int h = p - 1; h >= 0; h--) {
+                    const int lowsz = ipow(kc, p - 1 - h), highsz = ipow(kp, h), wpred = ipow(kp, p - 1 - h);
+                    const int n_out = highsz * kc * lowsz;
+                    for (int o = tid; o < n_out; o += nt) {
+                        const int low = o % lowsz, rest = o / lowsz, th = rest % kc, high = rest / kc;
+                        const int gcur = R.gid[th];
+                        int best = INT32_MAX, barg = 0;
+                        for (int sh = 0; sh < kp; sh++) {
+                            const int in = (high * kp + sh) * lowsz + low;
+                            const int v = Xin[in] + (Rp.gid[sh] != gcur ? 32 : 0);
+                            if (v < best) { best = v; barg = Ain[in] + sh * wpred; }
+                        }
+                        Xout[o] = best; Aout[o] = (uint16_t)barg;
+                    }
+                    __syncthreads();
+                    int32_t* tx = Xin; Xin = Xout; Xout = tx; uint16_t* ta = Ain; Ain = Aout; Aout = ta;
+                }
+                // ---- affine part and zero-switch predecessor
+                for (int t = tid; t < S; t += nt) {
+                    int dig[MAX_PLOIDY]; { int x = t; for (int h = p - 1; h >= 0; h--) { dig[h] = x % kc; x /= kc; } }
+                    int val = Xin[t]; int pred = Ain[t];
+                    int sw = 0; { int x = pred; for (int h = p - 1; h >= 0; h--) { const int sh = x % kp; x /= kp; sw += Rp.gid[sh] != R.gid[dig[h]]; } }
+                    if (sw) {
+                        val += 8;
+                        int sstar = 0; bool ok = true;
+                        for (int h = 0; h < p; h++) {
+                            int l = -1; for (int x = 0; x < kp; x++) if (Rp.gid[x] == R.gid[dig[h]]) l = x;
+                            if (l < 0) { ok = false; break; }
+                            sstar = sstar * kp + l;
+                        }
+                        if (ok) { const int v2 = Dprev[sstar]; if (v2 < val || (v2 == val && sstar < pred)) { val = v2; pred = sstar; } }
+                    }
+                    const int v = cc[t];
+                    const bool allowed = (v >= 0) || !any;
+                    const int cost = v >= 0 ? v : (-1 - v);
+                    Dcur[t] = allowed ? min(val + cost, DP_INF) : DP_INF;
+                    back[(int64_t)q * SM + t] = (uint16_t)pred;
+                }
+            }
+            __syncthreads();
+            { int32_t* tx = Dprev; Dprev = Dcur; Dcur = tx; }
+            kp = kc;
+        }
+        // ---- final minimum (lowest code) and backtrace
+        if (tid == 0) {
+            const int S = ipow(kp, p);
+            int best = INT32_MAX, cur = 0;
+            for (int t = 0; t < S; t++) if (Dprev[t] < best) { best = Dprev[t]; cur = t; }
+            d.dp_cost[c] = (double)best;
+            for (int q = n_pos - 1; q >= 0; q--) {
+                const PosRec& R = d.rec[p0 + q];
+                const int kc = R.k;
+                int x = cur;
+                for (int h = p - 1; h >= 0; h--) {
+                    const int dg = x % kc; x /= kc;
+                    d.path[(p0 + q) * p + h] = R.gid[dg];
+                    d.hap_allele[(p0 + q) * p + h] = R.cons_cm[dg];
+                }
+                if (q > 0) cur = back[(int64_t)q * SM + cur];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- CSR cells of the final matrix
+template <int BITS>
+__global__ void __launch_bounds__(256) k_write_cells(DB d) {
+    const int wpb = blockDim.x >> 5, lane = lane_id();
+    for (int64_t f = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); f < d.NF; f += (int64_t)gridDim.x * wpb) {
+        const int c = d.fr_chain[f];
+        const int i = (int)(f - d.frow_off[c]);
+        const uint32_t* row = d.codes + d.code_off[c] + (int64_t)i * d.ch_words[c];
+        const int first = d.fr_first[f], last = d.fr_last[f];
+        int64_t base = d.cell_off[f];
+        for (int bb = first; bb <= last; bb += 32) {
+            const int b = bb + lane;
+            const uint32_t code = b <= last ? get_code(row, b, BITS) : 0u;
+            const unsigned m = __ballot_sync(0xffffffffu, code != 0);
+            if (code) { const int64_t o = base + __popc(m & ((1u << lane) - 1u)); d.cell_pos[o] = b; d.cell_allele[o] = (uint8_t)(code - 1); }
+            base += __popc(m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- exclusive scan (int32 -> int64), three launches
+constexpr int SCAN_BLOCK = 1024;
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_local(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out, int64_t* __restrict__ block_sum) {
+    __shared__ int64_t s[SCAN_BLOCK];
+    const int64_t x = blockIdx.x * (int64_t)SCAN_BLOCK + threadIdx.x;
+    const int64_t v = x < n ? in[x] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        int64_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (x < n) out[x] = s[threadIdx.x] - v;
+    if (threadIdx.x == SCAN_BLOCK - 1) block_sum[blockIdx.x] = s[threadIdx.x];
+}
+__global__ void k_scan_blocks(int64_t* block_sum, int64_t nb, int64_t* total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { int64_t acc = 0; for (int64_t x = 0; x < nb; x++) { int64_t v = block_sum[x]; block_sum[x] = acc; acc += v; } *total = acc; }
+}
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(int64_t* out, int64_t n, const int64_t* __restrict__ block_sum, const int64_t* __restrict__ total) {
+    const int64_t x = blockIdx.x * (int64_t)SCAN_BLOCK + threadIdx.x;
+    if (x < n) out[x] += block_sum[blockIdx.x];
+    if (x == 0) out[n] = *total;
+}
+
+}  // namespace ahs

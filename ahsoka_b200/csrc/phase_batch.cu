@@ -1,0 +1,579 @@
+// phase_batch.cu — host side of the C ABI (include/ahsoka_b200.h): uploads the CSR batch, runs the
+// sm_100a kernels of k_project / k_score / k_cluster / k_thread on one stream, downloads the
+// result.  No torch, no CPU fallback: without a usable CUDA device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "device_batch.cuh"
+#include "k_project.cuh"
+#include "k_score.cuh"
+#include "k_cluster.cuh"
+#include "k_thread.cuh"
+
+namespace ahs {
+
+static thread_local char g_err[512] = "";
+static void set_err(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
+
+struct CudaFail { cudaError_t e; const char* what; int line; };
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) throw CudaFail{_e, #call, __LINE__}; } while (0)
+struct LimitFail { std::string msg; };
+struct ArgFail { std::string msg; };
+
+constexpr int MAX_READS_CLUSTER = 8192;
+constexpr int MAX_POSITIONS = 32767;
+
+// ------------------------------------------------------------------ memory pools (persist per device)
+struct Pool {
+    struct Chunk { char* p; size_t cap, used; };
+    std::vector<Chunk> chunks; bool host;
+    explicit Pool(bool h) : host(h) {}
+    void reset() { for (auto& c : chunks) c.used = 0; }
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        for (auto& c : chunks) if (c.cap - c.used >= bytes) { void* r = c.p + c.used; c.used += bytes; return r; }
+        size_t cap = std::max(bytes, (size_t)(host ? 64 : 256) << 20);
+        Chunk c; c.cap = cap; c.used = bytes;
+        if (host) CK(cudaHostAlloc((void**)&c.p, cap, cudaHostAllocDefault)); else CK(cudaMalloc((void**)&c.p, cap));
+        chunks.push_back(c);
+        return c.p;
+    }
+    template <class T> T* get(size_t n) { return (T*)alloc(n * sizeof(T)); }
+    void release() { for (auto& c : chunks) { if (host) cudaFreeHost(c.p); else cudaFree(c.p); } chunks.clear(); }
+};
+
+struct Ctx {
+    int device = -1; cudaStream_t stream = nullptr; Pool dev{false}, pin{true}, outp{true};
+    int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
+    cudaEvent_t ev[10];
+    std::mutex mu;
+};
+static std::mutex g_ctx_mu;
+static Ctx* g_ctx[64] = {nullptr};
+
+static Ctx* get_ctx(int device) {
+    std::lock_guard<std::mutex> g(g_ctx_mu);
+    if (device < 0 || device >= 64) throw ArgFail{"device ordinal out of range"};
+    if (g_ctx[device]) return g_ctx[device];
+    int n = 0; CK(cudaGetDeviceCount(&n));
+    if (device >= n) throw ArgFail{"no such CUDA device"};
+    CK(cudaSetDevice(device));
+    Ctx* c = new Ctx(); c->device = device;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sms = prop.multiProcessorCount;
+    // fixed-point log tables of rule R1 (oracle/core/phase_core.hpp): llrint(ln(x/1024) * 2^20)
+    std::vector<int64_t> ln(1025, 0), ln1(1025, 0);
+    for (int x = 0; x <= 1024; x++) {
+        if (x >= 1) ln[x] = llrint(std::log((double)x / 1024.0) * 1048576.0);
+        if (x <= 1023) ln1[x] = llrint(std::log(1.0 - (double)x / 1024.0) * 1048576.0);
+    }
+    CK(cudaMalloc(&c->d_ln, 1025 * 8)); CK(cudaMalloc(&c->d_ln1, 1025 * 8));
+    CK(cudaMemcpy(c->d_ln, ln.data(), 1025 * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_ln1, ln1.data(), 1025 * 8, cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * 4096 + 64));
+    g_ctx[device] = c;
+    return c;
+}
+
+// ------------------------------------------------------------------ validation
+struct Sizes { int64_t C, NB, NA, NAN_, NR, NE, NEN, M; int max_k; };
+
+static Sizes validate(const ahs_batch_in* in) {
+    if (!in) throw ArgFail{"null batch"};
+    if (in->n_chains < 0) throw ArgFail{"n_chains < 0"};
+    if (in->ploidy < 1 || in->ploidy > MAX_PLOIDY) throw LimitFail{"ploidy outside [1," + std::to_string(MAX_PLOIDY) + "]"};
+    Sizes s{}; s.C = in->n_chains;
+    if (s.C == 0) return s;
+    auto mono = [&](const int64_t* off, int64_t n, const char* name) {
+        if (!off) throw ArgFail{std::string(name) + " is null"};
+        if (off[0] != 0) throw ArgFail{std::string(name) + "[0] != 0"};
+        for (int64_t i = 0; i < n; i++) if (off[i + 1] < off[i]) throw ArgFail{std::string(name) + " not monotone"};
+    };
+    mono(in->bubble_off, s.C, "bubble_off"); s.NB = in->bubble_off[s.C];
+    mono(in->allele_off, s.NB, "allele_off"); s.NA = in->allele_off[s.NB];
+    mono(in->anode_off, s.NA, "anode_off"); s.NAN_ = in->anode_off[s.NA];
+    mono(in->read_off, s.C, "read_off"); s.NR = in->read_off[s.C];
+    mono(in->entry_off, s.C, "entry_off"); s.NE = in->entry_off[s.C];
+    mono(in->enode_off, s.NE, "enode_off"); s.NEN = in->enode_off[s.NE];
+    s.max_k = 0;
+    for (int64_t b = 0; b < s.NB; b++) s.max_k = std::max<int>(s.max_k, (int)(in->allele_off[b + 1] - in->allele_off[b]));
+    if (s.max_k > MAX_ALLELES) throw LimitFail{"a bubble has more than 15 alleles"};
+    for (int64_t a = 0; a < s.NA; a++) if (in->anode_off[a + 1] == in->anode_off[a]) throw ArgFail{"empty allele path"};
+    for (int64_t c = 0; c < s.C; c++) {
+        const int64_t B = in->bubble_off[c + 1] - in->bubble_off[c], R = in->read_off[c + 1] - in->read_off[c];
+        if (B > MAX_POSITIONS) throw LimitFail{"chain with more than 32767 bubbles"};
+        const int64_t e0 = in->entry_off[c], e1 = in->entry_off[c + 1];
+        for (int64_t e = e0; e < e1; e++) if (in->entry_read[e] < 0 || in->entry_read[e] >= R) throw ArgFail{"entry_read out of range"};
+        if (in->stage_a_order) {
+            std::vector<char> seen(B, 0);
+            for (int64_t b = 0; b < B; b++) { int32_t v = in->stage_a_order[in->bubble_off[c] + b]; if (v < 0 || v >= B || seen[v]) throw ArgFail{"stage_a_order is not a permutation"}; seen[v] = 1; }
+        }
+        s.M += (B > 1) ? B * R : 0;
+    }
+    return s;
+}
+
+static inline int grid_for(int64_t items, int per_block, int sms) {
+    int64_t g = (items + per_block - 1) / per_block;
+    int64_t cap = (int64_t)sms * 16;
+    return (int)std::max<int64_t>(1, std::min(g, cap));
+}
+
+// ------------------------------------------------------------------ the pipeline
+struct Pipeline {
+    Ctx* cx; const ahs_batch_in* in; Sizes sz; DB d{};
+    std::vector<int64_t> h_mrow_off, h_frow_off, h_pos_off, h_code_off, h_cw_off, h_back_off;
+    std::vector<int32_t> h_status, h_nfinal, h_npos, h_words;
+    int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0;
+    float ms[8] = {0};
+
+    template <class T> const T* up(const T* h, int64_t n) {
+        T* p = cx->dev.get<T>((size_t)std::max<int64_t>(n, 1));
+        if (n > 0) CK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, cx->stream));
+        return p;
+    }
+    template <class T> T* dalloc(int64_t n) { return cx->dev.get<T>((size_t)std::max<int64_t>(n, 1)); }
+    template <class T> T* dzero(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0, std::max<int64_t>(n, 1) * sizeof(T), cx->stream)); return p; }
+    template <class T> T* dfill_ff(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0xff, std::max<int64_t>(n, 1) * sizeof(T), cx->stream)); return p; }
+
+    void upload() {
+        cudaStream_t st = cx->stream;
+        const int64_t C = sz.C;
+        d.C = (int32_t)C; d.ploidy = in->ploidy; d.bits = sz.max_k <= 3 ? 2 : 4;
+        d.NB = sz.NB; d.NA = sz.NA; d.NAN_ = sz.NAN_; d.NR = sz.NR; d.NE = sz.NE; d.NEN = sz.NEN;
+        d.bubble_off = up(in->bubble_off, C + 1); d.allele_off = up(in->allele_off, sz.NB + 1); d.anode_off = up(in->anode_off, sz.NA + 1);
+        d.read_off = up(in->read_off, C + 1); d.entry_off = up(in->entry_off, C + 1); d.enode_off = up(in->enode_off, sz.NE + 1);
+        d.anode = up(in->anode, sz.NAN_); d.enode = up(in->enode, sz.NEN); d.entry_read = up(in->entry_read, sz.NE);
+        d.entry_identity = up(in->entry_identity, sz.NE);
+        d.stage_a_order = in->stage_a_order ? up(in->stage_a_order, sz.NB) : nullptr;
+        h_mrow_off.assign(C, 0);
+        int64_t acc = 0;
+        for (int64_t c = 0; c < C; c++) {
+            h_mrow_off[c] = acc;
+            const int64_t B = in->bubble_off[c + 1] - in->bubble_off[c], R = in->read_off[c + 1] - in->read_off[c];
+            if (B > 1) acc += B * R;
+            if (acc & 1) acc++;                                    // keep chain bases 4-byte aligned for the 32-bit atomics
+        }
+        sz.M = acc;
+        d.mrow_off = (int64_t*)up(h_mrow_off.data(), C);
+        (void)st;
+    }
+
+    // allocate and initialise everything phase 1 writes; called once per run (also per resident iteration)
+    void alloc_phase1() {
+        const int64_t C = sz.C;
+        d.bubble_chain = dalloc<int32_t>(sz.NB); d.allele_bubble = dalloc<int32_t>(sz.NA); d.entry_chain = dalloc<int32_t>(sz.NE);
+        d.read_chain = dalloc<int32_t>(sz.NR); d.rankA = dalloc<int32_t>(sz.NB);
+        uint64_t ts = 1024; while ((int64_t)ts < 2 * sz.NA) ts <<= 1;
+        d.hmask = (uint32_t)(ts - 1);
+        d.hkeys = dalloc<uint64_t>((int64_t)ts); d.hhead = dalloc<int32_t>((int64_t)ts); d.inc_next = dalloc<int32_t>(sz.NA);
+        d.bubble_univ = dalloc<uint32_t>(sz.NB);
+        d.mask = dalloc<uint16_t>(sz.M + 2);
+        d.create_key = dalloc<uint64_t>(sz.NR); d.createA_key = dalloc<uint64_t>(sz.NR); d.first_entry = dalloc<uint32_t>(sz.NR);
+        d.has_good = dalloc<uint8_t>(sz.NR);
+        d.rdA_cnt = dalloc<int32_t>(sz.NR); d.rdA_first = dalloc<int32_t>(sz.NR); d.rdA_last = dalloc<int32_t>(sz.NR); d.rdA_mapq = dalloc<int32_t>(sz.NR);
+        d.rd_nv = dalloc<int32_t>(sz.NR); d.rd_first = dalloc<int32_t>(sz.NR); d.rd_last = dalloc<int32_t>(sz.NR); d.rd_mapq = dalloc<int32_t>(sz.NR);
+        d.rd_pass = dalloc<uint8_t>(sz.NR); d.ord = dalloc<int32_t>(sz.NR); d.okey = dalloc<int32_t>(sz.NR);
+        d.poscov = dalloc<uint8_t>(sz.NB); d.pos_compact = dalloc<int32_t>(sz.NB);
+        d.ch_status = dalloc<int32_t>(C); d.ch_maxpos = dalloc<int32_t>(C); d.ch_flags = dalloc<int32_t>(C); d.ch_T = dalloc<int32_t>(C);
+        d.ch_nfinal = dalloc<int32_t>(C); d.ch_npos = dalloc<int32_t>(C); d.ch_maxspan = dalloc<int32_t>(C); d.ch_words = dalloc<int32_t>(C);
+        d.ch_nclusters = dalloc<int32_t>(C);
+        d.tot_cells = dalloc<int64_t>(1); d.tot_pairs = dalloc<int64_t>(1); d.err_flags = dalloc<int32_t>(1);
+        d.ln = cx->d_ln; d.ln1 = cx->d_ln1;
+    }
+
+    void init_phase1() {
+        cudaStream_t st = cx->stream; const int64_t C = sz.C;
+        CK(cudaMemsetAsync(d.hkeys, 0xff, ((size_t)d.hmask + 1) * 8, st)); CK(cudaMemsetAsync(d.hhead, 0xff, ((size_t)d.hmask + 1) * 4, st));
+        CK(cudaMemsetAsync(d.bubble_univ, 0xff, std::max<int64_t>(sz.NB, 1) * 4, st));
+        CK(cudaMemsetAsync(d.mask, 0, (sz.M + 2) * 2, st));
+        CK(cudaMemsetAsync(d.create_key, 0xff, std::max<int64_t>(sz.NR, 1) * 8, st)); CK(cudaMemsetAsync(d.createA_key, 0xff, std::max<int64_t>(sz.NR, 1) * 8, st));
+        CK(cudaMemsetAsync(d.first_entry, 0xff, std::max<int64_t>(sz.NR, 1) * 4, st)); CK(cudaMemsetAsync(d.has_good, 0, std::max<int64_t>(sz.NR, 1), st));
+        CK(cudaMemsetAsync(d.poscov, 0, std::max<int64_t>(sz.NB, 1), st));
+        CK(cudaMemsetAsync(d.ch_status, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxpos, 0xff, C * 4, st)); CK(cudaMemsetAsync(d.ch_flags, 0, C * 4, st));
+        CK(cudaMemsetAsync(d.ch_nfinal, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxspan, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_nclusters, 0, C * 4, st));
+        CK(cudaMemsetAsync(d.tot_cells, 0, 8, st)); CK(cudaMemsetAsync(d.tot_pairs, 0, 8, st)); CK(cudaMemsetAsync(d.err_flags, 0, 4, st));
+    }
+
+    void scan(const int32_t* in32, int64_t n, int64_t* out) {       // out[n+1]
+        cudaStream_t st = cx->stream;
+        const int64_t nb = std::max<int64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+        int64_t* bs = dalloc<int64_t>(nb + 1);
+        k_scan_local<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(in32, n, out, bs);
+        k_scan_blocks<<<1, 32, 0, st>>>(bs, nb, bs + nb);
+        k_scan_add<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(out, n, bs, bs + nb);
+        CK(cudaGetLastError());
+    }
+
+    template <int BITS> void run_bits() {
+        cudaStream_t st = cx->stream; const int sms = cx->sms; const int64_t C = sz.C;
+        const int TB = 256;
+        CK(cudaEventRecord(cx->ev[0], st));
+        init_phase1();
+        // ---- owner maps + trigger table
+        if (sz.NB) k_owner<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d.bubble_off, (int)C, sz.NB, d.bubble_chain);
+        if (sz.NA) k_owner<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d.allele_off, (int)sz.NB, sz.NA, d.allele_bubble);
+        if (sz.NE) k_owner<<<grid_for(sz.NE, TB, sms), TB, 0, st>>>(d.entry_off, (int)C, sz.NE, d.entry_chain);
+        if (sz.NR) k_owner<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d.read_off, (int)C, sz.NR, d.read_chain);
+        if (sz.NB) k_rank_a<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d);
+        if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d);
+        // ---- projection
+        if (sz.NE) k_project<<<grid_for(sz.NE, 8, sms), TB, 0, st>>>(d);
+        CK(cudaEventRecord(cx->ev[1], st));
+        if (sz.NR) k_read_stage_a<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d);
+        if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d);
+        k_chain_T<<<grid_for(C, TB, sms), TB, 0, st>>>(d);
+        if (sz.NR) k_read_rows<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d);
+        if (sz.NR) k_read_rank<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d);
+        k_chain_sort<<<grid_for(C, 64, sms), 64, 0, st>>>(d);
+        k_count_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d);
+        CK(cudaGetLastError());
+        // ---- sync #1: per-chain sizes -> offsets of the per-chain workspaces
+        h_status.resize(C); h_nfinal.resize(C); h_npos.resize(C);
+        int32_t h_err = 0;
+        CK(cudaMemcpyAsync(h_status.data(), d.ch_status, C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_nfinal.data(), d.ch_nfinal, C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_npos.data(), d.ch_npos, C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_tot_cells, d.tot_cells, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_err, d.err_flags, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_err & 1) throw ArgFail{"empty allele path"};
+        if (h_err & 2) throw LimitFail{"a bubble has more than 15 alleles"};
+        h_frow_off.assign(C + 1, 0); h_pos_off.assign(C + 1, 0); h_code_off.assign(C, 0); h_cw_off.assign(C, 0); h_back_off.assign(C, 0); h_words.assign(C, 0);
+        const int per_word = 32 / BITS;
+        int64_t S_max = 1; for (int i = 0; i < in->ploidy; i++) S_max *= 2 * in->ploidy;
+        d.S_max = (int32_t)S_max;
+        n_code_words = 0; n_cw = 0;
+        bool status_changed = false;
+        for (int64_t c = 0; c < C; c++) {
+            if (h_status[c] == AHS_CHAIN_OK && h_nfinal[c] > MAX_READS_CLUSTER) { h_status[c] = AHS_CHAIN_TOO_LARGE; status_changed = true; }
+            const bool ok = h_status[c] == AHS_CHAIN_OK;
+            const int64_t n = ok ? h_nfinal[c] : 0, np = ok ? h_npos[c] : 0;
+            const int64_t B = in->bubble_off[c + 1] - in->bubble_off[c];
+            h_words[c] = (int32_t)((B + per_word - 1) / per_word);
+            h_frow_off[c + 1] = h_frow_off[c] + n; h_pos_off[c + 1] = h_pos_off[c] + np;
+            h_code_off[c] = n_code_words; n_code_words += n * h_words[c];
+            h_cw_off[c] = n_cw; n_cw += n * n;
+            h_back_off[c] = h_pos_off[c] * S_max;
+        }
+        const int64_t NF = h_frow_off[C], NP = h_pos_off[C];
+        d.NF = NF; d.NP = NP;
+        if (status_changed) CK(cudaMemcpyAsync(d.ch_status, h_status.data(), C * 4, cudaMemcpyHostToDevice, st));
+        d.frow_off = (int64_t*)up(h_frow_off.data(), C + 1); d.pos_off = (int64_t*)up(h_pos_off.data(), C + 1);
+        d.code_off = (int64_t*)up(h_code_off.data(), C); d.cw_off = (int64_t*)up(h_cw_off.data(), C); d.back_off = (int64_t*)up(h_back_off.data(), C);
+        CK(cudaMemcpyAsync(d.ch_words, h_words.data(), C * 4, cudaMemcpyHostToDevice, st));
+        d.fr_chain = dalloc<int32_t>(NF); d.fr_first = dalloc<int32_t>(NF); d.fr_last = dalloc<int32_t>(NF); d.fr_mapq = dalloc<int32_t>(NF);
+        d.fr_id = dalloc<int32_t>(NF); d.fr_nv = dalloc<int32_t>(NF); d.fr_cluster = dzero<int32_t>(NF);
+        d.codes = dzero<uint32_t>(n_code_words);
+        d.pos = dalloc<int32_t>(NP); d.pos_chain = dalloc<int32_t>(NP);
+        d.es = dalloc<uint16_t>(NF); d.ed = dalloc<uint16_t>(NF);
+        d.W = dzero<int32_t>(n_cw); d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw);
+        d.ce_active = dalloc<uint8_t>(NF); d.ce_dirty = dalloc<uint8_t>(NF); d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
+        d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
+        d.rec = dalloc<PosRec>(NP); d.back = dalloc<uint16_t>(NP * S_max);
+        d.path = dzero<int32_t>(NP * in->ploidy); d.hap_allele = dzero<uint8_t>(NP * in->ploidy); d.dp_cost = dzero<double>(C);
+        d.cell_off = dalloc<int64_t>(NF + 1); d.cell_pos = dalloc<int32_t>(h_tot_cells); d.cell_allele = dalloc<uint8_t>(h_tot_cells);
+        int32_t* counters = dzero<int32_t>(4);
+        if (NF) k_owner<<<grid_for(NF, TB, sms), TB, 0, st>>>(d.frow_off, (int)C, NF, d.fr_chain);
+        if (NP) k_owner<<<grid_for(NP, TB, sms), TB, 0, st>>>(d.pos_off, (int)C, NP, d.pos_chain);
+        if (NF) k_pack_rows<<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
+        k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d);
+        CK(cudaEventRecord(cx->ev[2], st));
+        // ---- scoring.  Reads with more than RATE_SMEM_KEYS candidate partners sort in HBM scratch.
+        {
+            // upper bound per read = chain size; only chains above the shared-memory capacity get scratch
+            std::vector<int64_t> koff(NF + 1, 0);
+            int64_t tot = 0; bool any = false;
+            for (int64_t c = 0; c < C; c++) {
+                const int64_t n = h_frow_off[c + 1] - h_frow_off[c];
+                int64_t cap = 0;
+                if (n > RATE_SMEM_KEYS) { cap = 1; while (cap < n) cap <<= 1; any = true; }
+                for (int64_t i = 0; i < n; i++) { koff[h_frow_off[c] + i] = tot; tot += cap; }
+            }
+            koff[NF] = tot;
+            if (any) { d.key_scratch = dalloc<uint64_t>(tot); d.key_scratch_off = (int64_t*)up(koff.data(), NF + 1); }
+            else { d.key_scratch = nullptr; d.key_scratch_off = nullptr; }
+        }
+        if (NF) k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
+        if (NF) k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
+        CK(cudaEventRecord(cx->ev[3], st));
+        // ---- cluster editing
+        if (NF) k_cluster_edit<<<std::min<int64_t>(C, (int64_t)sms * 8), CE_THREADS, 0, st>>>(d, counters);
+        CK(cudaEventRecord(cx->ev[4], st));
+        // ---- coverage / consensus, threading
+        if (NP) k_consensus<BITS><<<grid_for(NP, 4, sms), 128, 0, st>>>(d);
+        CK(cudaEventRecord(cx->ev[5], st));
+        if (NP) k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1);
+        CK(cudaEventRecord(cx->ev[6], st));
+        // ---- CSR cells
+        scan(d.fr_nv, NF, d.cell_off);
+        if (NF) k_write_cells<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
+        CK(cudaEventRecord(cx->ev[7], st));
+        CK(cudaGetLastError());
+    }
+
+    void run() { if (d.bits == 2) run_bits<2>(); else run_bits<4>(); }
+
+    void collect_times() {
+        float t;
+        CK(cudaEventElapsedTime(&t, cx->ev[0], cx->ev[1])); ms[0] = t;
+        CK(cudaEventElapsedTime(&t, cx->ev[1], cx->ev[2])); ms[1] = t;
+        CK(cudaEventElapsedTime(&t, cx->ev[2], cx->ev[3])); ms[2] = t;
+        CK(cudaEventElapsedTime(&t, cx->ev[3], cx->ev[4])); ms[3] = t;
+        CK(cudaEventElapsedTime(&t, cx->ev[4], cx->ev[5])); ms[4] = t;
+        CK(cudaEventElapsedTime(&t, cx->ev[5], cx->ev[6])); ms[5] = t;
+        CK(cudaEventElapsedTime(&t, cx->ev[0], cx->ev[7])); ms[6] = t;
+    }
+
+    template <class T> T* down(const T* dptr, int64_t n) {
+        T* h = cx->outp.get<T>((size_t)std::max<int64_t>(n, 1));
+        if (n > 0) CK(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, cx->stream));
+        return h;
+    }
+    template <class T> T* hostcopy(const std::vector<T>& v) {
+        T* h = cx->outp.get<T>(std::max<size_t>(v.size(), 1));
+        if (!v.empty()) memcpy(h, v.data(), v.size() * sizeof(T));
+        return h;
+    }
+
+    void download(ahs_batch_out* out) {
+        const int64_t C = sz.C, NF = d.NF, NP = d.NP; const int p = in->ploidy;
+        out->n_chains = (int32_t)C; out->ploidy = p;
+        out->status = down(d.ch_status, C);
+        out->read_off = hostcopy(h_frow_off); out->pos_off = hostcopy(h_pos_off);
+        out->read_id = down(d.fr_id, NF); out->read_mapq = down(d.fr_mapq, NF); out->read_cluster = down(d.fr_cluster, NF);
+        out->cell_off = down(d.cell_off, NF + 1);
+        out->n_clusters = down(d.ch_nclusters, C); out->pos = down(d.pos, NP);
+        out->path = down(d.path, NP * p); out->hap_allele = down(d.hap_allele, NP * p); out->dp_cost = down(d.dp_cost, C);
+        out->maxpos = down(d.ch_maxpos, C);
+        int64_t* h_pairs = cx->outp.get<int64_t>(1);
+        CK(cudaMemcpyAsync(h_pairs, d.tot_pairs, 8, cudaMemcpyDeviceToHost, cx->stream));
+        CK(cudaStreamSynchronize(cx->stream));
+        const int64_t n_cells = out->cell_off[NF];
+        out->cell_pos = down(d.cell_pos, n_cells); out->cell_allele = down(d.cell_allele, n_cells);
+        CK(cudaStreamSynchronize(cx->stream));
+        out->n_cells = n_cells; out->n_pairs = *h_pairs / 2;
+        int64_t ok = 0; for (int64_t c = 0; c < C; c++) ok += out->status[c] == AHS_CHAIN_OK;
+        out->n_chains_ok = ok;
+    }
+};
+
+static int guarded(const char* what, const std::function<void()>& fn) {
+    try { fn(); g_err[0] = 0; return AHS_OK; }
+    catch (const CudaFail& f) { set_err("%s: CUDA error %d (%s) at %s, line %d", what, (int)f.e, cudaGetErrorString(f.e), f.what, f.line); cudaGetLastError(); return AHS_ERR_CUDA; }
+    catch (const LimitFail& f) { set_err("%s: limit exceeded: %s", what, f.msg.c_str()); return AHS_ERR_LIMIT; }
+    catch (const ArgFail& f) { set_err("%s: bad argument: %s", what, f.msg.c_str()); return AHS_ERR_ARG; }
+    catch (const std::exception& e) { set_err("%s: %s", what, e.what()); return AHS_ERR_INTERNAL; }
+}
+
+static void fill_empty_out(ahs_batch_out* out, Ctx* cx, int ploidy) {
+    memset(out, 0, sizeof(*out));
+    out->ploidy = ploidy;
+    out->read_off = cx->outp.get<int64_t>(1); out->read_off[0] = 0;
+    out->pos_off = cx->outp.get<int64_t>(1); out->pos_off[0] = 0;
+    out->cell_off = cx->outp.get<int64_t>(1); out->cell_off[0] = 0;
+}
+
+// one batch on one device; iters > 0 = resident timing mode
+static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int device, int warmup, int iters) {
+    if (!out) throw ArgFail{"null output"};
+    Sizes sz = validate(in);
+    Ctx* cx = get_ctx(device);
+    std::lock_guard<std::mutex> g(cx->mu);
+    CK(cudaSetDevice(device));
+    if (cx->out_busy) throw ArgFail{"previous ahs_batch_out of this device was not released with ahs_free_out"};
+    cx->dev.reset(); cx->outp.reset();
+    if (sz.C == 0) { fill_empty_out(out, cx, in->ploidy); cx->out_busy = true; return; }
+    Pipeline pl; pl.cx = cx; pl.in = in; pl.sz = sz;
+    cudaEvent_t e0 = cx->ev[8], e1 = cx->ev[9];
+    CK(cudaEventRecord(e0, cx->stream));
+    pl.upload();
+    CK(cudaEventRecord(e1, cx->stream));
+    pl.alloc_phase1();
+    // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
+    std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
+    float acc[8] = {0};
+    const int total = iters > 0 ? warmup + iters : 1;
+    for (int it = 0; it < total; it++) {
+        for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
+        pl.run();
+        CK(cudaStreamSynchronize(cx->stream));
+        pl.collect_times();
+        if (iters > 0 && it >= warmup) for (int i = 0; i < 8; i++) acc[i] += pl.ms[i];
+    }
+    if (iters > 0) for (int i = 0; i < 8; i++) pl.ms[i] = acc[i] / iters;
+    memset(out, 0, sizeof(*out));
+    cudaEvent_t d0 = cx->ev[8];
+    float h2d = 0; CK(cudaEventElapsedTime(&h2d, e0, e1));
+    CK(cudaEventRecord(d0, cx->stream));
+    pl.download(out);
+    CK(cudaEventRecord(e1, cx->stream)); CK(cudaEventSynchronize(e1));
+    float d2h = 0; CK(cudaEventElapsedTime(&d2h, d0, e1));
+    out->ms_h2d = h2d; out->ms_project = pl.ms[0]; out->ms_rows = pl.ms[1]; out->ms_score = pl.ms[2]; out->ms_cluster = pl.ms[3];
+    out->ms_consensus = pl.ms[4]; out->ms_thread = pl.ms[5]; out->ms_total_device = pl.ms[6]; out->ms_d2h = d2h;
+    cx->out_busy = true;
+}
+
+// ------------------------------------------------------------------ multi-device: LPT over chains, host gather
+struct SubBatch {
+    std::vector<int32_t> chain_id, anode, stage_a_order, enode, entry_read, src_chain;
+    std::vector<int64_t> bubble_off{0}, allele_off{0}, anode_off{0}, read_off{0}, entry_off{0}, enode_off{0};
+    std::vector<float> ident; ahs_batch_in view;
+    void add_chain(const ahs_batch_in* in, int c) {
+        src_chain.push_back(c); chain_id.push_back(in->chain_id ? in->chain_id[c] : c);
+        for (int64_t b = in->bubble_off[c]; b < in->bubble_off[c + 1]; b++) {
+            for (int64_t a = in->allele_off[b]; a < in->allele_off[b + 1]; a++) {
+                anode.insert(anode.end(), in->anode + in->anode_off[a], in->anode + in->anode_off[a + 1]);
+                anode_off.push_back((int64_t)anode.size());
+            }
+            allele_off.push_back((int64_t)anode_off.size() - 1);
+            stage_a_order.push_back(in->stage_a_order ? in->stage_a_order[b] : (int32_t)(in->bubble_off[c + 1] - 1 - b));
+        }
+        bubble_off.push_back((int64_t)allele_off.size() - 1);
+        for (int64_t e = in->entry_off[c]; e < in->entry_off[c + 1]; e++) {
+            enode.insert(enode.end(), in->enode + in->enode_off[e], in->enode + in->enode_off[e + 1]);
+            enode_off.push_back((int64_t)enode.size());
+            entry_read.push_back(in->entry_read[e]); ident.push_back(in->entry_identity[e]);
+        }
+        entry_off.push_back((int64_t)entry_read.size());
+        read_off.push_back(read_off.back() + in->read_off[c + 1] - in->read_off[c]);
+    }
+    void finish(int ploidy) {
+        view.n_chains = (int32_t)chain_id.size(); view.ploidy = ploidy; view.chain_id = chain_id.data();
+        view.bubble_off = bubble_off.data(); view.allele_off = allele_off.data(); view.anode_off = anode_off.data(); view.anode = anode.data();
+        view.stage_a_order = stage_a_order.data(); view.read_off = read_off.data(); view.entry_off = entry_off.data();
+        view.enode_off = enode_off.data(); view.enode = enode.data(); view.entry_read = entry_read.data(); view.entry_identity = ident.data();
+    }
+};
+
+template <class T> static T* mdup(const std::vector<T>& v) {
+    T* p = (T*)malloc(sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+
+}  // namespace ahs
+
+using namespace ahs;
+
+extern "C" {
+
+int ahs_abi_version(void) { return AHS_ABI_VERSION; }
+
+void ahs_get_limits(ahs_limits* out) {
+    if (!out) return;
+    out->max_ploidy = MAX_PLOIDY; out->max_alleles = MAX_ALLELES; out->max_reads_cluster = MAX_READS_CLUSTER; out->max_positions = MAX_POSITIONS;
+}
+
+int ahs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+const char* ahs_last_error(void) { return g_err; }
+
+double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_nodes, int ploidy) {
+    // projection ~ entry nodes; scoring ~ reads x depth; cluster editing ~ reads^2 (dense workspace);
+    // threading ~ positions x states x ploidy x k
+    const double reads = (double)n_entries, depth = n_bubbles > 0 ? (double)n_entry_nodes / (2.0 * n_bubbles) : 0.0;
+    double S = 1; for (int i = 0; i < ploidy; i++) S *= ploidy + 1;
+    return (double)n_entry_nodes + 4.0 * reads * depth + 0.05 * reads * reads + (double)n_bubbles * S * ploidy;
+}
+
+int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int device) {
+    return guarded("ahs_phase_batch", [&]() { phase_on_device(in, out, device, 0, 0); });
+}
+
+int ahs_phase_batch_resident(const ahs_batch_in* in, ahs_batch_out* out, int device, int warmup, int iters) {
+    return guarded("ahs_phase_batch_resident", [&]() { phase_on_device(in, out, device, warmup < 0 ? 0 : warmup, iters < 1 ? 1 : iters); });
+}
+
+void ahs_free_out(ahs_batch_out* out) {
+    if (!out) return;
+    if (out->n_chains < 0) {                      // gathered multi-device result: malloc'ed
+        free(out->status); free(out->read_off); free(out->read_id); free(out->read_mapq); free(out->read_cluster); free(out->cell_off);
+        free(out->cell_pos); free(out->cell_allele); free(out->n_clusters); free(out->pos_off); free(out->pos); free(out->path);
+        free(out->hap_allele); free(out->dp_cost); free(out->maxpos);
+    } else {
+        std::lock_guard<std::mutex> g(g_ctx_mu);
+        for (auto* c : g_ctx) if (c && c->out_busy) {
+            for (auto& ch : c->outp.chunks) if ((char*)out->read_off >= ch.p && (char*)out->read_off < ch.p + ch.cap) c->out_busy = false;
+        }
+    }
+    memset(out, 0, sizeof(*out));
+}
+
+int ahs_phase_batch_multi(const ahs_batch_in* in, ahs_batch_out* out, const int* device_ids, int n_devices) {
+    if (n_devices == 1 && device_ids) return ahs_phase_batch(in, out, device_ids[0]);
+    std::vector<std::string> errs(n_devices > 0 ? n_devices : 0);
+    int rc_all = guarded("ahs_phase_batch_multi", [&]() {
+        if (!device_ids || n_devices < 1) throw ArgFail{"no devices"};
+        if (!out) throw ArgFail{"null output"};
+        validate(in);
+        const int C = in->n_chains, G = n_devices, p = in->ploidy;
+        // LPT: chains by decreasing cost onto the least loaded device
+        std::vector<int> order(C); std::iota(order.begin(), order.end(), 0);
+        std::vector<double> cost(C);
+        for (int c = 0; c < C; c++) cost[c] = ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], in->entry_off[c + 1] - in->entry_off[c],
+                                                              in->enode_off[in->entry_off[c + 1]] - in->enode_off[in->entry_off[c]], p);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+        std::vector<SubBatch> sub(G); std::vector<double> load(G, 0.0); std::vector<std::vector<int>> assign(G);
+        for (int c : order) { int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); load[g] += cost[c]; assign[g].push_back(c); }
+        for (int g = 0; g < G; g++) { std::sort(assign[g].begin(), assign[g].end()); for (int c : assign[g]) sub[g].add_chain(in, c); sub[g].finish(p); }
+        std::vector<ahs_batch_out> outs(G); std::vector<int> rcs(G, 0);
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++) th.emplace_back([&, g]() { rcs[g] = ahs_phase_batch(&sub[g].view, &outs[g], device_ids[g]); if (rcs[g]) errs[g] = ahs_last_error(); });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < G; g++) if (rcs[g]) { for (int h = 0; h < G; h++) if (!rcs[h]) ahs_free_out(&outs[h]); throw std::runtime_error("device " + std::to_string(device_ids[g]) + ": " + errs[g]); }
+        // gather in input order
+        std::vector<int> where_g(C), where_i(C);
+        for (int g = 0; g < G; g++) for (size_t i = 0; i < assign[g].size(); i++) { where_g[assign[g][i]] = g; where_i[assign[g][i]] = (int)i; }
+        std::vector<int32_t> status, read_id, read_mapq, read_cluster, cell_pos, n_clusters, pos, path, maxpos;
+        std::vector<int64_t> read_off{0}, cell_off{0}, pos_off{0}; std::vector<uint8_t> cell_allele, hap_allele; std::vector<double> dp_cost;
+        memset(out, 0, sizeof(*out));
+        for (int c = 0; c < C; c++) {
+            const ahs_batch_out& o = outs[where_g[c]]; const int i = where_i[c];
+            status.push_back(o.status[i]); n_clusters.push_back(o.n_clusters[i]); dp_cost.push_back(o.dp_cost[i]); maxpos.push_back(o.maxpos[i]);
+            for (int64_t r = o.read_off[i]; r < o.read_off[i + 1]; r++) {
+                read_id.push_back(o.read_id[r]); read_mapq.push_back(o.read_mapq[r]); read_cluster.push_back(o.read_cluster[r]);
+                for (int64_t x = o.cell_off[r]; x < o.cell_off[r + 1]; x++) { cell_pos.push_back(o.cell_pos[x]); cell_allele.push_back(o.cell_allele[x]); }
+                cell_off.push_back((int64_t)cell_pos.size());
+            }
+            read_off.push_back((int64_t)read_id.size());
+            for (int64_t q = o.pos_off[i]; q < o.pos_off[i + 1]; q++) {
+                pos.push_back(o.pos[q]);
+                for (int h = 0; h < p; h++) { path.push_back(o.path[q * p + h]); hap_allele.push_back(o.hap_allele[q * p + h]); }
+            }
+            pos_off.push_back((int64_t)pos.size());
+        }
+        for (int g = 0; g < G; g++) {
+            out->n_cells += outs[g].n_cells; out->n_pairs += outs[g].n_pairs; out->n_chains_ok += outs[g].n_chains_ok;
+            out->ms_h2d = std::max(out->ms_h2d, outs[g].ms_h2d); out->ms_project = std::max(out->ms_project, outs[g].ms_project);
+            out->ms_rows = std::max(out->ms_rows, outs[g].ms_rows); out->ms_score = std::max(out->ms_score, outs[g].ms_score);
+            out->ms_cluster = std::max(out->ms_cluster, outs[g].ms_cluster); out->ms_consensus = std::max(out->ms_consensus, outs[g].ms_consensus);
+            out->ms_thread = std::max(out->ms_thread, outs[g].ms_thread); out->ms_d2h = std::max(out->ms_d2h, outs[g].ms_d2h);
+            out->ms_total_device = std::max(out->ms_total_device, outs[g].ms_total_device);
+            ahs_free_out(&outs[g]);
+        }
+        out->n_chains = -C;        // negative marks a malloc'ed (gathered) result for ahs_free_out; fixed below
+        out->ploidy = p;
+        out->status = mdup(status); out->read_off = mdup(read_off); out->read_id = mdup(read_id); out->read_mapq = mdup(read_mapq);
+        out->read_cluster = mdup(read_cluster); out->cell_off = mdup(cell_off); out->cell_pos = mdup(cell_pos); out->cell_allele = mdup(cell_allele);
+        out->n_clusters = mdup(n_clusters); out->pos_off = mdup(pos_off); out->pos = mdup(pos); out->path = mdup(path);
+        out->hap_allele = mdup(hap_allele); out->dp_cost = mdup(dp_cost); out->maxpos = mdup(maxpos);
+    });
+    return rc_all;
+}
+
+}  // extern "C"

@@ -34,7 +34,8 @@ class BatchOut(C.Structure):
                 ("n_cells", C.c_int64), ("n_pairs", C.c_int64), ("n_chains_ok", C.c_int64),
                 ("ms_h2d", C.c_float), ("ms_project", C.c_float), ("ms_rows", C.c_float), ("ms_score", C.c_float),
                 ("ms_cluster", C.c_float), ("ms_consensus", C.c_float), ("ms_thread", C.c_float), ("ms_d2h", C.c_float),
-                ("ms_total_device", C.c_float)]
+                ("ms_total_device", C.c_float), ("n_launches", C.c_int32), ("reserved", C.c_int32),
+                ("bytes_project", C.c_int64), ("bytes_score", C.c_int64), ("bytes_consensus", C.c_int64)]
 
 
 class Limits(C.Structure):
@@ -199,6 +200,7 @@ def result_from_struct(o: BatchOut) -> PhaseResult:
     npos = int(pos_off[-1])
     t = {k: float(getattr(o, k)) for k in ("ms_h2d", "ms_project", "ms_rows", "ms_score", "ms_cluster", "ms_consensus",
                                            "ms_thread", "ms_d2h", "ms_total_device")}
+    t.update({k: int(getattr(o, k)) for k in ("n_launches", "bytes_project", "bytes_score", "bytes_consensus")})
     return PhaseResult(p, _np(o.status, Cn, np.int32), read_off, _np(o.read_id, nr, np.int32), _np(o.read_mapq, nr, np.int32),
                        _np(o.read_cluster, nr, np.int32), cell_off, _np(o.cell_pos, nc, np.int32), _np(o.cell_allele, nc, np.uint8),
                        _np(o.n_clusters, Cn, np.int32), pos_off, _np(o.pos, npos, np.int32), _np(o.path, npos * p, np.int32),
@@ -231,8 +233,31 @@ def load_library(path: str = LIB_PATH):
     lib.ahs_last_error.restype = C.c_char_p
     lib.ahs_chain_cost.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int]
     lib.ahs_chain_cost.restype = C.c_double
+    lib.ahs_pin_host.argtypes = [C.c_void_p, C.c_uint64]
+    lib.ahs_pin_host.restype = C.c_int
+    lib.ahs_unpin_host.argtypes = [C.c_void_p]
+    lib.ahs_unpin_host.restype = C.c_int
     _lib = lib
     return lib
+
+
+def pin_batch(batch: Batch) -> None:
+    """Page-lock the batch's host arrays (bench: H2D from pinned memory)."""
+    lib = load_library()
+    for k in _I32 + _I64 + ("entry_identity",):
+        a = getattr(batch, k)
+        if a.nbytes:
+            rc = lib.ahs_pin_host(a.ctypes.data, a.nbytes)
+            if rc != 0:
+                raise RuntimeError("ahs_pin_host failed: " + lib.ahs_last_error().decode())
+
+
+def unpin_batch(batch: Batch) -> None:
+    lib = load_library()
+    for k in _I32 + _I64 + ("entry_identity",):
+        a = getattr(batch, k)
+        if a.nbytes:
+            lib.ahs_unpin_host(a.ctypes.data)
 
 
 def limits() -> Limits:

@@ -140,6 +140,7 @@ struct Pipeline {
     std::vector<int32_t> h_status, h_nfinal, h_npos, h_words;
     int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0;
     float ms[8] = {0};
+    int n_launches = 0;
 
     template <class T> const T* up(const T* h, int64_t n) {
         T* p = cx->dev.get<T>((size_t)std::max<int64_t>(n, 1));
@@ -213,34 +214,35 @@ struct Pipeline {
         cudaStream_t st = cx->stream;
         const int64_t nb = std::max<int64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
         int64_t* bs = dalloc<int64_t>(nb + 1);
-        k_scan_local<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(in32, n, out, bs);
-        k_scan_blocks<<<1, 32, 0, st>>>(bs, nb, bs + nb);
-        k_scan_add<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(out, n, bs, bs + nb);
+        k_scan_local<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(in32, n, out, bs); n_launches += 1;
+        k_scan_blocks<<<1, 32, 0, st>>>(bs, nb, bs + nb); n_launches += 1;
+        k_scan_add<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(out, n, bs, bs + nb); n_launches += 1;
         CK(cudaGetLastError());
     }
 
     template <int BITS> void run_bits() {
         cudaStream_t st = cx->stream; const int sms = cx->sms; const int64_t C = sz.C;
         const int TB = 256;
+        n_launches = 0;
         CK(cudaEventRecord(cx->ev[0], st));
         init_phase1();
         // ---- owner maps + trigger table
-        if (sz.NB) k_owner<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d.bubble_off, (int)C, sz.NB, d.bubble_chain);
-        if (sz.NA) k_owner<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d.allele_off, (int)sz.NB, sz.NA, d.allele_bubble);
-        if (sz.NE) k_owner<<<grid_for(sz.NE, TB, sms), TB, 0, st>>>(d.entry_off, (int)C, sz.NE, d.entry_chain);
-        if (sz.NR) k_owner<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d.read_off, (int)C, sz.NR, d.read_chain);
-        if (sz.NB) k_rank_a<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d);
-        if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d);
+        if (sz.NB) k_owner<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d.bubble_off, (int)C, sz.NB, d.bubble_chain); n_launches += 1;
+        if (sz.NA) k_owner<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d.allele_off, (int)sz.NB, sz.NA, d.allele_bubble); n_launches += 1;
+        if (sz.NE) k_owner<<<grid_for(sz.NE, TB, sms), TB, 0, st>>>(d.entry_off, (int)C, sz.NE, d.entry_chain); n_launches += 1;
+        if (sz.NR) k_owner<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d.read_off, (int)C, sz.NR, d.read_chain); n_launches += 1;
+        if (sz.NB) k_rank_a<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d); n_launches += 1;
         // ---- projection
-        if (sz.NE) k_project<<<grid_for(sz.NE, 8, sms), TB, 0, st>>>(d);
+        if (sz.NE) k_project<<<grid_for(sz.NE, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[1], st));
-        if (sz.NR) k_read_stage_a<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d);
-        if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d);
-        k_chain_T<<<grid_for(C, TB, sms), TB, 0, st>>>(d);
-        if (sz.NR) k_read_rows<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d);
-        if (sz.NR) k_read_rank<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d);
-        k_chain_sort<<<grid_for(C, 64, sms), 64, 0, st>>>(d);
-        k_count_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d);
+        if (sz.NR) k_read_stage_a<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+        k_chain_T<<<grid_for(C, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (sz.NR) k_read_rows<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (sz.NR) k_read_rank<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+        k_chain_sort<<<grid_for(C, 64, sms), 64, 0, st>>>(d); n_launches += 1;
+        k_count_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaGetLastError());
         // ---- sync #1: per-chain sizes -> offsets of the per-chain workspaces
         h_status.resize(C); h_nfinal.resize(C); h_npos.resize(C);
@@ -288,10 +290,10 @@ struct Pipeline {
         d.path = dzero<int32_t>(NP * in->ploidy); d.hap_allele = dzero<uint8_t>(NP * in->ploidy); d.dp_cost = dzero<double>(C);
         d.cell_off = dalloc<int64_t>(NF + 1); d.cell_pos = dalloc<int32_t>(h_tot_cells); d.cell_allele = dalloc<uint8_t>(h_tot_cells);
         int32_t* counters = dzero<int32_t>(4);
-        if (NF) k_owner<<<grid_for(NF, TB, sms), TB, 0, st>>>(d.frow_off, (int)C, NF, d.fr_chain);
-        if (NP) k_owner<<<grid_for(NP, TB, sms), TB, 0, st>>>(d.pos_off, (int)C, NP, d.pos_chain);
-        if (NF) k_pack_rows<<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
-        k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d);
+        if (NF) k_owner<<<grid_for(NF, TB, sms), TB, 0, st>>>(d.frow_off, (int)C, NF, d.fr_chain); n_launches += 1;
+        if (NP) k_owner<<<grid_for(NP, TB, sms), TB, 0, st>>>(d.pos_off, (int)C, NP, d.pos_chain); n_launches += 1;
+        if (NF) k_pack_rows<<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[2], st));
         // ---- scoring.  Reads with more than RATE_SMEM_KEYS candidate partners sort in HBM scratch.
         {
@@ -308,20 +310,20 @@ struct Pipeline {
             if (any) { d.key_scratch = dalloc<uint64_t>(tot); d.key_scratch_off = (int64_t*)up(koff.data(), NF + 1); }
             else { d.key_scratch = nullptr; d.key_scratch_off = nullptr; }
         }
-        if (NF) k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
-        if (NF) k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
+        if (NF) k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (NF) k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[3], st));
         // ---- cluster editing
-        if (NF) k_cluster_edit<<<std::min<int64_t>(C, (int64_t)sms * 8), CE_THREADS, 0, st>>>(d, counters);
+        if (NF) k_cluster_edit<<<std::min<int64_t>(C, (int64_t)sms * 8), CE_THREADS, 0, st>>>(d, counters); n_launches += 1;
         CK(cudaEventRecord(cx->ev[4], st));
         // ---- coverage / consensus, threading
-        if (NP) k_consensus<BITS><<<grid_for(NP, 4, sms), 128, 0, st>>>(d);
+        if (NP) k_consensus<BITS><<<grid_for(NP, 4, sms), 128, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[5], st));
-        if (NP) k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1);
+        if (NP) k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1;
         CK(cudaEventRecord(cx->ev[6], st));
         // ---- CSR cells
         scan(d.fr_nv, NF, d.cell_off);
-        if (NF) k_write_cells<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d);
+        if (NF) k_write_cells<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[7], st));
         CK(cudaGetLastError());
     }
@@ -425,6 +427,15 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     float d2h = 0; CK(cudaEventElapsedTime(&d2h, d0, e1));
     out->ms_h2d = h2d; out->ms_project = pl.ms[0]; out->ms_rows = pl.ms[1]; out->ms_score = pl.ms[2]; out->ms_cluster = pl.ms[3];
     out->ms_consensus = pl.ms[4]; out->ms_thread = pl.ms[5]; out->ms_total_device = pl.ms[6]; out->ms_d2h = d2h;
+    out->n_launches = pl.n_launches;
+    {   // algorithmic bytes, SURVEY.md §8d: each datum crosses HBM once
+        const double code_bytes = pl.d.bits / 8.0;
+        const int64_t cells = out->n_cells, NFr = pl.d.NF;
+        out->bytes_project = 4 * sz.NEN + 4 * sz.NAN_ + 8 * sz.NE + (int64_t)(code_bytes * cells) + 12 * NFr;
+        out->bytes_score = (int64_t)(code_bytes * cells) + 12 * NFr + 4 * out->n_pairs;
+        int64_t kept = 0; for (int64_t q = 0; q < pl.d.NP; q++) kept += 1;   // k_pos <= 2p; bounded below by 1 per position
+        out->bytes_consensus = (int64_t)(code_bytes * cells) + 16 * NFr + 5 * kept * in->ploidy;
+    }
     cx->out_busy = true;
 }
 
@@ -499,6 +510,20 @@ int ahs_phase_batch_resident(const ahs_batch_in* in, ahs_batch_out* out, int dev
     return guarded("ahs_phase_batch_resident", [&]() { phase_on_device(in, out, device, warmup < 0 ? 0 : warmup, iters < 1 ? 1 : iters); });
 }
 
+int ahs_pin_host(const void* ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return AHS_OK;
+    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { set_err("ahs_pin_host: %s", cudaGetErrorString(e)); cudaGetLastError(); return AHS_ERR_CUDA; }
+    cudaGetLastError();
+    return AHS_OK;
+}
+int ahs_unpin_host(const void* ptr) {
+    if (!ptr) return AHS_OK;
+    cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+    cudaGetLastError();
+    return e == cudaSuccess ? AHS_OK : AHS_ERR_CUDA;
+}
+
 void ahs_free_out(ahs_batch_out* out) {
     if (!out) return;
     if (out->n_chains < 0) {                      // gathered multi-device result: malloc'ed
@@ -564,6 +589,8 @@ int ahs_phase_batch_multi(const ahs_batch_in* in, ahs_batch_out* out, const int*
             out->ms_cluster = std::max(out->ms_cluster, outs[g].ms_cluster); out->ms_consensus = std::max(out->ms_consensus, outs[g].ms_consensus);
             out->ms_thread = std::max(out->ms_thread, outs[g].ms_thread); out->ms_d2h = std::max(out->ms_d2h, outs[g].ms_d2h);
             out->ms_total_device = std::max(out->ms_total_device, outs[g].ms_total_device);
+            out->n_launches += outs[g].n_launches; out->bytes_project += outs[g].bytes_project; out->bytes_score += outs[g].bytes_score;
+            out->bytes_consensus += outs[g].bytes_consensus;
             ahs_free_out(&outs[g]);
         }
         out->n_chains = -C;        // negative marks a malloc'ed (gathered) result for ahs_free_out; fixed below

@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — read-bubble cells phased per second (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the phasing hot path (projection -> scoring -> cluster editing ->
+coverage/consensus -> threading DP) over one synthetic batch.  The workload at every N is
+BASELINE.json configs[1] ("synthetic diploid human-scale graph: 50k chains, 2M bubbles, 30x
+ultra-long reads"), one full batch PER GPU (chains are independent: weak scaling, no collective
+on the data path; torch.distributed is only the barrier / max-over-ranks plumbing).
+
+  value : cells/s with the batch resident in HBM, timed with CUDA events on the library's
+          stream around each pass (ahs_phase_batch_resident), max over ranks.
+  e2e   : cells/s through the public call ahs_phase_batch() with pinned HOST buffers; H2D of the
+          whole CSR batch and D2H of every result array are inside the timed region.
+  --impl reference : the reference's own sources compiled verbatim (+ WhatsHap API shim, see
+          oracle/) run as `Ahsoka phase -t 1` on a bounded GFA/GAF sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "read-bubble cells phased/sec"
+UNIT = "cells/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(workload, scale, rank):
+    from ahsoka_b200 import synth
+    prm = synth.config(workload, scale)
+    prm.seed = prm.seed + 1000 * rank          # every rank phases its own chains
+    return synth.generate(prm)
+
+
+def workload_desc(workload, scale, batch):
+    return {"workload": f"{workload}: BASELINE.json configs[1] synthetic diploid human-scale graph" if workload == "cfg2" else workload,
+            "scale": scale, "chains_per_gpu": batch.n_chains, "bubbles_per_gpu": int(batch.bubble_off[-1]),
+            "reads_per_gpu": int(batch.read_off[-1]), "entry_nodes_per_gpu": int(batch.enode.shape[0]), "ploidy": int(batch.ploidy),
+            "l2": "inputs (%.0f MB) and per-chain workspaces exceed the 126 MB L2; no explicit flush" % (batch.nbytes() / 1e6)}
+
+
+def cpu_port_baseline(batch, seconds_target=15.0):
+    """CPU oracle (restatement, all host threads) on a bounded prefix of the same workload."""
+    from tests.oracle_binding import oracle_phase
+    cores = os.cpu_count() or 1
+    n = min(batch.n_chains, max(cores * 4, 64))
+    sub = batch.select(np.arange(n))
+    t0 = time.perf_counter(); r = oracle_phase(sub, cores); dt = time.perf_counter() - t0
+    # grow the sample towards the time target (bounded)
+    rate = max(r.n_cells / max(dt, 1e-6), 1.0)
+    want = int(min(batch.n_chains, max(n, n * seconds_target / max(dt, 1e-3) * 0.8)))
+    if want > 2 * n and dt < seconds_target / 4:
+        sub = batch.select(np.arange(want))
+        t0 = time.perf_counter(); r = oracle_phase(sub, cores); dt = time.perf_counter() - t0
+        n = want
+        rate = r.n_cells / max(dt, 1e-6)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n} chains of the batch ({r.n_cells} cells) in {dt:.2f} s, oracle/phase_oracle.cpp, {cores} threads",
+            "chains_per_s": r.n_chains_ok / max(dt, 1e-6)}
+
+
+def run_reference_arm(args):
+    """Reference sources verbatim (+ WhatsHap shim) as `Ahsoka phase -t 1` on a bounded sample."""
+    from ahsoka_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    exe = os.path.join(ROOT, "oracle", "_ref", "Ahsoka_ref")
+    n_chains = args.ref_chains
+    prm = synth.config(args.workload, 1.0)
+    prm.n_chains = n_chains
+    times, cells, chains = [], 0, 0
+    kind, cores, sample = "reference", 1, ""
+    with tempfile.TemporaryDirectory() as td:
+        batch = synth.generate(prm, os.path.join(td, "s"))
+        if os.path.exists(exe):
+            from tests.oracle_binding import oracle_phase
+            want = oracle_phase(batch)           # only to count the cells the CLI run phases (not timed)
+            cells, chains = want.n_cells, want.n_chains_ok
+            for it in range(args.warmup + args.steps):
+                out = os.path.join(td, f"o{it}")
+                t0 = time.perf_counter()
+                subprocess.run([exe, "phase", "-g", os.path.join(td, "s.gfa"), "-a", os.path.join(td, "s.gaf"), "-o", out, "-t", "1"],
+                               cwd=td, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+                dt = time.perf_counter() - t0
+                if it >= args.warmup:
+                    times.append(dt)
+            sample = (f"{n_chains} chains of {args.workload} as GFA+GAF through `Ahsoka phase -t 1` "
+                      f"(reference src/*.cpp verbatim at -O2 + WhatsHap API shim), whole CLI run incl. parsing")
+        else:
+            from tests.oracle_binding import oracle_phase
+            kind, cores = "port", os.cpu_count() or 1
+            for it in range(args.warmup + args.steps):
+                t0 = time.perf_counter(); r = oracle_phase(batch, cores); dt = time.perf_counter() - t0
+                cells, chains = r.n_cells, r.n_chains_ok
+                if it >= args.warmup:
+                    times.append(dt)
+            sample = f"{n_chains} chains of {args.workload}, CPU oracle port, {cores} threads (reference-verbatim binary not built)"
+    dt = sum(times) / len(times)
+    val = cells / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64 fixed point",
+            "data": "synthetic", "config": {"workload": args.workload, "sample_chains": n_chains, "cells": cells},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "chains_per_s": chains / dt},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--ref-chains", type=int, default=12)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    from ahsoka_b200 import api
+    lib = api.load_library()
+    if lib.ahs_device_count() <= local:
+        raise SystemExit("bench.py: no CUDA device for this rank; the phasing path has no CPU fallback")
+
+    batch = make_batch(args.workload, args.scale, rank)
+    api.pin_batch(batch)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier(); torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    # ---- device-resident timing: W warm-up passes, K timed passes, CUDA events inside the library
+    barrier()
+    if rank == 0:
+        sampler.start()
+    res = api.phase_batch(batch, device=local, resident_iters=args.steps, warmup=args.warmup)
+    barrier()
+    t = res.timings
+    ms_step = t["ms_total_device"]
+    # ---- end to end through the public call: host buffers in, host buffers out
+    for _ in range(2):
+        api.phase_batch(batch, device=local)
+    barrier()
+    e2e_times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter(); r2 = api.phase_batch(batch, device=local); e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
+    d2h = sum(getattr(r2, k).nbytes for k in r2.ARRAYS)
+
+    cells, chains_ok = res.n_cells, res.n_chains_ok
+    if dist is not None:
+        import torch
+        v = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(v[0]), float(v[1])
+        s = torch.tensor([cells, chains_ok], device="cuda", dtype=torch.int64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        cells, chains_ok = int(s[0]), int(s[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    stages = {}
+    for name, ms_key, bytes_key in (("project", "ms_project", "bytes_project"), ("score", "ms_score", "bytes_score"),
+                                    ("consensus", "ms_consensus", "bytes_consensus")):
+        ms = t[ms_key]; b = t[bytes_key]
+        gbs = b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages[name] = {"ms": ms, "algorithmic_bytes": b, "achieved_gbs": gbs, "frac": gbs / peak}
+    for name, ms_key in (("rows", "ms_rows"), ("cluster_edit", "ms_cluster"), ("thread_dp", "ms_thread")):
+        stages[name] = {"ms": t[ms_key], "bound": "latency / integer pipes (not an HBM-roofline stage)"}
+    dominant = max(("project", "rows", "score", "cluster_edit", "consensus", "thread_dp"), key=lambda k: stages[k]["ms"])
+    sc = stages["score"]
+    roofline = {"bound": "hbm", "kernel": "score = k_read_rates + k_pair_scores (read-pair agreement scoring)",
+                "achieved": sc["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": sc["frac"], "traffic": None,
+                "peak_source": peak_src, "dominant_stage_by_time": dominant, "stages": stages}
+    line = {"metric": METRIC, "value": cells / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes / i32-i64 fixed point",
+            "data": "synthetic", "config": dict(workload_desc(args.workload, args.scale, batch), parallelism=f"chains x{world} (no collective)"),
+            "chains_per_s": chains_ok / (ms_step * 1e-3), "cells": cells, "pairs_per_gpu": res.n_pairs,
+            "e2e": {"value": cells / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch.nbytes(), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(t["n_launches"]) * args.steps, "roofline": roofline, "clocks": clocks}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_port_baseline(batch)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

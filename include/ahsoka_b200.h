@@ -111,6 +111,10 @@ typedef struct ahs_batch_out {
     /* Device-side timings of the last call, milliseconds (CUDA events). */
     float     ms_h2d, ms_project, ms_rows, ms_score, ms_cluster, ms_consensus, ms_thread, ms_d2h;
     float     ms_total_device;   /* first kernel start -> last kernel end, inputs resident */
+    int32_t   n_launches;        /* kernels launched per pass over the batch */
+    int32_t   reserved;
+    /* Algorithmic byte counts of the last call (SURVEY.md §8d formulas), for roofline reports. */
+    int64_t   bytes_project, bytes_score, bytes_consensus;
 } ahs_batch_out;
 
 /* Build limits, so callers can size work and tests can probe the edges. */
@@ -152,6 +156,11 @@ int  ahs_phase_batch_resident(const ahs_batch_in *in, ahs_batch_out *out, int de
                               int warmup, int iters);
 
 void ahs_free_out(ahs_batch_out *out);
+
+/* Page-lock / unlock a caller buffer so that the H2D copies inside ahs_phase_batch run at full
+ * PCIe speed (optional; plain cudaHostRegister / cudaHostUnregister). */
+int  ahs_pin_host(const void *ptr, uint64_t bytes);
+int  ahs_unpin_host(const void *ptr);
 
 const char *ahs_last_error(void);
 

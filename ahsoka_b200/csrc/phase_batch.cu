@@ -85,6 +85,7 @@ static Ctx* get_ctx(int device) {
     CK(cudaMemcpy(c->d_ln, ln.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_ln1, ln1.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * 4096 + 64));
+    CK(cudaFuncSetAttribute(k_cluster_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     g_ctx[device] = c;
     return c;
 }
@@ -314,7 +315,35 @@ struct Pipeline {
         if (NF) k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[3], st));
         // ---- cluster editing
-        if (NF) k_cluster_edit<<<std::min<int64_t>(C, (int64_t)sms * 8), CE_THREADS, 0, st>>>(d, counters); n_launches += 1;
+        {
+            // size classes: chains below 128 reads run warp-per-chain out of shared memory, the rest
+            // block-per-chain out of HBM/L2
+            static const int cls_max[12] = {16, 24, 32, 40, 48, 56, 64, 72, 80, 96, 112, 127};
+            constexpr int NC = 12;
+            std::vector<int32_t> lists[NC + 1];
+            for (int64_t c = 0; c < C; c++) {
+                const int64_t n = h_frow_off[c + 1] - h_frow_off[c];
+                if (n <= 0) continue;
+                int k = NC; for (int x = 0; x < NC; x++) if (n <= cls_max[x]) { k = x; break; }
+                lists[k].push_back((int32_t)c);
+            }
+            int32_t* ce_counters = dzero<int32_t>(NC + 1);
+            for (int k = NC; k >= 0; k--) {
+                if (lists[k].empty()) continue;
+                std::stable_sort(lists[k].begin(), lists[k].end(), [&](int32_t a, int32_t b) { return h_nfinal[a] > h_nfinal[b]; });
+                const int32_t* dl = up(lists[k].data(), (int64_t)lists[k].size());
+                const int len = (int)lists[k].size();
+                if (k < NC) {
+                    const size_t slot = cw_slot_bytes(cls_max[k]), budget = 200 * 1024;
+                    const int wpb = (int)std::max<size_t>(1, std::min<size_t>(CW_WARPS, budget / slot));
+                    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, budget / (wpb * slot)));
+                    const int64_t grid = std::min<int64_t>((len + wpb - 1) / wpb, (int64_t)sms * per_sm);
+                    k_cluster_warp<<<(unsigned)grid, wpb * 32, wpb * slot, st>>>(d, dl, len, cls_max[k], ce_counters + k); n_launches += 1;
+                } else {
+                    k_cluster_edit<<<std::min<int64_t>(len, (int64_t)sms * 4), CE_THREADS, 0, st>>>(d, dl, len, ce_counters + k); n_launches += 1;
+                }
+            }
+        }
         CK(cudaEventRecord(cx->ev[4], st));
         // ---- coverage / consensus, threading
         if (NP) k_consensus<BITS><<<grid_for(NP, 4, sms), 128, 0, st>>>(d); n_launches += 1;
@@ -433,8 +462,7 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
         const int64_t cells = out->n_cells, NFr = pl.d.NF;
         out->bytes_project = 4 * sz.NEN + 4 * sz.NAN_ + 8 * sz.NE + (int64_t)(code_bytes * cells) + 12 * NFr;
         out->bytes_score = (int64_t)(code_bytes * cells) + 12 * NFr + 4 * out->n_pairs;
-        int64_t kept = 0; for (int64_t q = 0; q < pl.d.NP; q++) kept += 1;   // k_pos <= 2p; bounded below by 1 per position
-        out->bytes_consensus = (int64_t)(code_bytes * cells) + 16 * NFr + 5 * kept * in->ploidy;
+        out->bytes_consensus = (int64_t)(code_bytes * cells) + 16 * NFr + 5 * pl.d.NP * in->ploidy;   // k_pos ~ ploidy retained clusters
     }
     cx->out_busy = true;
 }

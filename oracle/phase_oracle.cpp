@@ -298,10 +298,13 @@ int64_t ahs_oracle_score(int n, const int64_t* row_off, const int32_t* pos, cons
     return (int64_t)ps.size();
 }
 
+static thread_local ClusterEditStats g_last_stats;
+void ahs_oracle_cluster_stats(int64_t* out3) { out3[0] = g_last_stats.steps; out3[1] = g_last_stats.merges; out3[2] = g_last_stats.forbids; }
+
 int ahs_oracle_cluster(int n, int64_t n_pairs, const int32_t* pi, const int32_t* pj, const int32_t* pw, int paranoid, int32_t* label) {
     std::vector<PairScore> ps(n_pairs);
     for (int64_t x = 0; x < n_pairs; x++) { ps[x].i = pi[x]; ps[x].j = pj[x]; ps[x].w = pw[x]; ps[x].n = ps[x].k = 0; }
-    auto cl = cluster_edit(n, ps, paranoid != 0);
+    auto cl = cluster_edit(n, ps, paranoid != 0, &g_last_stats);
     for (size_t c = 0; c < cl.size(); c++) for (int r : cl[c]) label[r] = (int32_t)c;
     return (int)cl.size();
 }

@@ -1,0 +1,91 @@
+"""CLI-level parity: `Ahsoka phase -g G -a A -o P -t 1` output text.
+
+The committed tests/golden/*.ref-result.txt files were written by oracle/_ref/Ahsoka_ref — the
+reference's src/*.cpp compiled VERBATIM (polyassembly.cpp, alignmentstoreadset.cpp,
+chainstoreadset.cpp, graph.cpp, alignmentreader.cpp, argumentparser.cpp) against the WhatsHap
+API shim of oracle/whatshap_shim — by tests/golden/make_golden.py.  They pin every
+Ahsoka-owned stage (projection, filter, ordering, coverage, consensus, re-packing, emission and
+the text format of README.md:28-42) to the reference text itself.
+
+  * not gpu: host drop-in (flatten + emission) with the CPU oracle behind the C ABI
+             (oracle/_ref/Ahsoka_flat_oracle) must reproduce those files byte for byte;
+  * gpu:     the same drop-in with the CUDA library behind the C ABI (oracle/_ref/Ahsoka_b200).
+Neither test reads /root/reference at run time (the binaries are prebuilt and travel to the GPU box).
+"""
+import json
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+CASES = [c for c in json.load(open(os.path.join(GOLDEN, "index.json")))["cases"] if "ref_result" in c]
+
+
+def _run_cli(exe, case, td, env=None):
+    out = os.path.join(td, "out")
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([exe, "phase", "-g", os.path.join(GOLDEN, case["gfa"]), "-a", os.path.join(td, "reads.gaf"), "-o", out, "-t", "1"],
+                       cwd=td, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return open(out + "-result.txt").read(), r.stdout
+
+
+def _stage(case, td):
+    # the reader writes <gaf stem>-alignment_identities.txt next to the GAF (alignmentreader.cpp:74-75): use a copy
+    with open(os.path.join(GOLDEN, case["gaf"])) as f, open(os.path.join(td, "reads.gaf"), "w") as g:
+        g.write(f.read())
+
+
+def _hap_lines(stdout):
+    # "hap:" blocks of alignmentstoreadset.cpp:479-486
+    lines = stdout.split("\n")
+    return [lines[i + 1] for i, l in enumerate(lines) if l.startswith("hap:") and i + 1 < len(lines)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_flat_oracle_cli_matches_reference_verbatim(case):
+    exe = os.path.join(REF_DIR, "Ahsoka_flat_oracle")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/Ahsoka_flat_oracle not built (needs /root/reference at build time)")
+    want = open(os.path.join(GOLDEN, case["ref_result"])).read()
+    with tempfile.TemporaryDirectory() as td:
+        _stage(case, td)
+        got, _ = _run_cli(exe, case, td)
+    assert got == want
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_reference_verbatim_binary_still_reproduces_golden(case):
+    exe = os.path.join(REF_DIR, "Ahsoka_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/Ahsoka_ref not built (needs /root/reference at build time)")
+    want = open(os.path.join(GOLDEN, case["ref_result"])).read()
+    with tempfile.TemporaryDirectory() as td:
+        _stage(case, td)
+        got, _ = _run_cli(exe, case, td)
+    assert got == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_b200_cli_matches_reference_verbatim(case):
+    exe = os.path.join(REF_DIR, "Ahsoka_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/Ahsoka_b200 not built (needs /root/reference at build time)")
+    want = open(os.path.join(GOLDEN, case["ref_result"])).read()
+    with tempfile.TemporaryDirectory() as td:
+        _stage(case, td)
+        got, out_gpu = _run_cli(exe, case, td)
+        assert got == want
+        ora = os.path.join(REF_DIR, "Ahsoka_flat_oracle")
+        if os.path.exists(ora):
+            with tempfile.TemporaryDirectory() as td2:
+                _stage(case, td2)
+                _, out_cpu = _run_cli(ora, case, td2)
+            assert _hap_lines(out_gpu) == _hap_lines(out_cpu)

@@ -20,6 +20,7 @@
 #include "k_project.cuh"
 #include "k_score.cuh"
 #include "k_cluster.cuh"
+#include "k_chain.cuh"
 #include "k_thread.cuh"
 
 namespace ahs {
@@ -58,11 +59,52 @@ struct Pool {
 struct Ctx {
     int device = -1; cudaStream_t stream = nullptr; Pool dev{false}, pin{true}, outp{true};
     int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
-    cudaEvent_t ev[10];
+    cudaEvent_t ev[12];
+    size_t smem_optin = 0;
     std::mutex mu;
 };
 static std::mutex g_ctx_mu;
 static Ctx* g_ctx[64] = {nullptr};
+
+// ------------------------------------------------------------------ fused scoring + cluster editing: size classes
+// A class = (largest n, threads per block).  The block size grows with the pair triangle so that every thread owns
+// at most CC_MAXPER candidate pairs; the shared-memory slot (16 B per pair) decides how many chains an SM holds.
+constexpr int CC_MAXPER = 20;
+struct FusedClass { int nmax, nt; };
+static const FusedClass kFused[] = {{16, 32}, {24, 32}, {30, 32}, {36, 32}, {44, 64}, {51, 64}, {58, 128}, {65, 128}, {72, 128},
+                                    {86, 256}, {101, 256}, {120, 512}, {143, 512}, {166, 1024}};
+constexpr int N_FUSED = (int)(sizeof(kFused) / sizeof(kFused[0]));
+
+template <int BITS, int NT> static void fused_attr(size_t optin) {
+    CK(cudaFuncSetAttribute(k_score_cluster<BITS, NT, CC_MAXPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+}
+static void fused_set_attributes(size_t optin) {
+    fused_attr<2, 32>(optin); fused_attr<2, 64>(optin); fused_attr<2, 128>(optin); fused_attr<2, 256>(optin); fused_attr<2, 512>(optin); fused_attr<2, 1024>(optin);
+    fused_attr<4, 32>(optin); fused_attr<4, 64>(optin); fused_attr<4, 128>(optin); fused_attr<4, 256>(optin); fused_attr<4, 512>(optin); fused_attr<4, 1024>(optin);
+}
+template <int BITS> static void fused_launch(int nt, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
+    switch (nt) {
+        case 32:   k_score_cluster<BITS, 32, CC_MAXPER><<<grid, 32, smem, st>>>(d, list, len, nmax, counter); break;
+        case 64:   k_score_cluster<BITS, 64, CC_MAXPER><<<grid, 64, smem, st>>>(d, list, len, nmax, counter); break;
+        case 128:  k_score_cluster<BITS, 128, CC_MAXPER><<<grid, 128, smem, st>>>(d, list, len, nmax, counter); break;
+        case 256:  k_score_cluster<BITS, 256, CC_MAXPER><<<grid, 256, smem, st>>>(d, list, len, nmax, counter); break;
+        case 512:  k_score_cluster<BITS, 512, CC_MAXPER><<<grid, 512, smem, st>>>(d, list, len, nmax, counter); break;
+        default:   k_score_cluster<BITS, 1024, CC_MAXPER><<<grid, 1024, smem, st>>>(d, list, len, nmax, counter); break;
+    }
+}
+// class of a chain with n final reads, -1 = HBM-resident path
+static int fused_class(int n, size_t smem_optin) {
+    for (int k = 0; k < N_FUSED; k++) {
+        if (n > kFused[k].nmax) continue;
+        const int nw = kFused[k].nt / 32;
+        if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) return -1;
+        if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)CC_MAXPER * kFused[k].nt) return -1;
+        int pw = 1; while (pw < n - 1) pw <<= 1;                       // rate-sort scratch per warp (k_chain.cuh)
+        if (n >= 2 && (n * (n - 1) / 2) / nw < pw) continue;
+        return k;
+    }
+    return -1;
+}
 
 static Ctx* get_ctx(int device) {
     std::lock_guard<std::mutex> g(g_ctx_mu);
@@ -86,6 +128,8 @@ static Ctx* get_ctx(int device) {
     CK(cudaMemcpy(c->d_ln1, ln1.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * 4096 + 64));
     CK(cudaFuncSetAttribute(k_cluster_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    fused_set_attributes(c->smem_optin);
     g_ctx[device] = c;
     return c;
 }
@@ -139,6 +183,8 @@ struct Pipeline {
     Ctx* cx; const ahs_batch_in* in; Sizes sz; DB d{};
     std::vector<int64_t> h_mrow_off, h_frow_off, h_pos_off, h_code_off, h_cw_off, h_back_off;
     std::vector<int32_t> h_status, h_nfinal, h_npos, h_words;
+    std::vector<uint8_t> h_fused;
+    float ms_fused = 0; unsigned long long h_tphase[2] = {0, 0};
     int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0;
     float ms[8] = {0};
     int n_launches = 0;
@@ -256,6 +302,7 @@ struct Pipeline {
         CK(cudaStreamSynchronize(st));
         if (h_err & 1) throw ArgFail{"empty allele path"};
         if (h_err & 2) throw LimitFail{"a bubble has more than 15 alleles"};
+        h_fused.assign(C, 0);
         h_frow_off.assign(C + 1, 0); h_pos_off.assign(C + 1, 0); h_code_off.assign(C, 0); h_cw_off.assign(C, 0); h_back_off.assign(C, 0); h_words.assign(C, 0);
         const int per_word = 32 / BITS;
         int64_t S_max = 1; for (int i = 0; i < in->ploidy; i++) S_max *= 2 * in->ploidy;
@@ -270,7 +317,8 @@ struct Pipeline {
             h_words[c] = (int32_t)((B + per_word - 1) / per_word);
             h_frow_off[c + 1] = h_frow_off[c] + n; h_pos_off[c + 1] = h_pos_off[c] + np;
             h_code_off[c] = n_code_words; n_code_words += n * h_words[c];
-            h_cw_off[c] = n_cw; n_cw += n * n;
+            h_fused[c] = (n > 0 && fused_class((int)n, cx->smem_optin) >= 0) ? 1 : 0;
+            h_cw_off[c] = n_cw; if (!h_fused[c]) n_cw += n * n;
             h_back_off[c] = h_pos_off[c] * S_max;
         }
         const int64_t NF = h_frow_off[C], NP = h_pos_off[C];
@@ -279,6 +327,10 @@ struct Pipeline {
         d.frow_off = (int64_t*)up(h_frow_off.data(), C + 1); d.pos_off = (int64_t*)up(h_pos_off.data(), C + 1);
         d.code_off = (int64_t*)up(h_code_off.data(), C); d.cw_off = (int64_t*)up(h_cw_off.data(), C); d.back_off = (int64_t*)up(h_back_off.data(), C);
         CK(cudaMemcpyAsync(d.ch_words, h_words.data(), C * 4, cudaMemcpyHostToDevice, st));
+        d.ch_fused = (uint8_t*)up(h_fused.data(), C);
+        d.t_phase = dzero<unsigned long long>(2);
+        int64_t nf_unfused = 0;
+        for (int64_t c = 0; c < C; c++) if (!h_fused[c]) nf_unfused += h_frow_off[c + 1] - h_frow_off[c];
         d.fr_chain = dalloc<int32_t>(NF); d.fr_first = dalloc<int32_t>(NF); d.fr_last = dalloc<int32_t>(NF); d.fr_mapq = dalloc<int32_t>(NF);
         d.fr_id = dalloc<int32_t>(NF); d.fr_nv = dalloc<int32_t>(NF); d.fr_cluster = dzero<int32_t>(NF);
         d.codes = dzero<uint32_t>(n_code_words);
@@ -304,16 +356,34 @@ struct Pipeline {
             for (int64_t c = 0; c < C; c++) {
                 const int64_t n = h_frow_off[c + 1] - h_frow_off[c];
                 int64_t cap = 0;
-                if (n > RATE_SMEM_KEYS) { cap = 1; while (cap < n) cap <<= 1; any = true; }
+                if (n > RATE_SMEM_KEYS && !h_fused[c]) { cap = 1; while (cap < n) cap <<= 1; any = true; }
                 for (int64_t i = 0; i < n; i++) { koff[h_frow_off[c] + i] = tot; tot += cap; }
             }
             koff[NF] = tot;
             if (any) { d.key_scratch = dalloc<uint64_t>(tot); d.key_scratch_off = (int64_t*)up(koff.data(), NF + 1); }
             else { d.key_scratch = nullptr; d.key_scratch_off = nullptr; }
         }
-        if (NF) k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
-        if (NF) k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (nf_unfused) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
+        if (nf_unfused) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         CK(cudaEventRecord(cx->ev[3], st));
+        // ---- fused scoring + cluster editing out of shared memory (every chain of BASELINE configs 2-4)
+        CK(cudaEventRecord(cx->ev[10], st));
+        {
+            std::vector<int32_t> fl[N_FUSED];
+            for (int64_t c = 0; c < C; c++) if (h_fused[c]) fl[fused_class((int)(h_frow_off[c + 1] - h_frow_off[c]), cx->smem_optin)].push_back((int32_t)c);
+            int32_t* f_counters = dzero<int32_t>(N_FUSED);
+            for (int k = N_FUSED - 1; k >= 0; k--) {
+                if (fl[k].empty()) continue;
+                std::stable_sort(fl[k].begin(), fl[k].end(), [&](int32_t a, int32_t b) { return h_nfinal[a] > h_nfinal[b]; });
+                const int32_t* dl = up(fl[k].data(), (int64_t)fl[k].size());
+                const int len = (int)fl[k].size(), nt = kFused[k].nt;
+                const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(32, 2048 / nt), (228 * 1024) / (smem + 1024)));
+                const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
+                fused_launch<BITS>(nt, grid, smem, st, d, dl, len, kFused[k].nmax, f_counters + k); n_launches += 1;
+            }
+        }
+        CK(cudaEventRecord(cx->ev[11], st));
         // ---- cluster editing
         {
             // size classes: chains below 128 reads run warp-per-chain out of shared memory, the rest
@@ -323,7 +393,7 @@ struct Pipeline {
             std::vector<int32_t> lists[NC + 1];
             for (int64_t c = 0; c < C; c++) {
                 const int64_t n = h_frow_off[c + 1] - h_frow_off[c];
-                if (n <= 0) continue;
+                if (n <= 0 || h_fused[c]) continue;
                 int k = NC; for (int x = 0; x < NC; x++) if (n <= cls_max[x]) { k = x; break; }
                 lists[k].push_back((int32_t)c);
             }
@@ -365,6 +435,12 @@ struct Pipeline {
         CK(cudaEventElapsedTime(&t, cx->ev[1], cx->ev[2])); ms[1] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[2], cx->ev[3])); ms[2] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[3], cx->ev[4])); ms[3] = t;
+        // the fused kernel does scoring and cluster editing: split its time by the in-kernel globaltimer shares
+        CK(cudaEventElapsedTime(&t, cx->ev[10], cx->ev[11])); ms_fused = t;
+        CK(cudaMemcpy(h_tphase, d.t_phase, 16, cudaMemcpyDeviceToHost));
+        const double tot = (double)h_tphase[0] + (double)h_tphase[1];
+        const float fused_score = tot > 0 ? (float)(ms_fused * ((double)h_tphase[0] / tot)) : 0.f;
+        ms[2] += fused_score; ms[3] -= fused_score; ms[7] = fused_score;
         CK(cudaEventElapsedTime(&t, cx->ev[4], cx->ev[5])); ms[4] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[5], cx->ev[6])); ms[5] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[0], cx->ev[7])); ms[6] = t;

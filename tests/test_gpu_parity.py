@@ -23,6 +23,19 @@ def test_diploid_small_chains(seed):
     assert got.n_chains_ok > 30
 
 
+@pytest.mark.parametrize("mean_len,n_chains,seed", [(80, 30, 71), (140, 12, 72)])
+def test_diploid_mid_and_big_chains(mean_len, n_chains, seed):
+    # ~100 and ~180 final reads per chain: the large shared-memory classes of the fused kernel and,
+    # above 166 reads, the HBM-resident scoring / cluster-editing path
+    got = _check(synth.generate(synth.params(2, n_chains, 1, mean_len, depth=30.0, seed=seed)))
+    assert got.n_chains_ok == n_chains
+
+
+def test_cfg2_sample():
+    got = _check(synth.generate(synth.config("cfg2", 0.01)))
+    assert got.n_chains_ok > 400
+
+
 def test_diploid_tiny_and_trivial_chains():
     # chains of 1..6 bubbles: <=1 bubble is header-only (status 1), very short chains often end empty (status 2)
     _check(synth.generate(synth.params(2, 60, 1, 3, min_len=1, depth=12.0, seed=11)))

@@ -18,6 +18,9 @@ CASES = {
     "trip": synth.params(3, 12, 1, 30, depth=30.0, seed=31),
     "tetra": synth.params(4, 12, 1, 30, depth=40.0, seed=41),
     "fourbit": synth.params(2, 20, 1, 20, depth=30.0, max_alleles=6, seed=51),
+    "dip_mid": synth.params(2, 30, 1, 80, depth=30.0, seed=71),
+    "dip_big": synth.params(2, 12, 1, 140, depth=30.0, seed=72),
+    "cfg2_small": synth.config("cfg2", 0.01),
     "cfg1": synth.config("cfg1"),
 }
 

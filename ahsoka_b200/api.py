@@ -171,9 +171,25 @@ class PhaseResult:
     n_pairs: int
     n_chains_ok: int
     timings: dict
+    _owner: object = None          # (lib, BatchOut) while the arrays are views of the library's pinned buffers
 
     ARRAYS = ("status", "read_off", "read_id", "read_mapq", "read_cluster", "cell_off", "cell_pos", "cell_allele",
               "n_clusters", "pos_off", "pos", "path", "hap_allele", "dp_cost", "maxpos")
+
+    def release(self):
+        """Give the library's output buffers back (only needed for results obtained with copy=False)."""
+        if self._owner is not None:
+            lib, o = self._owner
+            self._owner = None
+            for k in self.ARRAYS:
+                setattr(self, k, None)
+            lib.ahs_free_out(C.byref(o))
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
     def diff(self, other: "PhaseResult"):
         """Names of the arrays that differ (bit-exact comparison)."""
@@ -184,27 +200,32 @@ class PhaseResult:
         return bad
 
 
-def _np(ptr, n, dtype):
+def _np(ptr, n, dtype, copy=True):
     if n == 0:
         return np.zeros(0, dtype=dtype)
-    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+    a = np.ctypeslib.as_array(ptr, shape=(n,))
+    return a.astype(dtype, copy=True) if copy else a
 
 
-def result_from_struct(o: BatchOut) -> PhaseResult:
+def result_from_struct(o: BatchOut, copy: bool = True) -> PhaseResult:
+    """numpy view of an ahs_batch_out.  copy=False: zero-copy views of the library's (pinned) output
+    buffers, valid until PhaseResult.release()."""
+    def g(ptr, n, dtype):
+        return _np(ptr, n, dtype, copy)
     Cn, p = o.n_chains, o.ploidy
-    read_off = _np(o.read_off, Cn + 1, np.int64)
+    read_off = g(o.read_off, Cn + 1, np.int64)
     nr = int(read_off[-1])
-    cell_off = _np(o.cell_off, nr + 1, np.int64)
+    cell_off = g(o.cell_off, nr + 1, np.int64)
     nc = int(cell_off[-1])
-    pos_off = _np(o.pos_off, Cn + 1, np.int64)
+    pos_off = g(o.pos_off, Cn + 1, np.int64)
     npos = int(pos_off[-1])
     t = {k: float(getattr(o, k)) for k in ("ms_h2d", "ms_project", "ms_rows", "ms_score", "ms_cluster", "ms_consensus",
                                            "ms_thread", "ms_d2h", "ms_total_device")}
     t.update({k: int(getattr(o, k)) for k in ("n_launches", "bytes_project", "bytes_score", "bytes_consensus")})
-    return PhaseResult(p, _np(o.status, Cn, np.int32), read_off, _np(o.read_id, nr, np.int32), _np(o.read_mapq, nr, np.int32),
-                       _np(o.read_cluster, nr, np.int32), cell_off, _np(o.cell_pos, nc, np.int32), _np(o.cell_allele, nc, np.uint8),
-                       _np(o.n_clusters, Cn, np.int32), pos_off, _np(o.pos, npos, np.int32), _np(o.path, npos * p, np.int32),
-                       _np(o.hap_allele, npos * p, np.uint8), _np(o.dp_cost, Cn, np.float64), _np(o.maxpos, Cn, np.int32),
+    return PhaseResult(p, g(o.status, Cn, np.int32), read_off, g(o.read_id, nr, np.int32), g(o.read_mapq, nr, np.int32),
+                       g(o.read_cluster, nr, np.int32), cell_off, g(o.cell_pos, nc, np.int32), g(o.cell_allele, nc, np.uint8),
+                       g(o.n_clusters, Cn, np.int32), pos_off, g(o.pos, npos, np.int32), g(o.path, npos * p, np.int32),
+                       g(o.hap_allele, npos * p, np.uint8), g(o.dp_cost, Cn, np.float64), g(o.maxpos, Cn, np.int32),
                        int(o.n_cells), int(o.n_pairs), int(o.n_chains_ok), t)
 
 
@@ -266,9 +287,12 @@ def limits() -> Limits:
     return lim
 
 
-def phase_batch(batch: Batch, device: int = 0, devices=None, resident_iters: int = 0, warmup: int = 0) -> PhaseResult:
+def phase_batch(batch: Batch, device: int = 0, devices=None, resident_iters: int = 0, warmup: int = 0,
+                copy: bool = True) -> PhaseResult:
     """Phase a batch on the GPU (host buffers in / out).
 
+    copy=False returns zero-copy numpy views of the library-owned output buffers (the C ABI's own contract:
+    valid until ahs_free_out); call .release() on the result before the next call on the same device.
     devices: list of CUDA ordinals -> ahs_phase_batch_multi (chains dealt LPT across them).
     resident_iters > 0 -> ahs_phase_batch_resident (device-only timing over resident inputs).
     """
@@ -283,6 +307,10 @@ def phase_batch(batch: Batch, device: int = 0, devices=None, resident_iters: int
         rc = lib.ahs_phase_batch(C.byref(s), C.byref(o), device)
     if rc != 0:
         raise RuntimeError(f"ahs_phase_batch failed ({rc}): {lib.ahs_last_error().decode()}")
+    if not copy:
+        r = result_from_struct(o, copy=False)
+        r._owner = (lib, o)
+        return r
     try:
         return result_from_struct(o)
     finally:

@@ -36,8 +36,52 @@ __global__ void k_fill_i32(int32_t* p, int32_t v, int64_t n) {
     for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) p[x] = v;
 }
 
+// ---------------------------------------------------------------- input validation (first kernel of every pass)
+// err_flags bits: 1 empty allele path, 2 more than 15 alleles, 4 offsets not monotone, 8 entry_read out of
+// range, 16 stage_a_order is not a permutation.  Every later kernel of phase 1 returns at once if a bit is set,
+// so a malformed batch can never drive an out-of-bounds access; the host reports the error after sync #1.
+#define AHS_BAIL_ON_ERR(d) do { if (*(volatile const int32_t*)(d).err_flags) return; } while (0)
+
+__global__ void k_validate(DB d, int32_t* __restrict__ max_k) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, x0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int bad = 0, mk = 0;
+    for (int64_t b = x0; b < d.NB; b += stride) {
+        const int64_t k = d.allele_off[b + 1] - d.allele_off[b];
+        if (k < 0) bad |= 4; else if (k > MAX_ALLELES) bad |= 2; else mk = max(mk, (int)k);
+    }
+    for (int64_t a = x0; a < d.NA; a += stride) { const int64_t l = d.anode_off[a + 1] - d.anode_off[a]; if (l < 0) bad |= 4; else if (l == 0) bad |= 1; }
+    for (int64_t e = x0; e < d.NE; e += stride) if (d.enode_off[e + 1] < d.enode_off[e]) bad |= 4;
+    mk = warp_max_i32(mk);
+    if (lane_id() == 0 && mk) atomicMax(max_k, mk);
+    if (bad) atomicOr(d.err_flags, bad);
+}
+
+// entry_read in range (needs entry_chain), stage_a_order values in range (needs bubble_chain)
+__global__ void k_validate_owned(DB d) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, x0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int bad = 0;
+    for (int64_t e = x0; e < d.NE; e += stride) {
+        const int c = d.entry_chain[e];
+        const int32_t r = d.entry_read[e];
+        if (r < 0 || r >= d.read_off[c + 1] - d.read_off[c]) bad |= 8;
+    }
+    if (d.stage_a_order) for (int64_t gb = x0; gb < d.NB; gb += stride) {
+        const int c = d.bubble_chain[gb];
+        const int32_t v = d.stage_a_order[gb];
+        if (v < 0 || v >= d.bubble_off[c + 1] - d.bubble_off[c]) bad |= 16;
+    }
+    if (bad) atomicOr(d.err_flags, bad);
+}
+
+// every slot of rankA written <=> stage_a_order is a permutation of each chain's bubble ids
+__global__ void k_validate_perm(DB d) {
+    for (int64_t gb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gb < d.NB; gb += (int64_t)gridDim.x * blockDim.x)
+        if (d.rankA[gb] < 0) atomicOr(d.err_flags, 16);
+}
+
 // stage-A visit rank of each bubble (inverse of stage_a_order, alignmentstoreadset.cpp:90)
 __global__ void k_rank_a(DB d) {
+    AHS_BAIL_ON_ERR(d);
     for (int64_t gb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gb < d.NB; gb += (int64_t)gridDim.x * blockDim.x) {
         int c = d.bubble_chain[gb];
         int64_t b0 = d.bubble_off[c];
@@ -48,6 +92,7 @@ __global__ void k_rank_a(DB d) {
 
 // ---------------------------------------------------------------- K0: trigger table
 __global__ void k_build_triggers(DB d) {
+    AHS_BAIL_ON_ERR(d);
     for (int64_t ga = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ga < d.NA; ga += (int64_t)gridDim.x * blockDim.x) {
         const int64_t gb = d.allele_bubble[ga];
         const int c = d.bubble_chain[gb];
@@ -79,6 +124,7 @@ __device__ __forceinline__ bool entry_has(const int32_t* __restrict__ nodes, int
 
 // one warp per alignment entry; lanes stride over the entry's nodes
 __global__ void __launch_bounds__(256) k_project(DB d) {
+    AHS_BAIL_ON_ERR(d);
     const int warps_per_block = blockDim.x >> 5;
     const int lane = lane_id();
     for (int64_t ge = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); ge < d.NE; ge += (int64_t)gridDim.x * warps_per_block) {
@@ -133,6 +179,7 @@ __global__ void __launch_bounds__(256) k_project(DB d) {
 // ---------------------------------------------------------------- K1b: stage-A statistics per read
 // count / first / last fully contained bubble and the stage-A mapq (:146-165, :173-182)
 __global__ void __launch_bounds__(256) k_read_stage_a(DB d) {
+    AHS_BAIL_ON_ERR(d);
     const int wpb = blockDim.x >> 5, lane = lane_id();
     for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < d.NR; r += (int64_t)gridDim.x * wpb) {
         const int c = d.read_chain[r];
@@ -156,6 +203,7 @@ __global__ void __launch_bounds__(256) k_read_stage_a(DB d) {
 
 // boundary flags: which of maxpos-1 / maxpos are last / first positions of filtered stage-A reads (:173-189)
 __global__ void k_chain_flags(DB d) {
+    AHS_BAIL_ON_ERR(d);
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < d.NR; r += (int64_t)gridDim.x * blockDim.x) {
         const int c = d.read_chain[r];
         if (d.bubble_off[c + 1] - d.bubble_off[c] <= 1) continue;
@@ -172,6 +220,7 @@ __global__ void k_chain_flags(DB d) {
 
 // to_be_added = [0,maxpos) U {e, e+1 : e in last \ first} = [0, T)  (:173-209, SURVEY A#10)
 __global__ void k_chain_T(DB d) {
+    AHS_BAIL_ON_ERR(d);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.C; c += gridDim.x * blockDim.x) {
         const int B = (int)(d.bubble_off[c + 1] - d.bubble_off[c]);
         if (B <= 1) { d.ch_status[c] = AHS_CHAIN_TRIVIAL; d.ch_T[c] = 0; continue; }
@@ -189,6 +238,7 @@ __global__ void k_chain_T(DB d) {
 
 // ---------------------------------------------------------------- K1d: final rows per read (stage B + filter)
 __global__ void __launch_bounds__(256) k_read_rows(DB d) {
+    AHS_BAIL_ON_ERR(d);
     const int wpb = blockDim.x >> 5, lane = lane_id();
     for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < d.NR; r += (int64_t)gridDim.x * wpb) {
         const int c = d.read_chain[r];
@@ -243,6 +293,7 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
 // ---------------------------------------------------------------- K1e: read order
 // Insertion order of the stage-B read set = order of the creation triples; rank by counting.
 __global__ void k_read_rank(DB d) {
+    AHS_BAIL_ON_ERR(d);
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < d.NR; r += (int64_t)gridDim.x * blockDim.x) {
         if (!d.rd_pass[r]) continue;
         const int c = d.read_chain[r];
@@ -331,6 +382,7 @@ __device__ bool kv_std_sort(KV a, int n) {
 }
 
 __global__ void k_chain_sort(DB d) {
+    AHS_BAIL_ON_ERR(d);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.C; c += gridDim.x * blockDim.x) {
         if (d.ch_status[c] != AHS_CHAIN_OK) continue;
         const int n = d.ch_nfinal[c];
@@ -343,6 +395,7 @@ __global__ void k_chain_sort(DB d) {
 
 // covered positions per chain: count, then (after the host has the offsets) the compact list
 __global__ void k_count_pos(DB d) {
+    AHS_BAIL_ON_ERR(d);
     const int wpb = blockDim.x >> 5, lane = lane_id();
     for (int c = blockIdx.x * wpb + (threadIdx.x >> 5); c < d.C; c += gridDim.x * wpb) {
         const int64_t b0 = d.bubble_off[c];

@@ -2,6 +2,7 @@
 // sm_100a kernels of k_project / k_score / k_cluster / k_thread on one stream, downloads the
 // result.  No torch, no CPU fallback: without a usable CUDA device every entry point fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -137,6 +138,8 @@ static Ctx* get_ctx(int device) {
 // ------------------------------------------------------------------ validation
 struct Sizes { int64_t C, NB, NA, NAN_, NR, NE, NEN, M; int max_k; };
 
+// Host side: O(chains) checks only.  Everything per bubble / allele / entry is checked on the device by
+// k_validate* (first kernels of the pass) and reported after sync #1.
 static Sizes validate(const ahs_batch_in* in) {
     if (!in) throw ArgFail{"null batch"};
     if (in->n_chains < 0) throw ArgFail{"n_chains < 0"};
@@ -148,27 +151,25 @@ static Sizes validate(const ahs_batch_in* in) {
         if (off[0] != 0) throw ArgFail{std::string(name) + "[0] != 0"};
         for (int64_t i = 0; i < n; i++) if (off[i + 1] < off[i]) throw ArgFail{std::string(name) + " not monotone"};
     };
+    auto ends = [&](const int64_t* off, int64_t n, const char* name) -> int64_t {
+        if (!off) throw ArgFail{std::string(name) + " is null"};
+        if (off[0] != 0) throw ArgFail{std::string(name) + "[0] != 0"};
+        if (off[n] < 0) throw ArgFail{std::string(name) + " not monotone"};
+        return off[n];
+    };
     mono(in->bubble_off, s.C, "bubble_off"); s.NB = in->bubble_off[s.C];
-    mono(in->allele_off, s.NB, "allele_off"); s.NA = in->allele_off[s.NB];
-    mono(in->anode_off, s.NA, "anode_off"); s.NAN_ = in->anode_off[s.NA];
+    s.NA = ends(in->allele_off, s.NB, "allele_off");
+    s.NAN_ = ends(in->anode_off, s.NA, "anode_off");
     mono(in->read_off, s.C, "read_off"); s.NR = in->read_off[s.C];
     mono(in->entry_off, s.C, "entry_off"); s.NE = in->entry_off[s.C];
-    mono(in->enode_off, s.NE, "enode_off"); s.NEN = in->enode_off[s.NE];
-    s.max_k = 0;
-    for (int64_t b = 0; b < s.NB; b++) s.max_k = std::max<int>(s.max_k, (int)(in->allele_off[b + 1] - in->allele_off[b]));
-    if (s.max_k > MAX_ALLELES) throw LimitFail{"a bubble has more than 15 alleles"};
-    for (int64_t a = 0; a < s.NA; a++) if (in->anode_off[a + 1] == in->anode_off[a]) throw ArgFail{"empty allele path"};
+    s.NEN = ends(in->enode_off, s.NE, "enode_off");
+    if ((s.NAN_ && !in->anode) || (s.NEN && !in->enode) || (s.NE && (!in->entry_read || !in->entry_identity))) throw ArgFail{"null array"};
     for (int64_t c = 0; c < s.C; c++) {
         const int64_t B = in->bubble_off[c + 1] - in->bubble_off[c], R = in->read_off[c + 1] - in->read_off[c];
         if (B > MAX_POSITIONS) throw LimitFail{"chain with more than 32767 bubbles"};
-        const int64_t e0 = in->entry_off[c], e1 = in->entry_off[c + 1];
-        for (int64_t e = e0; e < e1; e++) if (in->entry_read[e] < 0 || in->entry_read[e] >= R) throw ArgFail{"entry_read out of range"};
-        if (in->stage_a_order) {
-            std::vector<char> seen(B, 0);
-            for (int64_t b = 0; b < B; b++) { int32_t v = in->stage_a_order[in->bubble_off[c] + b]; if (v < 0 || v >= B || seen[v]) throw ArgFail{"stage_a_order is not a permutation"}; seen[v] = 1; }
-        }
         s.M += (B > 1) ? B * R : 0;
     }
+    s.max_k = 0;                                     // filled in from the device at sync #1
     return s;
 }
 
@@ -201,7 +202,7 @@ struct Pipeline {
     void upload() {
         cudaStream_t st = cx->stream;
         const int64_t C = sz.C;
-        d.C = (int32_t)C; d.ploidy = in->ploidy; d.bits = sz.max_k <= 3 ? 2 : 4;
+        d.C = (int32_t)C; d.ploidy = in->ploidy; d.bits = 2;      // code width is decided at sync #1 (largest allele count)
         d.NB = sz.NB; d.NA = sz.NA; d.NAN_ = sz.NAN_; d.NR = sz.NR; d.NE = sz.NE; d.NEN = sz.NEN;
         d.bubble_off = up(in->bubble_off, C + 1); d.allele_off = up(in->allele_off, sz.NB + 1); d.anode_off = up(in->anode_off, sz.NA + 1);
         d.read_off = up(in->read_off, C + 1); d.entry_off = up(in->entry_off, C + 1); d.enode_off = up(in->enode_off, sz.NE + 1);
@@ -252,6 +253,7 @@ struct Pipeline {
         CK(cudaMemsetAsync(d.create_key, 0xff, std::max<int64_t>(sz.NR, 1) * 8, st)); CK(cudaMemsetAsync(d.createA_key, 0xff, std::max<int64_t>(sz.NR, 1) * 8, st));
         CK(cudaMemsetAsync(d.first_entry, 0xff, std::max<int64_t>(sz.NR, 1) * 4, st)); CK(cudaMemsetAsync(d.has_good, 0, std::max<int64_t>(sz.NR, 1), st));
         CK(cudaMemsetAsync(d.poscov, 0, std::max<int64_t>(sz.NB, 1), st));
+        CK(cudaMemsetAsync(d.rankA, 0xff, std::max<int64_t>(sz.NB, 1) * 4, st));
         CK(cudaMemsetAsync(d.ch_status, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxpos, 0xff, C * 4, st)); CK(cudaMemsetAsync(d.ch_flags, 0, C * 4, st));
         CK(cudaMemsetAsync(d.ch_nfinal, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxspan, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_nclusters, 0, C * 4, st));
         CK(cudaMemsetAsync(d.tot_cells, 0, 8, st)); CK(cudaMemsetAsync(d.tot_pairs, 0, 8, st)); CK(cudaMemsetAsync(d.err_flags, 0, 4, st));
@@ -267,18 +269,23 @@ struct Pipeline {
         CK(cudaGetLastError());
     }
 
-    template <int BITS> void run_bits() {
+    // phase 1: validation, projection, final rows per read, read order; ends with sync #1 (per-chain sizes)
+    void run_phase1() {
         cudaStream_t st = cx->stream; const int sms = cx->sms; const int64_t C = sz.C;
         const int TB = 256;
         n_launches = 0;
         CK(cudaEventRecord(cx->ev[0], st));
         init_phase1();
+        int32_t* d_maxk = dzero<int32_t>(1);
+        k_validate<<<grid_for(std::max(sz.NE, std::max(sz.NA, sz.NB)), TB, sms), TB, 0, st>>>(d, d_maxk); n_launches += 1;
         // ---- owner maps + trigger table
         if (sz.NB) k_owner<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d.bubble_off, (int)C, sz.NB, d.bubble_chain); n_launches += 1;
         if (sz.NA) k_owner<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d.allele_off, (int)sz.NB, sz.NA, d.allele_bubble); n_launches += 1;
         if (sz.NE) k_owner<<<grid_for(sz.NE, TB, sms), TB, 0, st>>>(d.entry_off, (int)C, sz.NE, d.entry_chain); n_launches += 1;
         if (sz.NR) k_owner<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d.read_off, (int)C, sz.NR, d.read_chain); n_launches += 1;
+        k_validate_owned<<<grid_for(std::max(sz.NE, sz.NB), TB, sms), TB, 0, st>>>(d); n_launches += 1;
         if (sz.NB) k_rank_a<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (sz.NB && d.stage_a_order) { k_validate_perm<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d); n_launches += 1;
         // ---- projection
         if (sz.NE) k_project<<<grid_for(sz.NE, 8, sms), TB, 0, st>>>(d); n_launches += 1;
@@ -299,9 +306,21 @@ struct Pipeline {
         CK(cudaMemcpyAsync(h_npos.data(), d.ch_npos, C * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_tot_cells, d.tot_cells, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_err, d.err_flags, 4, cudaMemcpyDeviceToHost, st));
+        int32_t h_maxk = 0;
+        CK(cudaMemcpyAsync(&h_maxk, d_maxk, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        if (h_err & 4) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
         if (h_err & 1) throw ArgFail{"empty allele path"};
         if (h_err & 2) throw LimitFail{"a bubble has more than 15 alleles"};
+        if (h_err & 8) throw ArgFail{"entry_read out of range"};
+        if (h_err & 16) throw ArgFail{"stage_a_order is not a permutation"};
+        sz.max_k = h_maxk;
+        d.bits = sz.max_k <= 3 ? 2 : 4;
+    }
+
+    template <int BITS> void run_bits() {
+        cudaStream_t st = cx->stream; const int sms = cx->sms; const int64_t C = sz.C;
+        const int TB = 256;
         h_fused.assign(C, 0);
         h_frow_off.assign(C + 1, 0); h_pos_off.assign(C + 1, 0); h_code_off.assign(C, 0); h_cw_off.assign(C, 0); h_back_off.assign(C, 0); h_words.assign(C, 0);
         const int per_word = 32 / BITS;
@@ -427,7 +446,7 @@ struct Pipeline {
         CK(cudaGetLastError());
     }
 
-    void run() { if (d.bits == 2) run_bits<2>(); else run_bits<4>(); }
+    void run() { run_phase1(); if (d.bits == 2) run_bits<2>(); else run_bits<4>(); }
 
     void collect_times() {
         float t;
@@ -496,9 +515,23 @@ static void fill_empty_out(ahs_batch_out* out, Ctx* cx, int ploidy) {
 }
 
 // one batch on one device; iters > 0 = resident timing mode
+struct HostTrace {       // AHS_TRACE=1: wall-clock of the host-side steps of one call, on stderr
+    bool on; std::chrono::steady_clock::time_point t0; std::string line;
+    HostTrace() : on(getenv("AHS_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96]; snprintf(buf, sizeof buf, " %s=%.2fms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        line += buf; t0 = t1;
+    }
+    ~HostTrace() { if (on) fprintf(stderr, "[ahs trace]%s\n", line.c_str()); }
+};
+
 static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int device, int warmup, int iters) {
     if (!out) throw ArgFail{"null output"};
+    HostTrace tr;
     Sizes sz = validate(in);
+    tr.mark("validate");
     Ctx* cx = get_ctx(device);
     std::lock_guard<std::mutex> g(cx->mu);
     CK(cudaSetDevice(device));
@@ -510,6 +543,7 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     CK(cudaEventRecord(e0, cx->stream));
     pl.upload();
     CK(cudaEventRecord(e1, cx->stream));
+    tr.mark("upload_enqueue");
     pl.alloc_phase1();
     // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
     std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
@@ -518,7 +552,9 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     for (int it = 0; it < total; it++) {
         for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
         pl.run();
+        tr.mark("run_enqueue");
         CK(cudaStreamSynchronize(cx->stream));
+        tr.mark("run_sync");
         pl.collect_times();
         if (iters > 0 && it >= warmup) for (int i = 0; i < 8; i++) acc[i] += pl.ms[i];
     }
@@ -529,6 +565,7 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     CK(cudaEventRecord(d0, cx->stream));
     pl.download(out);
     CK(cudaEventRecord(e1, cx->stream)); CK(cudaEventSynchronize(e1));
+    tr.mark("download");
     float d2h = 0; CK(cudaEventElapsedTime(&d2h, d0, e1));
     out->ms_h2d = h2d; out->ms_project = pl.ms[0]; out->ms_rows = pl.ms[1]; out->ms_score = pl.ms[2]; out->ms_cluster = pl.ms[3];
     out->ms_consensus = pl.ms[4]; out->ms_thread = pl.ms[5]; out->ms_total_device = pl.ms[6]; out->ms_d2h = d2h;

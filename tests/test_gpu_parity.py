@@ -68,3 +68,42 @@ def test_four_bit_codes_diploid_many_alleles():
 def test_resident_mode_same_result():
     b = synth.generate(synth.params(2, 30, 1, 30, depth=30.0, seed=61))
     _check(b, resident_iters=2, warmup=1)
+
+
+def test_zero_copy_views_and_release():
+    b = synth.generate(synth.params(2, 20, 1, 20, depth=30.0, seed=81))
+    want = oracle_phase(b)
+    got = api.phase_batch(b, copy=False)
+    assert not got.diff(want)
+    # the output buffers are still owned by the library: a second call on the device must be refused ...
+    with pytest.raises(RuntimeError):
+        api.phase_batch(b)
+    got.release()
+    # ... and accepted again after the release
+    assert not api.phase_batch(b).diff(want)
+
+
+def _broken(b, **kw):
+    import copy
+    c = copy.copy(b)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def test_malformed_batches_are_rejected_not_mis_phased():
+    b = synth.generate(synth.params(2, 8, 1, 12, depth=20.0, seed=91))
+    er = b.entry_read.copy(); er[3] = 10 ** 6
+    with pytest.raises(RuntimeError, match="entry_read"):
+        api.phase_batch(_broken(b, entry_read=er))
+    ao = b.allele_off.copy(); ao[5], ao[6] = ao[6] + 1, ao[5]
+    with pytest.raises(RuntimeError, match="monotone"):
+        api.phase_batch(_broken(b, allele_off=ao))
+    so = b.stage_a_order.copy(); so[1] = so[0]
+    with pytest.raises(RuntimeError, match="permutation"):
+        api.phase_batch(_broken(b, stage_a_order=so))
+    eo = b.enode_off.copy(); eo[2] = eo[3] + 5
+    with pytest.raises(RuntimeError, match="monotone"):
+        api.phase_batch(_broken(b, enode_off=eo))
+    # the library is still usable afterwards
+    assert not api.phase_batch(b).diff(oracle_phase(b))

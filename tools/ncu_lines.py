@@ -36,7 +36,11 @@ def main():
         m = pat_ins.match(l)
         if m:
             seq.append(cur)
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], stdout=subprocess.PIPE, text=True).stdout
+    if rep.endswith(".csv"):      # `ncu -i x.ncu-rep --page source --csv --kernel-id :::N` exported on the GPU box
+        out = open(rep).read()
+    else:
+        ncu_kern = os.environ.get("NCU_KERNEL", kern)
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + ncu_kern], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(out.split("\n")))
     hi = [i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r]
     H = rows[hi[0]]

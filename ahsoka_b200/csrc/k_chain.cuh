@@ -1,27 +1,31 @@
-// k_chain.cuh — read-pair scoring FUSED with cluster editing, one thread block per chain, every
-// intermediate in shared memory.
+// k_chain.cuh — read-pair scoring FUSED with cluster editing, one thread block per chain.
 //
 // Replaces ReadScoring::scoreReadsetLocal + ClusterEditingSolver::run (call sites reference
 // src/alignmentstoreadset.cpp:308-315; algorithms: oracle/core/phase_core.hpp rules R1 and R2) for
 // chains with at most CC_MAXN final reads — every chain of BASELINE configs 2-4.  Larger chains take
 // the HBM-resident path (k_read_rates / k_pair_scores / k_cluster_edit).
 //
-// Per chain the block reads only the packed allele rows (code_bytes per cell) and 12 B of row
+// Per chain the block reads only the packed allele rows (code_bytes per cell) and 8 B of row
 // descriptors per read from HBM and writes 4 B of cluster label per read: the pair scores never
 // leave the SM ("fuse K2 into clustering input").
 //
-// Shared-memory layout for a class with at most nmax reads, tri = nmax(nmax-1)/2 pairs:
-//   W   int32[tri]    Q10 pair weight, upper triangle row-major; 0 = no edge, FORB = forbidden.
-//                     During scoring it holds (n << 16 | k): overlap and disagreement counts.
-//   FP  int2 [tri]    x = icf, y = icp of the pair (rule R2); the rate-sort scratch during scoring.
-//   cand u32 [tri]    live candidate pairs: (triangle index << 16) | (a << 8) | b, a < b.
-//   + O(nmax) vectors (first/last position, es/ed rates, merge lists, labels).
+// Where the state lives
+//   registers  every thread OWNS up to CC_PER read pairs ("slots"): key = (a << 8 | b), a < b, plus
+//              the pair's induced costs icf / icp (rule R2).  Scans for the best candidate and all
+//              induced-cost updates are register arithmetic by the owner; a slot only ever dies
+//              (merge / forbid) or is relabelled in place ((b,x) becomes (a,x) when b merges into a),
+//              so no list is ever appended to.
+//   shared     W[n][ns] int32, the symmetric weight matrix (0 = no edge, CC_FORB = forbidden), row
+//              stride ns odd -> conflict-free row AND column walks; per-node records of the current
+//              merge (old weights to a and b, merged weight), the fresh induced costs of the merged
+//              node's pairs, and per-node bit masks of the edges flagged in a forbid round.
 // int32 is exact: every weight and induced cost is bounded by the sum of |w| over the chain's pairs
-// <= tri * 2^17 < 2^31 for nmax <= 181.
+// <= 16290 * 2^17 < 2^31 for n <= 181.
 //
-// The greedy loop is sequential by definition (argmax -> merge or forbid); each step is spread over
-// the block: strided candidate scans with redux.sync reductions, one barrier per reduction.  Runs
-// of single-edge forbids are batched EXACTLY (see "round" below).
+// The greedy loop is sequential by definition (argmax -> merge or forbid).  One step = a few
+// barrier-separated passes in which every thread walks its own slots; the argmax of the next step
+// is folded into the last pass of the current one.  Runs of single-edge forbids are batched EXACTLY
+// (see "round" below).
 #pragma once
 #include "common.cuh"
 #include "device_batch.cuh"
@@ -29,377 +33,315 @@
 
 namespace ahs {
 
-constexpr int CC_MAXN = 176;
+constexpr int CC_MAXN = 128;
+constexpr int32_t CC_FORB = -0x7fffffff;          // forbidden edge inside this kernel (-CC_FORB is representable)
 constexpr uint32_t CC_DEAD = 0xffffffffu;
+constexpr uint32_t CC_POS = 1u << 16;             // slot flag: weight > 0
+constexpr uint32_t CC_FLAG = 1u << 17;            // slot flag: edge is part of the tentative forbid round
 
-__host__ __device__ inline int cc_flist_cap(int nmax) { return 4 * nmax; }
+__host__ __device__ inline int cc_ns(int nmax) { return nmax | 1; }
+__host__ __device__ inline int cc_mw(int nmax) { return (nmax + 31) / 32; }
 
 __host__ __device__ inline size_t cc_smem_bytes(int nmax, int nthreads) {
-    const size_t tri = (size_t)nmax * (nmax - 1) / 2;
-    size_t b = tri * 16;                                  // W, FP, cand
-    b += (size_t)nmax * (4 * 5);                          // first, last, wa, wb, nw
-    b += (size_t)nmax * (2 * 2);                          // es, ed
-    b += (size_t)cc_flist_cap(nmax) * 8;                  // flagged (cand entry, old weight)
-    b += (size_t)nmax * 4;                                // list, posS, label, active (u8 each)
+    size_t b = (size_t)nmax * cc_ns(nmax) * 4 * 2;        // W, D
+    b += (size_t)nmax * 16;                               // node records {wa, wb, nw, -}
+    b += (size_t)nmax * 4 * 4;                            // frF, frP, first, last
+    b += (size_t)nmax * cc_mw(nmax) * 4;                  // fmask
     b += (size_t)(nthreads / 32) * 8 * 4 * 2;             // reduction scratch, double buffered
     b += 64;                                              // scalars
+    b += (size_t)nmax * 2 * 2;                            // es, ed
+    b += (size_t)nmax * 5;                                // alist, apos, label, active, nodefl (u8 each)
     return (b + 15) & ~(size_t)15;
-}
-
-struct CC {
-    int n, tri;
-    int32_t* W; int2* FP; uint32_t* cand;
-    int32_t *first, *last, *wa, *wb, *nw;
-    uint16_t *es, *ed;
-    uint32_t* fl_c; int32_t* fl_old;
-    uint8_t *list, *posS, *label, *active;
-    int32_t* red; int32_t* scal;      // scal[0] = ncand, [1] = nflag / list count, [2] = pair count
-    __device__ __forceinline__ int T(int x, int y) const { return ((x * (2 * n - x - 3)) >> 1) + y - 1; }     // x < y
-    __device__ __forceinline__ int TT(int x, int y) const { return x < y ? T(x, y) : T(y, x); }
-    __device__ __forceinline__ int w(int x, int y) const { return W[TT(x, y)]; }
-};
-
-struct CCScan { int M, kF, maxP, kP, maxPpos, live; };
-
-// max icf (M, ties -> smallest pair key), max icp (same tie rule), max icp over positive-weight
-// candidates, number of live candidates.  Every thread returns the same values.
-template <int NT>
-__device__ __forceinline__ CCScan cc_scan(const CC& s, int tid, int& phase) {
-    constexpr int NW = NT / 32;
-    int bf = -1, kf = 0xffff, bp = -1, kp = 0xffff, bpp = -1, live = 0;
-    const int ncand = s.scal[0];
-    for (int i = tid; i < ncand; i += NT) {
-        const uint32_t c = s.cand[i];
-        const int ti = (int)(c >> 16), key = (int)(c & 0xffffu);
-        const int w = s.W[ti];
-        if (w == 0 || w == FORB) continue;
-        const int2 fp = s.FP[ti];
-        live++;
-        if (fp.x > bf || (fp.x == bf && key < kf)) { bf = fp.x; kf = key; }
-        if (fp.y > bp || (fp.y == bp && key < kp)) { bp = fp.y; kp = key; }
-        if (w > 0 && fp.y > bpp) bpp = fp.y;
-    }
-    const int mf = __reduce_max_sync(0xffffffffu, bf);
-    const int mkf = __reduce_min_sync(0xffffffffu, bf == mf ? kf : 0xffff);
-    const int mp = __reduce_max_sync(0xffffffffu, bp);
-    const int mkp = __reduce_min_sync(0xffffffffu, bp == mp ? kp : 0xffff);
-    const int mpp = __reduce_max_sync(0xffffffffu, bpp);
-    const int lv = __reduce_add_sync(0xffffffffu, live);
-    CCScan o;
-    if (NW == 1) { o.M = mf; o.kF = mkf; o.maxP = mp; o.kP = mkp; o.maxPpos = mpp; o.live = lv; __syncwarp(); return o; }
-    int32_t* r = s.red + phase * (NW * 8);
-    if ((tid & 31) == 0) { int32_t* q = r + (tid >> 5) * 8; q[0] = mf; q[1] = mkf; q[2] = mp; q[3] = mkp; q[4] = mpp; q[5] = lv; }
-    __syncthreads();
-    o.M = -1; o.kF = 0xffff; o.maxP = -1; o.kP = 0xffff; o.maxPpos = -1; o.live = 0;
-#pragma unroll
-    for (int wv = 0; wv < NW; wv++) {
-        const int32_t* q = r + wv * 8;
-        const int a = q[0], ka = q[1], b = q[2], kb = q[3];
-        if (a > o.M || (a == o.M && ka < o.kF)) { o.M = a; o.kF = ka; }
-        if (b > o.maxP || (b == o.maxP && kb < o.kP)) { o.maxP = b; o.kP = kb; }
-        o.maxPpos = max(o.maxPpos, q[4]); o.live += q[5];
-    }
-    phase ^= 1;
-    return o;
-}
-
-// in-place compaction of the candidate list (drops pairs whose weight became 0 or FORB)
-template <int NT, int MAXPER>
-__device__ __forceinline__ void cc_compact(const CC& s, int tid, int& phase) {
-    constexpr int NW = NT / 32;
-    const int ncand = s.scal[0];
-    const int lane = tid & 31, wid = tid >> 5;
-    const int chunk = (ncand + NW - 1) / NW, lo = wid * chunk, hi = min(ncand, lo + chunk);
-    uint32_t keep[MAXPER]; int cnt = 0;
-#pragma unroll
-    for (int x = 0; x < MAXPER; x++) {
-        const int i = lo + x * 32 + lane;
-        uint32_t c = CC_DEAD;
-        if (i < hi) { c = s.cand[i]; const int w = s.W[c >> 16]; if (w == 0 || w == FORB) c = CC_DEAD; }
-        keep[x] = c;
-        cnt += __popc(__ballot_sync(0xffffffffu, c != CC_DEAD));
-    }
-    int32_t* r = s.red + phase * (NW * 8);
-    if (lane == 0) r[wid * 8 + 6] = cnt;
-    __syncthreads();                                        // all reads done, all counts visible
-    int base = 0, total = 0;
-#pragma unroll
-    for (int wv = 0; wv < NW; wv++) { const int v = r[wv * 8 + 6]; if (wv < wid) base += v; total += v; }
-#pragma unroll
-    for (int x = 0; x < MAXPER; x++) {
-        const uint32_t c = keep[x];
-        const unsigned m = __ballot_sync(0xffffffffu, c != CC_DEAD);
-        if (c != CC_DEAD) s.cand[base + __popc(m & ((1u << lane) - 1u))] = c;
-        base += __popc(m);
-    }
-    if (tid == 0) s.scal[0] = total;
-    phase ^= 1;
-    __syncthreads();
 }
 
 __device__ __forceinline__ unsigned long long cc_globaltimer() {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
 }
-__device__ __forceinline__ int cc_tf(int x, int y) { return (x > 0 && y > 0) ? min(x, y) : 0; }
-__device__ __forceinline__ int cc_tp(int x, int y) {
-    if (x > 0 && y < 0) return y == FORB ? x : min(x, -y);
-    if (x < 0 && y > 0) return x == FORB ? y : min(-x, y);
-    return 0;
+// tf(x,y) = min(x,y) if both positive else 0;  tp(x,y) = min(pos, |neg|) if the signs differ else 0  (rule R2)
+__device__ __forceinline__ int cc_tf(int x, int y) { return max(min(x, y), 0); }
+__device__ __forceinline__ int cc_tp(int x, int y) { const int lo = min(x, y), hi = max(x, y); return max(min(hi, -lo), 0); }
+
+struct CCBest {          // running argmax of one thread / of the block
+    int M, kF, maxP, kP, maxPpos;
+    __device__ __forceinline__ void clear() { M = -1; kF = 0xffff; maxP = -1; kP = 0xffff; maxPpos = -1; }
+    __device__ __forceinline__ void consider(uint32_t key, int f, int p) {
+        const int kq = (int)(key & 0xffffu);
+        if (f > M || (f == M && kq < kF)) { M = f; kF = kq; }
+        if (p > maxP || (p == maxP && kq < kP)) { maxP = p; kP = kq; }
+        if ((key & CC_POS) && p > maxPpos) maxPpos = p;
+    }
+};
+
+// block-wide combination: largest value first, smallest pair key (a,b) on ties.  Contains one barrier.
+__device__ __forceinline__ CCBest cc_warp_best(const CCBest& b) {
+    CCBest o;
+    o.M = __reduce_max_sync(0xffffffffu, b.M);
+    o.kF = __reduce_min_sync(0xffffffffu, b.M == o.M ? b.kF : 0xffff);
+    o.maxP = __reduce_max_sync(0xffffffffu, b.maxP);
+    o.kP = __reduce_min_sync(0xffffffffu, b.maxP == o.maxP ? b.kP : 0xffff);
+    o.maxPpos = __reduce_max_sync(0xffffffffu, b.maxPpos);
+    return o;
+}
+template <int NT>
+__device__ __forceinline__ CCBest cc_reduce(const CCBest& b, int32_t* red, int tid, int& phase) {
+    constexpr int NW = NT / 32;
+    CCBest w = cc_warp_best(b);
+    if (NW == 1) { __syncthreads(); return w; }
+    int32_t* r = red + phase * (NW * 8);
+    if ((tid & 31) == 0) { int32_t* q = r + (tid >> 5) * 8; q[0] = w.M; q[1] = w.kF; q[2] = w.maxP; q[3] = w.kP; q[4] = w.maxPpos; }
+    __syncthreads();
+    const int lane = tid & 31;
+    CCBest o; o.clear();
+    if (lane < NW) { const int32_t* q = r + lane * 8; o.M = q[0]; o.kF = q[1]; o.maxP = q[2]; o.kP = q[3]; o.maxPpos = q[4]; }
+    phase ^= 1;
+    return cc_warp_best(o);
 }
 
-template <int BITS, int NT, int MAXPER>
-__global__ void __launch_bounds__(NT) k_score_cluster(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
-                                                       int32_t* __restrict__ work_counter) {
+// resident blocks per SM the register allocation is held to (~64 registers per thread: 24 of them are the slots)
+__host__ __device__ constexpr int cc_min_blocks(int nt, int per) {
+    // registers per thread ~ 40 + 3 per slot
+    return per <= 4 ? (nt <= 32 ? 32 : nt <= 64 ? 20 : nt <= 128 ? 10 : nt <= 192 ? 6 : nt <= 256 ? 5 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1)
+                    : (nt <= 32 ? 24 : nt <= 64 ? 16 : nt <= 96 ? 10 : nt <= 128 ? 8 : nt <= 192 ? 5 : nt <= 256 ? 4 : nt <= 512 ? 2 : 1);
+}
+
+template <int BITS, int NT, int KPL, int PER>
+__global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
+                                                                         int32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char cc_sm[];
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const int tri_max = nmax * (nmax - 1) / 2;
-    CC s;
+    const int ns = cc_ns(nmax), mw = cc_mw(nmax);
+    int32_t *W, *D; int4* node; int32_t *frF, *frP, *first, *last; uint32_t* fmask; int32_t *red, *scal; uint16_t *es, *ed;
+    uint8_t *alist, *apos, *label, *active, *nodefl;
     {
         unsigned char* p = cc_sm;
-        s.FP = (int2*)p; p += (size_t)tri_max * 8;
-        s.W = (int32_t*)p; p += (size_t)tri_max * 4;
-        s.cand = (uint32_t*)p; p += (size_t)tri_max * 4;
-        s.first = (int32_t*)p; p += nmax * 4; s.last = (int32_t*)p; p += nmax * 4;
-        s.wa = (int32_t*)p; p += nmax * 4; s.wb = (int32_t*)p; p += nmax * 4; s.nw = (int32_t*)p; p += nmax * 4;
-        s.fl_c = (uint32_t*)p; p += cc_flist_cap(nmax) * 4; s.fl_old = (int32_t*)p; p += cc_flist_cap(nmax) * 4;
-        s.red = (int32_t*)p; p += NW * 8 * 4 * 2;
-        s.scal = (int32_t*)p; p += 64;
-        s.es = (uint16_t*)p; p += nmax * 2; s.ed = (uint16_t*)p; p += nmax * 2;
-        s.list = p; p += nmax; s.posS = p; p += nmax; s.label = p; p += nmax; s.active = p; p += nmax;
+        node = (int4*)p; p += (size_t)nmax * 16;
+        W = (int32_t*)p; p += (size_t)nmax * ns * 4;
+        D = (int32_t*)p; p += (size_t)nmax * ns * 4;
+        frF = (int32_t*)p; p += nmax * 4; frP = (int32_t*)p; p += nmax * 4;
+        first = (int32_t*)p; p += nmax * 4; last = (int32_t*)p; p += nmax * 4;
+        fmask = (uint32_t*)p; p += (size_t)nmax * mw * 4;
+        red = (int32_t*)p; p += NW * 8 * 4 * 2;
+        scal = (int32_t*)p; p += 64;                  // [0] active nodes, [1] edges flagged in the round, [3] work item
+        es = (uint16_t*)p; p += nmax * 2; ed = (uint16_t*)p; p += nmax * 2;
+        alist = p; p += nmax; apos = p; p += nmax; label = p; p += nmax; active = p; p += nmax; nodefl = p; p += nmax;
     }
-    const int FL_CAP = cc_flist_cap(nmax);
     int phase = 0;
     int64_t pairs_total = 0;
     unsigned long long t_score = 0, t_cluster = 0;      // thread 0: nanoseconds spent in the two halves (globaltimer)
+    uint32_t key[PER]; int F[PER], P[PER];
     while (true) {
         __syncthreads();
-        if (tid == 0) s.scal[3] = atomicAdd(work_counter, 1);
+        if (tid == 0) scal[3] = atomicAdd(work_counter, 1);
         __syncthreads();
-        const int item = s.scal[3];
+        const int item = scal[3];
         if (item >= n_list) break;
         const int c = chains[item];
         const int64_t f0 = d.frow_off[c];
         const int n = (int)(d.frow_off[c + 1] - f0);
-        s.n = n; s.tri = n * (n - 1) / 2;
-        const int tri = s.tri;
+        const int tri = n * (n - 1) / 2;
         const int words = d.ch_words[c];
+        const uint32_t* rows = d.codes + d.code_off[c];
         unsigned long long t_start = 0;
         if (tid == 0) t_start = cc_globaltimer();
-        const uint32_t* rows = d.codes + d.code_off[c];
         // ================================================================ scoring (rule R1)
-        for (int x = tid; x < n; x += NT) { s.first[x] = d.fr_first[f0 + x]; s.last[x] = d.fr_last[f0 + x]; s.active[x] = 1; s.label[x] = (uint8_t)x; }
-        for (int x = tid; x < tri; x += NT) s.W[x] = 0;
-        if (tid == 0) { s.scal[0] = 0; s.scal[2] = 0; s.scal[4] = 0; }
+        for (int x = tid; x < n; x += NT) {
+            first[x] = d.fr_first[f0 + x]; last[x] = d.fr_last[f0 + x];
+            active[x] = 1; label[x] = (uint8_t)x; alist[x] = (uint8_t)x; apos[x] = (uint8_t)x; nodefl[x] = 0;
+            W[x * ns + x] = 0;
+            for (int m = 0; m < mw; m++) fmask[x * mw + m] = 0;
+        }
+        if (tid == 0) { scal[0] = n; scal[1] = 0; }
         __syncthreads();
-        // overlap / disagreement counts, once per pair: warp per row, lanes over later reads of the band
-        for (int i = wid; i < n - 1; i += NW) {
-            const int first_i = s.first[i], last_i = s.last[i];
-            const uint32_t* ri = rows + (int64_t)i * words;
-            const int rowbase = s.T(i, 0);
-            for (int j0 = i + 1; j0 < n; j0 += 32) {
-                const int j = j0 + lane;
-                const bool valid = j < n && s.first[j] <= last_i;
-                if (valid) {
-                    int nn, kk; pair_nk<BITS>(ri, rows + (int64_t)j * words, max(first_i, s.first[j]), min(last_i, s.last[j]), nn, kk);
-                    if (nn > 0) s.W[rowbase + j] = (nn << 16) | kk;
+        // pair (x0,y0) = pair number tid of the row-major upper triangle (row x starts at x(2n-x-1)/2); pair number
+        // tid + k NT is reached by stepping NT places along the rows
+        int x0 = 0, y0 = 1;
+        if (tid < tri) {
+            const float tn = (float)(2 * n - 1);
+            int x = (int)((tn - sqrtf(tn * tn - 8.0f * (float)tid)) * 0.5f);
+            x = max(0, min(x, n - 2));
+            while (x > 0 && ((x * (2 * n - x - 1)) >> 1) > tid) x--;
+            while ((((x + 1) * (2 * n - x - 2)) >> 1) <= tid) x++;
+            x0 = x; y0 = x + 1 + tid - ((x * (2 * n - x - 1)) >> 1);
+        }
+        // overlap / disagreement counts, once per pair; W holds (n << 16 | k) for now
+        {
+            int x = x0, y = y0;
+            for (int ti = tid; ti < tri; ti += NT) {
+                int nk = 0;
+                if (first[y] <= last[x]) {                               // reads are sorted by first position
+                    int nn, kk; pair_nk<BITS>(rows + (int64_t)x * words, rows + (int64_t)y * words, first[y], min(last[x], last[y]), nn, kk);
+                    if (nn > 0) nk = (nn << 16) | kk;
                 }
-                if (!__any_sync(0xffffffffu, valid)) break;          // reads are sorted by first position
+                W[x * ns + y] = nk; W[y * ns + x] = nk;
+                if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
             }
         }
         __syncthreads();
-        // local rates per read: partners ordered by Hamming rate, pooled same / different rates
+        // local rates per read (one warp per read): the partners' Hamming rates are ranked by counting, the
+        // cut = max(1, m/p) lowest are pooled as same-haplotype pairs, the rest as different-haplotype pairs
         {
-            uint64_t* keys = (uint64_t*)s.FP + (size_t)wid * (tri / NW);     // tri/NW >= pow2(n-1) is checked on the host
             int pl = 0;
             for (int i = wid; i < n; i += NW) {
+                uint64_t kk[KPL]; int rank[KPL];
                 int m = 0;
-                for (int j0 = 0; j0 < n; j0 += 32) {
-                    const int j = j0 + lane;
-                    const int nk = (j < n && j != i) ? s.W[s.TT(i, j)] : 0;
-                    const unsigned bal = __ballot_sync(0xffffffffu, nk != 0);
-                    if (nk != 0) keys[m + __popc(bal & lt)] = rate_key(nk >> 16, nk & 0xffff);
-                    m += __popc(bal);
+#pragma unroll
+                for (int s = 0; s < KPL; s++) {
+                    const int j = s * 32 + lane;
+                    const int nk = j < n ? W[i * ns + j] : 0;
+                    kk[s] = nk ? rate_key(nk >> 16, nk & 0xffff) : ~0ull;
+                    rank[s] = 0;
+                    m += __popc(__ballot_sync(0xffffffffu, nk != 0));
                 }
-                int N = 1; while (N < m) N <<= 1;
-                for (int x = m + lane; x < N; x += 32) keys[x] = ~0ull;
-                __syncwarp();
-                for (int kk = 2; kk <= N; kk <<= 1)
-                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                        for (int x = lane; x < N; x += 32) {
-                            const int y = x ^ jj;
-                            if (y > x) {
-                                const uint64_t a = keys[x], b = keys[y];
-                                const bool up = (x & kk) == 0;
-                                if ((a > b) == up) { keys[x] = b; keys[y] = a; }
-                            }
-                        }
-                        __syncwarp();
-                    }
-                uint32_t es = 0, ed = 0;
+                uint32_t es_i = 0, ed_i = 0;
                 if (m > 0) {
-                    const int cut = max(1, m / d.ploidy);
-                    int64_t Ks = 0, Ns = 0, Kd = 0, Nd = 0;
-                    for (int x = lane; x < m; x += 32) {
-                        const uint64_t key = keys[x];
-                        const int64_t kk = (int64_t)(key & 0x7fff), nn = (int64_t)((key >> 15) & 0x7fff);
-                        if (x < cut) { Ks += kk; Ns += nn; } else { Kd += kk; Nd += nn; }
+#pragma unroll
+                    for (int s2 = 0; s2 < KPL; s2++) {
+                        const int qn = min(32, n - s2 * 32);
+                        for (int l2 = 0; l2 < qn; l2++) {
+                            const uint64_t bk = __shfl_sync(0xffffffffu, kk[s2], l2);
+                            const int q = s2 * 32 + l2;
+#pragma unroll
+                            for (int s = 0; s < KPL; s++) rank[s] += (bk < kk[s] || (bk == kk[s] && q < s * 32 + lane)) ? 1 : 0;
+                        }
                     }
-                    Ks = warp_sum_i64(Ks); Ns = warp_sum_i64(Ns); Kd = warp_sum_i64(Kd); Nd = warp_sum_i64(Nd);
-                    es = (uint32_t)((Ks * 1024 + Ns / 2) / Ns);
-                    ed = Nd > 0 ? (uint32_t)((Kd * 1024 + Nd / 2) / Nd) : es;
+                    const int cut = max(1, m / d.ploidy);
+                    int Ks = 0, Ns = 0, Kd = 0, Nd = 0;
+#pragma unroll
+                    for (int s = 0; s < KPL; s++) if (kk[s] != ~0ull) {
+                        const int kq = (int)(kk[s] & 0x7fff), nq = (int)((kk[s] >> 15) & 0x7fff);
+                        if (rank[s] < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
+                    }
+                    Ks = warp_sum_i32(Ks); Ns = warp_sum_i32(Ns); Kd = warp_sum_i32(Kd); Nd = warp_sum_i32(Nd);
+                    es_i = (uint32_t)(((int64_t)Ks * 1024 + Ns / 2) / Ns);
+                    ed_i = Nd > 0 ? (uint32_t)(((int64_t)Kd * 1024 + Nd / 2) / Nd) : es_i;
                 }
-                __syncwarp();
-                if (lane == 0) { s.es[i] = (uint16_t)es; s.ed[i] = (uint16_t)ed; }
+                if (lane == 0) { es[i] = (uint16_t)es_i; ed[i] = (uint16_t)ed_i; }
                 pl += m;
             }
             if (lane == 0) pairs_total += pl;
         }
         __syncthreads();
-        // pair weights (fixed-point log likelihood ratio) and the candidate list
-        for (int i = wid; i < n - 1; i += NW) {
-            const int rowbase = s.T(i, 0);
-            const int es_i = s.es[i], ed_i = s.ed[i];
-            for (int j0 = i + 1; j0 < n; j0 += 32) {
-                const int j = j0 + lane;
-                int w = 0, ti = 0;
-                if (j < n) {
-                    ti = rowbase + j;
-                    const int nk = s.W[ti];
-                    if (nk != 0) { w = pair_weight(d, nk >> 16, nk & 0xffff, es_i, ed_i, s.es[j], s.ed[j]); s.W[ti] = w; }
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, w != 0);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s.scal[0], __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (w != 0) s.cand[base + __popc(bal & lt)] = ((uint32_t)ti << 16) | (uint32_t)((i << 8) | j);
-                }
+        // pair weights (fixed-point log likelihood ratio)
+        {
+            int x = x0, y = y0;
+            for (int ti = tid; ti < tri; ti += NT) {
+                const int nk = W[x * ns + y];
+                if (nk != 0) { const int w = pair_weight(d, nk >> 16, nk & 0xffff, es[x], ed[x], es[y], ed[y]); W[x * ns + y] = w; W[y * ns + x] = w; }
+                if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
             }
         }
         __syncthreads();
         // ================================================================ cluster editing (rule R2)
         if (tid == 0) { const unsigned long long t1 = cc_globaltimer(); t_score += t1 - t_start; t_start = t1; }
-        // initial induced costs, one candidate per thread
+        CCBest mine; mine.clear();
+        // slots: thread tid owns the pairs number tid + k NT; initial induced costs (W[x][x] = 0 makes the third
+        // nodes t = x, y contribute nothing)
         {
-            const int ncand = s.scal[0];
-            for (int i = tid; i < ncand; i += NT) {
-                const uint32_t cd = s.cand[i];
-                const int ti = (int)(cd >> 16), x = (int)((cd >> 8) & 0xff), y = (int)(cd & 0xff);
-                const int w = s.W[ti];
-                int f = max(w, 0), p = max(-w, 0);
-                for (int t = 0; t < n; t++) {
-                    if (t == x || t == y) continue;
-                    const int wx = s.w(x, t); if (wx == 0) continue;
-                    const int wy = s.w(y, t);
-                    f += cc_tf(wx, wy); p += cc_tp(wx, wy);
+            int x = x0, y = y0;
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                key[k] = CC_DEAD; F[k] = 0; P[k] = 0;
+                if (k * NT + tid < tri) {
+                    const int32_t* rx = W + x * ns; const int32_t* ry = W + y * ns;
+                    const int w = rx[y];
+                    if (w != 0) {
+                        int f = max(w, 0), p = max(-w, 0);
+                        for (int t = 0; t < n; t++) { const int wx = rx[t], wy = ry[t]; f += cc_tf(wx, wy); p += cc_tp(wx, wy); }
+                        key[k] = (uint32_t)((x << 8) | y) | (w > 0 ? CC_POS : 0u); F[k] = f; P[k] = p;
+                        mine.consider(key[k], f, p);
+                    }
+                    if ((k + 1) * NT + tid < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
                 }
-                s.FP[ti] = make_int2(f, p);
             }
         }
-        __syncthreads();
+        CCBest so = cc_reduce<NT>(mine, red, tid, phase);
         bool force_single = false;
-        int n_at_compact = s.scal[0];
-        CCScan so = cc_scan<NT>(s, tid, phase);
         while (so.M >= 0) {
+            mine.clear();
             if (so.M >= so.maxP) {
                 // ------------------------------------------------ merge (a,b) into a
                 const int a = so.kF >> 8, b = so.kF & 0xff;
-                const int ncand = s.scal[0];           // read before anyone appends to the list below
-                if (tid == 0) s.scal[1] = 0;
+                for (int t = tid; t < n; t += NT) {
+                    int xa = W[a * ns + t], xb = W[b * ns + t];
+                    if (t == a || t == b) { xa = 0; xb = 0; }          // rows of inactive nodes are already zero
+                    const int nwv = (xa == CC_FORB || xb == CC_FORB) ? CC_FORB : xa + xb;
+                    node[t] = make_int4(xa, xb, nwv, 0);
+                    W[a * ns + t] = nwv; W[t * ns + a] = nwv; W[b * ns + t] = 0; W[t * ns + b] = 0;
+                    if (label[t] == b) label[t] = (uint8_t)a;
+                    if (t == b) {                                     // drop b from the list of active nodes
+                        active[b] = 0;
+                        const int nact = scal[0], pos = apos[b], lastn = alist[nact - 1];
+                        alist[pos] = (uint8_t)lastn; apos[lastn] = (uint8_t)pos; scal[0] = nact - 1;
+                    }
+                }
                 __syncthreads();
-                for (int t0 = wid * 32; t0 < n; t0 += NT) {
-                    const int t = t0 + lane;
-                    int xa = 0, xb = 0;
-                    if (t < n) { s.posS[t] = 0xff; if (s.active[t] && t != a && t != b) { xa = s.w(a, t); xb = s.w(b, t); } }
-                    const bool in = (xa != 0) || (xb != 0);
-                    const unsigned m = __ballot_sync(0xffffffffu, in);
-                    if (m) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&s.scal[1], __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (in) {
-                            const int pos = base + __popc(m & lt);
-                            s.list[pos] = (uint8_t)t; s.posS[t] = (uint8_t)pos;
-                            s.wa[pos] = xa; s.wb[pos] = xb; s.nw[pos] = (xa == FORB || xb == FORB) ? FORB : xa + xb;
+                // fresh induced costs of the pairs (a,x): one warp per x, lanes over the third nodes
+                {
+                    const int nact = scal[0];
+                    for (int xi = wid; xi < nact; xi += NW) {
+                        const int x = alist[xi];
+                        const int w = node[x].z;
+                        if (w == 0 || w == CC_FORB) continue;
+                        const int32_t* rx = W + x * ns;
+                        int f = 0, p = 0;
+                        for (int vi = lane; vi < nact; vi += 32) {
+                            const int v = alist[vi];
+                            const int t1 = node[v].z, t2 = rx[v];
+                            f += cc_tf(t1, t2); p += cc_tp(t1, t2);
                         }
+                        f = warp_sum_i32(f); p = warp_sum_i32(p);
+                        if (lane == 0) { frF[x] = f + max(w, 0); frP[x] = p + max(-w, 0); }
                     }
                 }
                 __syncthreads();
-                const int cnt = s.scal[1];
-                // candidate pairs inside S: the terms through a and b become one term through the merged node
-                for (int i = tid; i < ncand; i += NT) {
-                    const uint32_t cd = s.cand[i];
-                    const int x = (int)((cd >> 8) & 0xff), y = (int)(cd & 0xff);
-                    const int u = s.posS[x], v = s.posS[y];
-                    if (u == 0xff || v == 0xff) continue;
-                    const int ti = (int)(cd >> 16);
-                    const int w = s.W[ti];
-                    if (w == FORB || w == 0) continue;
-                    const int nu = s.nw[u], nv = s.nw[v], au = s.wa[u], av = s.wa[v], bu = s.wb[u], bv = s.wb[v];
-                    int2 fp = s.FP[ti];
-                    fp.x += cc_tf(nu, nv) - cc_tf(au, av) - cc_tf(bu, bv);
-                    fp.y += cc_tp(nu, nv) - cc_tp(au, av) - cc_tp(bu, bv);
-                    s.FP[ti] = fp;
-                }
-                // fresh induced costs of the pairs (a,x), x in S (their third nodes are exactly the members of S),
-                // new weights of rows a and b, new candidates
-                for (int u0 = wid * 32; u0 < cnt; u0 += NT) {
-                    const int u = u0 + lane;
-                    bool add = false; int x = 0, ti = 0;
-                    if (u < cnt) {
-                        x = s.list[u]; const int w = s.nw[u];
-                        ti = s.TT(a, x);
-                        if (w != 0 && w != FORB) {
-                            int f = max(w, 0), p = max(-w, 0);
-                            for (int v = 0; v < cnt; v++) if (v != u) { const int t1 = s.nw[v], t2 = s.w(x, s.list[v]); f += cc_tf(t1, t2); p += cc_tp(t1, t2); }
-                            s.FP[ti] = make_int2(f, p);
-                            add = s.wa[u] == 0;
-                        } else if (w == 0 && s.wa[u] != 0 && s.wa[u] != FORB) {
-                            s.scal[4] = 1;     // exact cancellation: the pair keeps a dead list entry that a later merge
-                        }                      // could revive next to a fresh one -> compact before that can happen
+                // every slot: pairs through a or b take the fresh costs (or die), all others swap the terms through
+                // a and b for the term through the merged node
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    const uint32_t kq = key[k];
+                    if (kq == CC_DEAD) continue;
+                    const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
+                    if (x == a || y == a || x == b || y == b) {
+                        // (a,o): continues with the merged weight; (b,o): takes over as (a,o) if a had no edge to o
+                        const bool thru_b = x == b || y == b;
+                        const int o = thru_b ? (x == b ? y : x) : (x == a ? y : x);
+                        const int4 no = node[o];                       // o == a or b: nw = 0 -> the slot of (a,b) dies
+                        if (no.z == 0 || no.z == CC_FORB || (thru_b && no.x != 0)) { key[k] = CC_DEAD; continue; }
+                        key[k] = (uint32_t)(a < o ? (a << 8) | o : (o << 8) | a) | (no.z > 0 ? CC_POS : 0u);
+                        F[k] = frF[o]; P[k] = frP[o];
+                    } else {
+                        const int4 nx = node[x], ny = node[y];
+                        F[k] += cc_tf(nx.z, ny.z) - cc_tf(nx.x, ny.x) - cc_tf(nx.y, ny.y);
+                        P[k] += cc_tp(nx.z, ny.z) - cc_tp(nx.x, ny.x) - cc_tp(nx.y, ny.y);
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, add);
-                    if (m) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&s.scal[0], __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (add) s.cand[base + __popc(m & lt)] = ((uint32_t)ti << 16) | (uint32_t)(a < x ? (a << 8) | x : (x << 8) | a);
-                    }
+                    mine.consider(key[k], F[k], P[k]);
                 }
-                __syncthreads();       // every read of the old rows a, b is done
-                for (int u = tid; u < cnt; u += NT) { const int x = s.list[u]; s.W[s.TT(a, x)] = s.nw[u]; s.W[s.TT(b, x)] = 0; }
-                for (int x = tid; x < n; x += NT) if (s.label[x] == b) s.label[x] = (uint8_t)a;
-                if (tid == 0) { s.W[s.T(a, b)] = 0; s.active[b] = 0; }
-                __syncthreads();
                 force_single = false;
-                so = cc_scan<NT>(s, tid, phase);
-                if (s.scal[4] || (so.live * 4 < n_at_compact * 3 && s.scal[0] > NT)) {
-                    __syncthreads();
-                    if (tid == 0) s.scal[4] = 0;
-                    cc_compact<NT, MAXPER>(s, tid, phase); n_at_compact = s.scal[0];
-                }
+                so = cc_reduce<NT>(mine, red, tid, phase);
             } else if (force_single || so.maxPpos > so.M) {
                 // ------------------------------------------------ one sequential forbid: the edge with the largest icp
-                const int a = so.kP >> 8, b = so.kP & 0xff, tab = s.T(a, b);
-                const int old = s.W[tab];
+                const int a = so.kP >> 8, b = so.kP & 0xff;
+                const int old = W[a * ns + b];
                 __syncthreads();
-                for (int t = tid; t < n; t += NT) {
-                    if (!s.active[t] || t == a || t == b) continue;
-                    const int ita = s.TT(t, a), itb = s.TT(t, b);
-                    const int ta = s.W[ita], tb = s.W[itb];
-                    if (ta != 0 && tb != 0) {
-                        int2 fa = s.FP[ita], fb = s.FP[itb];
-                        fa.x -= cc_tf(old, tb); fa.y += cc_tp(FORB, tb) - cc_tp(old, tb);        // pair (a,t), third node b
-                        fb.x -= cc_tf(old, ta); fb.y += cc_tp(FORB, ta) - cc_tp(old, ta);        // pair (b,t), third node a
-                        s.FP[ita] = fa; s.FP[itb] = fb;
+                if (tid == 0) { W[a * ns + b] = CC_FORB; W[b * ns + a] = CC_FORB; }
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    const uint32_t kq = key[k];
+                    if (kq == CC_DEAD) continue;
+                    const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
+                    if ((int)(kq & 0xffffu) == so.kP) { key[k] = CC_DEAD; continue; }
+                    int o = -1, third = 0;
+                    if (x == a || y == a) { o = x == a ? y : x; third = b; }          // pair (a,o), third node b
+                    else if (x == b || y == b) { o = x == b ? y : x; third = a; }     // pair (b,o), third node a
+                    if (o >= 0) {
+                        const int wt = W[o * ns + third];
+                        F[k] -= cc_tf(old, wt); P[k] += cc_tp(CC_FORB, wt) - cc_tp(old, wt);
                     }
+                    mine.consider(kq, F[k], P[k]);
                 }
-                if (tid == 0) s.W[tab] = FORB;
-                __syncthreads();
                 force_single = false;
-                so = cc_scan<NT>(s, tid, phase);
+                so = cc_reduce<NT>(mine, red, tid, phase);
             } else {
                 // ------------------------------------------------ round: forbid negative candidates with icp > M at once.
                 // Forbidding a negative edge changes no icf and only raises icp values, so every such edge stays
@@ -408,55 +350,79 @@ __global__ void __launch_bounds__(NT) k_score_cluster(DB d, const int32_t* __res
                 // checked on the state after the round (max icp over positive candidates <= new max icf); if it
                 // fails the round is undone and one sequential step is taken instead.
                 const int M = so.M;
-                if (tid == 0) s.scal[1] = 0;
+                int nfl = 0;
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    const uint32_t kq = key[k];
+                    if (kq == CC_DEAD || (kq & CC_POS) || P[k] <= M) continue;
+                    const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
+                    key[k] = kq | CC_FLAG; nfl++;
+                    atomicOr(&fmask[x * mw + (y >> 5)], 1u << (y & 31)); nodefl[x] = 1;
+                    atomicOr(&fmask[y * mw + (x >> 5)], 1u << (x & 31)); nodefl[y] = 1;
+                }
+                nfl = warp_sum_i32(nfl);
+                if (lane == 0 && nfl) atomicAdd(&scal[1], nfl);
                 __syncthreads();
-                const int ncand = s.scal[0];
-                for (int i = tid; i < ncand; i += NT) {
-                    const uint32_t cd = s.cand[i];
-                    const int ti = (int)(cd >> 16);
-                    const int w = s.W[ti];
-                    if (w < 0 && w != FORB && s.FP[ti].y > M) {
-                        const int pos = atomicAdd(&s.scal[1], 1);
-                        if (pos < FL_CAP) { s.fl_c[pos] = cd; s.fl_old[pos] = w; s.W[ti] = FORB; }
+                const int nflag = scal[1];
+                // D[x][t] = growth of icp(x,t) through the forbidden edges at x: the term through bb grows from
+                // min(|w_x,bb|, w_t,bb) to w_t,bb when w_t,bb > 0.  One warp per end node x, lanes over t.
+                for (int x = wid; x < n; x += NW) {
+                    if (!nodefl[x]) continue;
+                    const int32_t* rx = W + x * ns;
+                    for (int t = lane; t < n; t += 32) {
+                        const int32_t* rt = W + t * ns;
+                        int g = 0;
+                        for (int m = 0; m < mw; m++)
+                            for (uint32_t bits = fmask[x * mw + m]; bits; bits &= bits - 1) {
+                                const int bb = m * 32 + __ffs(bits) - 1;
+                                const int wtb = rt[bb];
+                                if (wtb > 0) g += max(wtb + rx[bb], 0);            // rx[bb] = weight of the forbidden edge < 0
+                            }
+                        D[x * ns + t] = g;
                     }
                 }
                 __syncthreads();
-                const int nflag = min(s.scal[1], FL_CAP);
-                for (int sign = 1; ; sign = -1) {
-                    for (int idx = tid; idx < nflag * n; idx += NT) {
-                        const int e = idx / n, t = idx - e * n;
-                        const uint32_t cd = s.fl_c[e];
-                        const int a = (int)((cd >> 8) & 0xff), b = (int)(cd & 0xff), old = s.fl_old[e];
-                        if (!s.active[t] || t == a || t == b) continue;
-                        const int ita = s.TT(t, a), itb = s.TT(t, b);
-                        const int ta = s.W[ita], tb = s.W[itb];
-                        if (ta != 0 && tb != 0) {
-                            const int da = cc_tp(FORB, tb) - cc_tp(old, tb), db = cc_tp(FORB, ta) - cc_tp(old, ta);
-                            if (da) atomicAdd(&s.FP[ita].y, sign * da);
-                            if (db) atomicAdd(&s.FP[itb].y, sign * db);
-                        }
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    const uint32_t kq = key[k];
+                    if (kq == CC_DEAD || (kq & CC_FLAG)) continue;
+                    const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
+                    if (nodefl[x]) P[k] += D[x * ns + y];
+                    if (nodefl[y]) P[k] += D[y * ns + x];
+                    mine.consider(kq, F[k], P[k]);
+                }
+                const CCBest v = cc_reduce<NT>(mine, red, tid, phase);
+                const bool ok = nflag == 1 || v.maxPpos < 0 || v.M < 0 || v.maxPpos <= v.M;
+                if (ok) so = v; else force_single = true;      // not ok: undo, then one sequential step on the unchanged `so`
+                // commit (weights -> forbidden, slots die) or roll back
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    const uint32_t kq = key[k];
+                    if (kq == CC_DEAD) continue;
+                    const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
+                    if (kq & CC_FLAG) {
+                        if (ok) { key[k] = CC_DEAD; W[x * ns + y] = CC_FORB; W[y * ns + x] = CC_FORB; }
+                        else key[k] = kq & ~CC_FLAG;
+                    } else if (!ok) {
+                        if (nodefl[x]) P[k] -= D[x * ns + y];
+                        if (nodefl[y]) P[k] -= D[y * ns + x];
                     }
-                    __syncthreads();
-                    if (sign < 0) break;
-                    const CCScan v = cc_scan<NT>(s, tid, phase);
-                    const bool ok = nflag == 1 || v.maxPpos < 0 || v.M < 0 || v.maxPpos <= v.M;
-                    if (ok) { so = v; break; }
-                    force_single = true;                   // undo below, then one sequential step on the unchanged `so`
                 }
-                if (force_single) {
-                    for (int e = tid; e < nflag; e += NT) s.W[s.fl_c[e] >> 16] = s.fl_old[e];
-                    __syncthreads();
-                }
+                __syncthreads();                               // every thread is done with the masks
+                for (int x = tid; x < n; x += NT) if (nodefl[x]) { nodefl[x] = 0; for (int m = 0; m < mw; m++) fmask[x * mw + m] = 0; }
+                if (tid == 0) scal[1] = 0;
+                __syncthreads();
             }
         }
         // ---- clusters: numbered by smallest member (= representative), ascending
+        __syncthreads();
         for (int x = tid; x < n; x += NT) {
-            const int rep = s.label[x];
+            const int rep = label[x];
             int cid = 0;
-            for (int y = 0; y < rep; y++) cid += s.active[y];
+            for (int y = 0; y < rep; y++) cid += active[y];
             d.fr_cluster[f0 + x] = cid;
         }
-        if (tid == 0) { int k = 0; for (int y = 0; y < n; y++) k += s.active[y]; d.ch_nclusters[c] = k; t_cluster += cc_globaltimer() - t_start; }
+        if (tid == 0) { d.ch_nclusters[c] = scal[0]; t_cluster += cc_globaltimer() - t_start; }
     }
     if (lane == 0 && pairs_total) atomicAdd((unsigned long long*)d.tot_pairs, (unsigned long long)pairs_total);
     if (tid == 0) { atomicAdd(d.t_phase, t_score); atomicAdd(d.t_phase + 1, t_cluster); }

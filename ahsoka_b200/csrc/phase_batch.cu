@@ -69,39 +69,36 @@ static Ctx* g_ctx[64] = {nullptr};
 
 // ------------------------------------------------------------------ fused scoring + cluster editing: size classes
 // A class = (largest n, threads per block).  The block size grows with the pair triangle so that every thread owns
-// at most CC_MAXPER candidate pairs; the shared-memory slot (16 B per pair) decides how many chains an SM holds.
-constexpr int CC_MAXPER = 20;
-struct FusedClass { int nmax, nt; };
-static const FusedClass kFused[] = {{16, 32}, {24, 32}, {30, 32}, {36, 32}, {44, 64}, {51, 64}, {58, 128}, {65, 128}, {72, 128},
-                                    {86, 256}, {101, 256}, {120, 512}, {143, 512}, {166, 1024}};
+// at most CC_PER pair slots; the shared-memory footprint (the n x n weight matrix) is sized by the class's largest n.
+struct FusedClass { int nmax, nt, per; };
+// 4 slots per thread up to 91 reads (tri <= 4 * 1024), 8 slots per thread up to 128 reads
+static const FusedClass kFused[] = {{16, 32, 8}, {23, 32, 8}, {28, 64, 8}, {32, 64, 8}, {36, 96, 8}, {39, 96, 8}, {42, 128, 8}, {45, 128, 8},
+                                    {50, 192, 8}, {55, 192, 8}, {60, 256, 8}, {64, 256, 8}, {71, 384, 8}, {78, 384, 8}, {85, 512, 8}, {91, 512, 8},
+                                    {101, 768, 8}, {111, 768, 8}, {120, 1024, 8}, {128, 1024, 8}};
 constexpr int N_FUSED = (int)(sizeof(kFused) / sizeof(kFused[0]));
+// ceil(nmax / 32) of the largest class using (nt, per)
+constexpr int cc_kpl(int nt, int per) { return per == 8 ? (nt <= 64 ? 1 : nt <= 256 ? 2 : nt <= 512 ? 3 : 4) : (nt <= 128 ? 1 : nt <= 512 ? 2 : 3); }
 
-template <int BITS, int NT> static void fused_attr(size_t optin) {
-    CK(cudaFuncSetAttribute(k_score_cluster<BITS, NT, CC_MAXPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
-}
+#define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8)
 static void fused_set_attributes(size_t optin) {
-    fused_attr<2, 32>(optin); fused_attr<2, 64>(optin); fused_attr<2, 128>(optin); fused_attr<2, 256>(optin); fused_attr<2, 512>(optin); fused_attr<2, 1024>(optin);
-    fused_attr<4, 32>(optin); fused_attr<4, 64>(optin); fused_attr<4, 128>(optin); fused_attr<4, 256>(optin); fused_attr<4, 512>(optin); fused_attr<4, 1024>(optin);
+#define X(NT, PER) CK(cudaFuncSetAttribute(k_score_cluster<2, NT, cc_kpl(NT, PER), PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
+                   CK(cudaFuncSetAttribute(k_score_cluster<4, NT, cc_kpl(NT, PER), PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+    AHS_FOR_EACH_NT(X)
+#undef X
 }
-template <int BITS> static void fused_launch(int nt, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
-    switch (nt) {
-        case 32:   k_score_cluster<BITS, 32, CC_MAXPER><<<grid, 32, smem, st>>>(d, list, len, nmax, counter); break;
-        case 64:   k_score_cluster<BITS, 64, CC_MAXPER><<<grid, 64, smem, st>>>(d, list, len, nmax, counter); break;
-        case 128:  k_score_cluster<BITS, 128, CC_MAXPER><<<grid, 128, smem, st>>>(d, list, len, nmax, counter); break;
-        case 256:  k_score_cluster<BITS, 256, CC_MAXPER><<<grid, 256, smem, st>>>(d, list, len, nmax, counter); break;
-        case 512:  k_score_cluster<BITS, 512, CC_MAXPER><<<grid, 512, smem, st>>>(d, list, len, nmax, counter); break;
-        default:   k_score_cluster<BITS, 1024, CC_MAXPER><<<grid, 1024, smem, st>>>(d, list, len, nmax, counter); break;
-    }
+template <int BITS> static void fused_launch(int nt, int per, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
+#define X(NT, PER) if (nt == NT && per == PER) { k_score_cluster<BITS, NT, cc_kpl(NT, PER), PER><<<grid, NT, smem, st>>>(d, list, len, nmax, counter); return; }
+    AHS_FOR_EACH_NT(X)
+#undef X
+    throw ArgFail{"fused_launch: no kernel for this block size"};
 }
 // class of a chain with n final reads, -1 = HBM-resident path
 static int fused_class(int n, size_t smem_optin) {
     for (int k = 0; k < N_FUSED; k++) {
         if (n > kFused[k].nmax) continue;
-        const int nw = kFused[k].nt / 32;
         if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) return -1;
-        if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)CC_MAXPER * kFused[k].nt) return -1;
-        int pw = 1; while (pw < n - 1) pw <<= 1;                       // rate-sort scratch per warp (k_chain.cuh)
-        if (n >= 2 && (n * (n - 1) / 2) / nw < pw) continue;
+        if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)kFused[k].per * kFused[k].nt) return -1;
+        if (kFused[k].nmax > 32 * cc_kpl(kFused[k].nt, kFused[k].per)) return -1;
         return k;
     }
     return -1;
@@ -397,9 +394,9 @@ struct Pipeline {
                 const int32_t* dl = up(fl[k].data(), (int64_t)fl[k].size());
                 const int len = (int)fl[k].size(), nt = kFused[k].nt;
                 const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
-                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(32, 2048 / nt), (228 * 1024) / (smem + 1024)));
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
                 const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-                fused_launch<BITS>(nt, grid, smem, st, d, dl, len, kFused[k].nmax, f_counters + k); n_launches += 1;
+                fused_launch<BITS>(nt, kFused[k].per, grid, smem, st, d, dl, len, kFused[k].nmax, f_counters + k); n_launches += 1;
             }
         }
         CK(cudaEventRecord(cx->ev[11], st));

@@ -1,14 +1,18 @@
-// k_chain.cuh — read-pair scoring FUSED with cluster editing, one thread block per chain.
+// k_chain.cuh — read-pair scoring and cluster editing out of shared memory, one thread block per chain.
 //
 // Replaces ReadScoring::scoreReadsetLocal + ClusterEditingSolver::run (call sites reference
 // src/alignmentstoreadset.cpp:308-315; algorithms: oracle/core/phase_core.hpp rules R1 and R2) for
-// chains with at most CC_MAXN final reads — every chain of BASELINE configs 2-4.  Larger chains take
+// chains with at most CC_MAXN final reads — every chain of BASELINE config 2.  Larger chains take
 // the HBM-resident path (k_read_rates / k_pair_scores / k_cluster_edit).
 //
-// Per chain the block reads only the packed allele rows (code_bytes per cell) and 8 B of row
-// descriptors per read from HBM and writes 4 B of cluster label per read: the pair scores never
-// leave the SM ("fuse K2 into clustering input").
+//   k_score_chain    K2: reads the packed allele rows (code_bytes per cell) + 8 B of row descriptors per
+//                    read, writes one int32 Q10 weight per read pair (upper triangle, row-major): exactly
+//                    the algorithmic traffic of SURVEY §8d.
+//   k_cluster_chain  reads those 4 B per pair once, writes 4 B of cluster label per read.
+// (Two kernels rather than one: the greedy loop of cluster editing is instruction-issue bound and its
+// code must stay inside the 32 KB L1.5 instruction cache; the pair weights cost 0.07 ms of HBM time.)
 //
+// k_cluster_chain:
 // Where the state lives
 //   registers  every thread OWNS up to CC_PER read pairs ("slots"): key = (a << 8 | b), a < b, plus
 //              the pair's induced costs icf / icp (rule R2).  Scans for the best candidate and all
@@ -35,9 +39,10 @@ namespace ahs {
 
 constexpr int CC_MAXN = 128;
 constexpr int32_t CC_FORB = -0x7fffffff;          // forbidden edge inside this kernel (-CC_FORB is representable)
-constexpr uint32_t CC_DEAD = 0xffffffffu;
-constexpr uint32_t CC_POS = 1u << 16;             // slot flag: weight > 0
-constexpr uint32_t CC_FLAG = 1u << 17;            // slot flag: edge is part of the tentative forbid round
+constexpr uint32_t CC_POS = 1u << 31;             // slot flag: weight > 0 (sign bit: see CCBest::consider)
+constexpr uint32_t CC_FLAG = 1u << 17;            // slot flag: edge was forbidden in a round (tentatively, then for good)
+constexpr uint32_t CC_DEAD = 1u << 18;            // slot flag: no candidate pair in this slot
+constexpr uint32_t CC_GONE = CC_FLAG | CC_DEAD;
 
 __host__ __device__ inline int cc_ns(int nmax) { return nmax | 1; }
 __host__ __device__ inline int cc_mw(int nmax) { return (nmax + 31) / 32; }
@@ -45,11 +50,10 @@ __host__ __device__ inline int cc_mw(int nmax) { return (nmax + 31) / 32; }
 __host__ __device__ inline size_t cc_smem_bytes(int nmax, int nthreads) {
     size_t b = (size_t)nmax * cc_ns(nmax) * 4 * 2;        // W, D
     b += (size_t)nmax * 16;                               // node records {wa, wb, nw, -}
-    b += (size_t)nmax * 4 * 4;                            // frF, frP, first, last
+    b += (size_t)nmax * 4 * 2;                            // frF, frP
     b += (size_t)nmax * cc_mw(nmax) * 4;                  // fmask
     b += (size_t)(nthreads / 32) * 8 * 4 * 2;             // reduction scratch, double buffered
     b += 64;                                              // scalars
-    b += (size_t)nmax * 2 * 2;                            // es, ed
     b += (size_t)nmax * 5;                                // alist, apos, label, active, nodefl (u8 each)
     return (b + 15) & ~(size_t)15;
 }
@@ -61,75 +65,97 @@ __device__ __forceinline__ unsigned long long cc_globaltimer() {
 __device__ __forceinline__ int cc_tf(int x, int y) { return max(min(x, y), 0); }
 __device__ __forceinline__ int cc_tp(int x, int y) { const int lo = min(x, y), hi = max(x, y); return max(min(hi, -lo), 0); }
 
-struct CCBest {          // running argmax of one thread / of the block
-    int M, kF, maxP, kP, maxPpos;
-    __device__ __forceinline__ void clear() { M = -1; kF = 0xffff; maxP = -1; kP = 0xffff; maxPpos = -1; }
+struct CCBest {          // running maxima of one thread / of the block: max icf, max icp, max icp over positive edges
+    int M, maxP, maxPpos;
+    __device__ __forceinline__ void clear() { M = -1; maxP = -1; maxPpos = -1; }
     __device__ __forceinline__ void consider(uint32_t key, int f, int p) {
-        const int kq = (int)(key & 0xffffu);
-        if (f > M || (f == M && kq < kF)) { M = f; kF = kq; }
-        if (p > maxP || (p == maxP && kq < kP)) { maxP = p; kP = kq; }
-        if ((key & CC_POS) && p > maxPpos) maxPpos = p;
+        M = max(M, f); maxP = max(maxP, p);
+        const int pos = (int)key >> 31;                 // all ones for a positive edge
+        maxPpos = max(maxPpos, (p & pos) | ~pos);       // p, or -1 for a negative edge
     }
 };
 
-// block-wide combination: largest value first, smallest pair key (a,b) on ties.  Contains one barrier.
-__device__ __forceinline__ CCBest cc_warp_best(const CCBest& b) {
-    CCBest o;
-    o.M = __reduce_max_sync(0xffffffffu, b.M);
-    o.kF = __reduce_min_sync(0xffffffffu, b.M == o.M ? b.kF : 0xffff);
-    o.maxP = __reduce_max_sync(0xffffffffu, b.maxP);
-    o.kP = __reduce_min_sync(0xffffffffu, b.maxP == o.maxP ? b.kP : 0xffff);
-    o.maxPpos = __reduce_max_sync(0xffffffffu, b.maxPpos);
-    return o;
-}
+// block-wide maxima.  Contains one barrier.
 template <int NT>
 __device__ __forceinline__ CCBest cc_reduce(const CCBest& b, int32_t* red, int tid, int& phase) {
     constexpr int NW = NT / 32;
-    CCBest w = cc_warp_best(b);
+    CCBest w;
+    w.M = __reduce_max_sync(0xffffffffu, b.M); w.maxP = __reduce_max_sync(0xffffffffu, b.maxP); w.maxPpos = __reduce_max_sync(0xffffffffu, b.maxPpos);
     if (NW == 1) { __syncthreads(); return w; }
-    int32_t* r = red + phase * (NW * 8);
-    if ((tid & 31) == 0) { int32_t* q = r + (tid >> 5) * 8; q[0] = w.M; q[1] = w.kF; q[2] = w.maxP; q[3] = w.kP; q[4] = w.maxPpos; }
+    int32_t* r = red + phase * (NW * 4);
+    if ((tid & 31) == 0) { int32_t* q = r + (tid >> 5) * 4; q[0] = w.M; q[1] = w.maxP; q[2] = w.maxPpos; }
     __syncthreads();
     const int lane = tid & 31;
     CCBest o; o.clear();
-    if (lane < NW) { const int32_t* q = r + lane * 8; o.M = q[0]; o.kF = q[1]; o.maxP = q[2]; o.kP = q[3]; o.maxPpos = q[4]; }
+    if (lane < NW) { const int32_t* q = r + lane * 4; o.M = q[0]; o.maxP = q[1]; o.maxPpos = q[2]; }
     phase ^= 1;
-    return cc_warp_best(o);
+    w.M = __reduce_max_sync(0xffffffffu, o.M); w.maxP = __reduce_max_sync(0xffffffffu, o.maxP); w.maxPpos = __reduce_max_sync(0xffffffffu, o.maxPpos);
+    return w;
 }
 
-// resident blocks per SM the register allocation is held to (~64 registers per thread: 24 of them are the slots)
-__host__ __device__ constexpr int cc_min_blocks(int nt, int per) {
-    // registers per thread ~ 40 + 3 per slot
-    return per <= 4 ? (nt <= 32 ? 32 : nt <= 64 ? 20 : nt <= 128 ? 10 : nt <= 192 ? 6 : nt <= 256 ? 5 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1)
-                    : (nt <= 32 ? 24 : nt <= 64 ? 16 : nt <= 96 ? 10 : nt <= 128 ? 8 : nt <= 192 ? 5 : nt <= 256 ? 4 : nt <= 512 ? 2 : 1);
+// smallest pair key (a << 8 | b) among the slots whose value equals the block maximum: the tie rule of rule R2.
+// `mine` = smallest matching key of this thread (0xffff if none).  Contains one barrier.
+__device__ __forceinline__ int cc_min_key(int mine, int32_t* cell, int tid, int& kphase) {
+    const int wmin = __reduce_min_sync(0xffffffffu, mine);
+    if ((tid & 31) == 0 && wmin < 0xffff) atomicMin(&cell[kphase], wmin);
+    if (tid == 0) cell[kphase ^ 1] = 0xffff;            // last read at least one barrier ago
+    __syncthreads();
+    const int r = cell[kphase];
+    kphase ^= 1;
+    return r;
 }
 
-template <int BITS, int NT, int KPL, int PER>
-__global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
-                                                                         int32_t* __restrict__ work_counter) {
+// shared-memory footprint of the scoring kernel
+__host__ __device__ inline size_t cs_smem_bytes(int nmax) {
+    return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15) & ~(size_t)15;
+}
+
+// ascending bitonic sort of 32*KPL 64-bit keys held KPL per lane (element e = s*32 + lane)
+template <int KPL>
+__device__ __forceinline__ void warp_sort_u64(uint64_t (&v)[KPL], int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= 32 * KPL; kk <<= 1) {
+#pragma unroll
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            if (jj >= 32) {
+#pragma unroll
+                for (int s = 0; s < KPL; s++) {
+                    if ((s & (jj >> 5)) == 0) {
+                        const int s2 = s | (jj >> 5);
+                        const bool up = ((s * 32) & kk) == 0;          // lane bits are below jj >= 32 <= kk/2
+                        const uint64_t a = v[s], b = v[s2];
+                        if ((a > b) == up) { v[s] = b; v[s2] = a; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < KPL; s++) {
+                    const bool up = ((s * 32 + lane) & kk) == 0;
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, v[s], jj);
+                    const bool keep_min = ((lane & jj) == 0) == up;
+                    v[s] = keep_min ? (other < v[s] ? other : v[s]) : (other > v[s] ? other : v[s]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: read-pair scoring of one chain per block (rule R1).  Wout[cw_off[c] + pair number] = Q10 weight,
+// pair number = position of (x,y), x < y, in the row-major upper triangle.
+// ------------------------------------------------------------------------------------------------
+template <int BITS, int NT, int KPL>
+__global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
+                                                    int32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char cc_sm[];
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ns = cc_ns(nmax), mw = cc_mw(nmax);
-    int32_t *W, *D; int4* node; int32_t *frF, *frP, *first, *last; uint32_t* fmask; int32_t *red, *scal; uint16_t *es, *ed;
-    uint8_t *alist, *apos, *label, *active, *nodefl;
-    {
-        unsigned char* p = cc_sm;
-        node = (int4*)p; p += (size_t)nmax * 16;
-        W = (int32_t*)p; p += (size_t)nmax * ns * 4;
-        D = (int32_t*)p; p += (size_t)nmax * ns * 4;
-        frF = (int32_t*)p; p += nmax * 4; frP = (int32_t*)p; p += nmax * 4;
-        first = (int32_t*)p; p += nmax * 4; last = (int32_t*)p; p += nmax * 4;
-        fmask = (uint32_t*)p; p += (size_t)nmax * mw * 4;
-        red = (int32_t*)p; p += NW * 8 * 4 * 2;
-        scal = (int32_t*)p; p += 64;                  // [0] active nodes, [1] edges flagged in the round, [3] work item
-        es = (uint16_t*)p; p += nmax * 2; ed = (uint16_t*)p; p += nmax * 2;
-        alist = p; p += nmax; apos = p; p += nmax; label = p; p += nmax; active = p; p += nmax; nodefl = p; p += nmax;
-    }
-    int phase = 0;
+    const int ns = cc_ns(nmax);
+    int32_t* W = (int32_t*)cc_sm;
+    int32_t* first = W + (size_t)nmax * ns; int32_t* last = first + nmax;
+    int32_t* scal = last + nmax;
+    uint16_t* es = (uint16_t*)(scal + 16); uint16_t* ed = es + nmax;
     int64_t pairs_total = 0;
-    unsigned long long t_score = 0, t_cluster = 0;      // thread 0: nanoseconds spent in the two halves (globaltimer)
-    uint32_t key[PER]; int F[PER], P[PER];
     while (true) {
         __syncthreads();
         if (tid == 0) scal[3] = atomicAdd(work_counter, 1);
@@ -142,19 +168,11 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
         const int tri = n * (n - 1) / 2;
         const int words = d.ch_words[c];
         const uint32_t* rows = d.codes + d.code_off[c];
-        unsigned long long t_start = 0;
-        if (tid == 0) t_start = cc_globaltimer();
-        // ================================================================ scoring (rule R1)
-        for (int x = tid; x < n; x += NT) {
-            first[x] = d.fr_first[f0 + x]; last[x] = d.fr_last[f0 + x];
-            active[x] = 1; label[x] = (uint8_t)x; alist[x] = (uint8_t)x; apos[x] = (uint8_t)x; nodefl[x] = 0;
-            W[x * ns + x] = 0;
-            for (int m = 0; m < mw; m++) fmask[x * mw + m] = 0;
-        }
-        if (tid == 0) { scal[0] = n; scal[1] = 0; }
+        int32_t* Wout = d.W + d.cw_off[c];
+        for (int x = tid; x < n; x += NT) { first[x] = d.fr_first[f0 + x]; last[x] = d.fr_last[f0 + x]; W[x * ns + x] = 0; }
         __syncthreads();
-        // pair (x0,y0) = pair number tid of the row-major upper triangle (row x starts at x(2n-x-1)/2); pair number
-        // tid + k NT is reached by stepping NT places along the rows
+        // pair (x0,y0) = pair number tid (row x of the triangle starts at x(2n-x-1)/2); pair number tid + k NT is
+        // reached by stepping NT places along the rows
         int x0 = 0, y0 = 1;
         if (tid < tri) {
             const float tn = (float)(2 * n - 1);
@@ -178,39 +196,29 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
             }
         }
         __syncthreads();
-        // local rates per read (one warp per read): the partners' Hamming rates are ranked by counting, the
+        // local rates per read (one warp per read): the partners' Hamming rates are sorted in registers, the
         // cut = max(1, m/p) lowest are pooled as same-haplotype pairs, the rest as different-haplotype pairs
         {
             int pl = 0;
             for (int i = wid; i < n; i += NW) {
-                uint64_t kk[KPL]; int rank[KPL];
+                uint64_t kk[KPL];
                 int m = 0;
 #pragma unroll
                 for (int s = 0; s < KPL; s++) {
                     const int j = s * 32 + lane;
                     const int nk = j < n ? W[i * ns + j] : 0;
                     kk[s] = nk ? rate_key(nk >> 16, nk & 0xffff) : ~0ull;
-                    rank[s] = 0;
                     m += __popc(__ballot_sync(0xffffffffu, nk != 0));
                 }
                 uint32_t es_i = 0, ed_i = 0;
                 if (m > 0) {
-#pragma unroll
-                    for (int s2 = 0; s2 < KPL; s2++) {
-                        const int qn = min(32, n - s2 * 32);
-                        for (int l2 = 0; l2 < qn; l2++) {
-                            const uint64_t bk = __shfl_sync(0xffffffffu, kk[s2], l2);
-                            const int q = s2 * 32 + l2;
-#pragma unroll
-                            for (int s = 0; s < KPL; s++) rank[s] += (bk < kk[s] || (bk == kk[s] && q < s * 32 + lane)) ? 1 : 0;
-                        }
-                    }
+                    warp_sort_u64<KPL>(kk, lane);
                     const int cut = max(1, m / d.ploidy);
                     int Ks = 0, Ns = 0, Kd = 0, Nd = 0;
 #pragma unroll
                     for (int s = 0; s < KPL; s++) if (kk[s] != ~0ull) {
                         const int kq = (int)(kk[s] & 0x7fff), nq = (int)((kk[s] >> 15) & 0x7fff);
-                        if (rank[s] < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
+                        if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
                     }
                     Ks = warp_sum_i32(Ks); Ns = warp_sum_i32(Ns); Kd = warp_sum_i32(Kd); Nd = warp_sum_i32(Nd);
                     es_i = (uint32_t)(((int64_t)Ks * 1024 + Ns / 2) / Ns);
@@ -222,36 +230,117 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
             if (lane == 0) pairs_total += pl;
         }
         __syncthreads();
-        // pair weights (fixed-point log likelihood ratio)
+        // pair weights (fixed-point log likelihood ratio), 4 B per pair to HBM
         {
             int x = x0, y = y0;
             for (int ti = tid; ti < tri; ti += NT) {
                 const int nk = W[x * ns + y];
-                if (nk != 0) { const int w = pair_weight(d, nk >> 16, nk & 0xffff, es[x], ed[x], es[y], ed[y]); W[x * ns + y] = w; W[y * ns + x] = w; }
+                Wout[ti] = nk ? pair_weight(d, nk >> 16, nk & 0xffff, es[x], ed[x], es[y], ed[y]) : 0;
+                if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
+            }
+        }
+    }
+    if (lane == 0 && pairs_total) atomicAdd((unsigned long long*)d.tot_pairs, (unsigned long long)pairs_total);
+}
+
+// resident blocks per SM the register allocation is held to (~64 registers per thread: 24 of them are the slots)
+__host__ __device__ constexpr int cc_min_blocks(int nt, int per) {
+    // registers per thread ~ 40 + 3 per slot
+    return per <= 4 ? (nt <= 32 ? 32 : nt <= 64 ? 20 : nt <= 128 ? 10 : nt <= 192 ? 6 : nt <= 256 ? 5 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1)
+                    : (nt <= 32 ? 24 : nt <= 64 ? 16 : nt <= 96 ? 10 : nt <= 128 ? 8 : nt <= 192 ? 5 : nt <= 256 ? 4 : nt <= 512 ? 2 : 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cluster editing of one chain per block (rule R2)
+// ------------------------------------------------------------------------------------------------
+template <int NT, int PER>
+__global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
+                                                                         int32_t* __restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char cc_sm[];
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ns = cc_ns(nmax), mw = cc_mw(nmax);
+    int32_t *W, *D; int4* node; int32_t *frF, *frP; uint32_t* fmask; int32_t *red, *scal;
+    uint8_t *alist, *apos, *label, *active, *nodefl;
+    {
+        unsigned char* p = cc_sm;
+        node = (int4*)p; p += (size_t)nmax * 16;
+        W = (int32_t*)p; p += (size_t)nmax * ns * 4;
+        D = (int32_t*)p; p += (size_t)nmax * ns * 4;
+        frF = (int32_t*)p; p += nmax * 4; frP = (int32_t*)p; p += nmax * 4;
+        fmask = (uint32_t*)p; p += (size_t)nmax * mw * 4;
+        red = (int32_t*)p; p += NW * 8 * 4 * 2;
+        scal = (int32_t*)p; p += 64;                  // [0] active nodes, [1] edges flagged in the round, [3] work item
+        alist = p; p += nmax; apos = p; p += nmax; label = p; p += nmax; active = p; p += nmax; nodefl = p; p += nmax;
+    }
+    int phase = 0, kphase = 0;
+    uint32_t key[PER]; int F[PER], P[PER];
+    while (true) {
+        __syncthreads();
+        if (tid == 0) scal[3] = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = scal[3];
+        if (item >= n_list) break;
+        const int c = chains[item];
+        const int64_t f0 = d.frow_off[c];
+        const int n = (int)(d.frow_off[c + 1] - f0);
+        const int tri = n * (n - 1) / 2;
+        const int32_t* Win = d.W + d.cw_off[c];
+        for (int x = tid; x < n; x += NT) {
+            active[x] = 1; label[x] = (uint8_t)x; alist[x] = (uint8_t)x; apos[x] = (uint8_t)x; nodefl[x] = 0;
+            W[x * ns + x] = 0;
+            for (int m = 0; m < mw; m++) fmask[x * mw + m] = 0;
+        }
+        if (tid == 0) { scal[0] = n; scal[1] = 0; scal[4] = 0xffff; scal[5] = 0xffff; kphase = 0; }
+        else kphase = 0;
+        int x0 = 0, y0 = 1;
+        if (tid < tri) {
+            const float tn = (float)(2 * n - 1);
+            int x = (int)((tn - sqrtf(tn * tn - 8.0f * (float)tid)) * 0.5f);
+            x = max(0, min(x, n - 2));
+            while (x > 0 && ((x * (2 * n - x - 1)) >> 1) > tid) x--;
+            while ((((x + 1) * (2 * n - x - 2)) >> 1) <= tid) x++;
+            x0 = x; y0 = x + 1 + tid - ((x * (2 * n - x - 1)) >> 1);
+        }
+        // weights: 4 B per pair from HBM into the symmetric matrix
+        {
+            int x = x0, y = y0;
+            for (int ti = tid; ti < tri; ti += NT) {
+                const int w = __ldg(Win + ti);
+                W[x * ns + y] = w; W[y * ns + x] = w;
                 if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
             }
         }
         __syncthreads();
-        // ================================================================ cluster editing (rule R2)
-        if (tid == 0) { const unsigned long long t1 = cc_globaltimer(); t_score += t1 - t_start; t_start = t1; }
+        // initial induced costs of the thread's own pairs (W[x][x] = 0 makes the third nodes t = x, y contribute
+        // nothing), parked in D so that this loop need not be unrolled over the register slots
+        {
+            int x = x0, y = y0;
+            for (int ti = tid; ti < tri; ti += NT) {
+                const int32_t* rx = W + x * ns; const int32_t* ry = W + y * ns;
+                const int w = rx[y];
+                if (w != 0) {
+                    int f = max(w, 0), p = max(-w, 0);
+                    for (int t = 0; t < n; t++) { const int wx = rx[t], wy = ry[t]; f += cc_tf(wx, wy); p += cc_tp(wx, wy); }
+                    D[ti] = f; D[tri + ti] = p;
+                }
+                if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
+            }
+        }
         CCBest mine; mine.clear();
-        // slots: thread tid owns the pairs number tid + k NT; initial induced costs (W[x][x] = 0 makes the third
-        // nodes t = x, y contribute nothing)
         {
             int x = x0, y = y0;
 #pragma unroll
             for (int k = 0; k < PER; k++) {
                 key[k] = CC_DEAD; F[k] = 0; P[k] = 0;
-                if (k * NT + tid < tri) {
-                    const int32_t* rx = W + x * ns; const int32_t* ry = W + y * ns;
-                    const int w = rx[y];
+                const int ti = k * NT + tid;
+                if (ti < tri) {
+                    const int w = W[x * ns + y];
                     if (w != 0) {
-                        int f = max(w, 0), p = max(-w, 0);
-                        for (int t = 0; t < n; t++) { const int wx = rx[t], wy = ry[t]; f += cc_tf(wx, wy); p += cc_tp(wx, wy); }
-                        key[k] = (uint32_t)((x << 8) | y) | (w > 0 ? CC_POS : 0u); F[k] = f; P[k] = p;
-                        mine.consider(key[k], f, p);
+                        key[k] = (uint32_t)((x << 8) | y) | (w > 0 ? CC_POS : 0u); F[k] = D[ti]; P[k] = D[tri + ti];
+                        mine.consider(key[k], F[k], P[k]);
                     }
-                    if ((k + 1) * NT + tid < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
+                    if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
                 }
             }
         }
@@ -260,8 +349,12 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
         while (so.M >= 0) {
             mine.clear();
             if (so.M >= so.maxP) {
-                // ------------------------------------------------ merge (a,b) into a
-                const int a = so.kF >> 8, b = so.kF & 0xff;
+                // ------------------------------------------------ merge (a,b) into a: the pair with the largest icf
+                int kmine = 0xffff;
+#pragma unroll
+                for (int k = 0; k < PER; k++) if (!(key[k] & CC_GONE) && F[k] == so.M) kmine = min(kmine, (int)(key[k] & 0xffffu));
+                const int kF = cc_min_key(kmine, scal + 4, tid, kphase);
+                const int a = kF >> 8, b = kF & 0xff;
                 for (int t = tid; t < n; t += NT) {
                     int xa = W[a * ns + t], xb = W[b * ns + t];
                     if (t == a || t == b) { xa = 0; xb = 0; }          // rows of inactive nodes are already zero
@@ -300,7 +393,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
                     const uint32_t kq = key[k];
-                    if (kq == CC_DEAD) continue;
+                    if (kq & CC_GONE) continue;
                     const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
                     if (x == a || y == a || x == b || y == b) {
                         // (a,o): continues with the merged weight; (b,o): takes over as (a,o) if a had no edge to o
@@ -321,16 +414,20 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
                 so = cc_reduce<NT>(mine, red, tid, phase);
             } else if (force_single || so.maxPpos > so.M) {
                 // ------------------------------------------------ one sequential forbid: the edge with the largest icp
-                const int a = so.kP >> 8, b = so.kP & 0xff;
+                int kmine = 0xffff;
+#pragma unroll
+                for (int k = 0; k < PER; k++) if (!(key[k] & CC_GONE) && P[k] == so.maxP) kmine = min(kmine, (int)(key[k] & 0xffffu));
+                const int kP = cc_min_key(kmine, scal + 4, tid, kphase);
+                const int a = kP >> 8, b = kP & 0xff;
                 const int old = W[a * ns + b];
                 __syncthreads();
                 if (tid == 0) { W[a * ns + b] = CC_FORB; W[b * ns + a] = CC_FORB; }
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
                     const uint32_t kq = key[k];
-                    if (kq == CC_DEAD) continue;
+                    if (kq & CC_GONE) continue;
                     const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
-                    if ((int)(kq & 0xffffu) == so.kP) { key[k] = CC_DEAD; continue; }
+                    if ((int)(kq & 0xffffu) == kP) { key[k] = CC_DEAD; continue; }
                     int o = -1, third = 0;
                     if (x == a || y == a) { o = x == a ? y : x; third = b; }          // pair (a,o), third node b
                     else if (x == b || y == b) { o = x == b ? y : x; third = a; }     // pair (b,o), third node a
@@ -350,11 +447,13 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
                 // checked on the state after the round (max icp over positive candidates <= new max icf); if it
                 // fails the round is undone and one sequential step is taken instead.
                 const int M = so.M;
+                __syncthreads();                               // the masks of the previous round are cleared
                 int nfl = 0;
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
                     const uint32_t kq = key[k];
-                    if (kq == CC_DEAD || (kq & CC_POS) || P[k] <= M) continue;
+                    if (kq & CC_FLAG) { key[k] = CC_DEAD; continue; }          // forbidden for good in an earlier round
+                    if ((kq & (CC_DEAD | CC_POS)) || P[k] <= M) continue;
                     const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
                     key[k] = kq | CC_FLAG; nfl++;
                     atomicOr(&fmask[x * mw + (y >> 5)], 1u << (y & 31)); nodefl[x] = 1;
@@ -382,36 +481,37 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
                     }
                 }
                 __syncthreads();
+                // the forbidden edges leave (their old weight is parked in D[x][y], which nobody else reads), the icp of
+                // the others grows
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
                     const uint32_t kq = key[k];
-                    if (kq == CC_DEAD || (kq & CC_FLAG)) continue;
+                    if (kq & CC_DEAD) continue;
                     const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
+                    if (kq & CC_FLAG) { D[x * ns + y] = W[x * ns + y]; W[x * ns + y] = CC_FORB; W[y * ns + x] = CC_FORB; continue; }
                     if (nodefl[x]) P[k] += D[x * ns + y];
                     if (nodefl[y]) P[k] += D[y * ns + x];
                     mine.consider(kq, F[k], P[k]);
                 }
                 const CCBest v = cc_reduce<NT>(mine, red, tid, phase);
                 const bool ok = nflag == 1 || v.maxPpos < 0 || v.M < 0 || v.maxPpos <= v.M;
-                if (ok) so = v; else force_single = true;      // not ok: undo, then one sequential step on the unchanged `so`
-                // commit (weights -> forbidden, slots die) or roll back
+                if (ok) so = v;
+                else {
+                    // roll back, then one sequential step on the unchanged `so`
+                    force_single = true;
 #pragma unroll
-                for (int k = 0; k < PER; k++) {
-                    const uint32_t kq = key[k];
-                    if (kq == CC_DEAD) continue;
-                    const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
-                    if (kq & CC_FLAG) {
-                        if (ok) { key[k] = CC_DEAD; W[x * ns + y] = CC_FORB; W[y * ns + x] = CC_FORB; }
-                        else key[k] = kq & ~CC_FLAG;
-                    } else if (!ok) {
+                    for (int k = 0; k < PER; k++) {
+                        const uint32_t kq = key[k];
+                        if (kq & CC_DEAD) continue;
+                        const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
+                        if (kq & CC_FLAG) { const int w = D[x * ns + y]; W[x * ns + y] = w; W[y * ns + x] = w; key[k] = kq & ~CC_FLAG; continue; }
                         if (nodefl[x]) P[k] -= D[x * ns + y];
                         if (nodefl[y]) P[k] -= D[y * ns + x];
                     }
+                    __syncthreads();                           // every thread is done with the masks
                 }
-                __syncthreads();                               // every thread is done with the masks
                 for (int x = tid; x < n; x += NT) if (nodefl[x]) { nodefl[x] = 0; for (int m = 0; m < mw; m++) fmask[x * mw + m] = 0; }
                 if (tid == 0) scal[1] = 0;
-                __syncthreads();
             }
         }
         // ---- clusters: numbered by smallest member (= representative), ascending
@@ -422,10 +522,8 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_score_cluster(DB
             for (int y = 0; y < rep; y++) cid += active[y];
             d.fr_cluster[f0 + x] = cid;
         }
-        if (tid == 0) { d.ch_nclusters[c] = scal[0]; t_cluster += cc_globaltimer() - t_start; }
+        if (tid == 0) d.ch_nclusters[c] = scal[0];
     }
-    if (lane == 0 && pairs_total) atomicAdd((unsigned long long*)d.tot_pairs, (unsigned long long)pairs_total);
-    if (tid == 0) { atomicAdd(d.t_phase, t_score); atomicAdd(d.t_phase + 1, t_cluster); }
 }
 
 }  // namespace ahs

@@ -67,38 +67,51 @@ struct Ctx {
 static std::mutex g_ctx_mu;
 static Ctx* g_ctx[64] = {nullptr};
 
-// ------------------------------------------------------------------ fused scoring + cluster editing: size classes
-// A class = (largest n, threads per block).  The block size grows with the pair triangle so that every thread owns
-// at most CC_PER pair slots; the shared-memory footprint (the n x n weight matrix) is sized by the class's largest n.
+// ------------------------------------------------------------------ shared-memory scoring + cluster editing: size classes
+// Cluster editing: a class = (largest n, threads per block, pair slots per thread).  The block size grows with the pair
+// triangle so that every thread owns at most `per` slots; the shared-memory footprint (two n x n int32 matrices) is
+// sized by the class's largest n.
 struct FusedClass { int nmax, nt, per; };
-// 4 slots per thread up to 91 reads (tri <= 4 * 1024), 8 slots per thread up to 128 reads
 static const FusedClass kFused[] = {{16, 32, 8}, {23, 32, 8}, {28, 64, 8}, {32, 64, 8}, {36, 96, 8}, {39, 96, 8}, {42, 128, 8}, {45, 128, 8},
                                     {50, 192, 8}, {55, 192, 8}, {60, 256, 8}, {64, 256, 8}, {71, 384, 8}, {78, 384, 8}, {85, 512, 8}, {91, 512, 8},
                                     {101, 768, 8}, {111, 768, 8}, {120, 1024, 8}, {128, 1024, 8}};
 constexpr int N_FUSED = (int)(sizeof(kFused) / sizeof(kFused[0]));
-// ceil(nmax / 32) of the largest class using (nt, per)
-constexpr int cc_kpl(int nt, int per) { return per == 8 ? (nt <= 64 ? 1 : nt <= 256 ? 2 : nt <= 512 ? 3 : 4) : (nt <= 128 ? 1 : nt <= 512 ? 2 : 3); }
+// Scoring: (largest n, threads per block, sort keys per lane)
+struct ScoreClass { int nmax, nt, kpl; };
+static const ScoreClass kScore[] = {{32, 64, 1}, {48, 128, 2}, {64, 128, 2}, {96, 256, 4}, {128, 256, 4}};
+constexpr int N_SCORE = (int)(sizeof(kScore) / sizeof(kScore[0]));
 
 #define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8)
+#define AHS_FOR_EACH_SC(X) X(64, 1) X(128, 2) X(256, 4)
 static void fused_set_attributes(size_t optin) {
-#define X(NT, PER) CK(cudaFuncSetAttribute(k_score_cluster<2, NT, cc_kpl(NT, PER), PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
-                   CK(cudaFuncSetAttribute(k_score_cluster<4, NT, cc_kpl(NT, PER), PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+#define X(NT, PER) CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
     AHS_FOR_EACH_NT(X)
 #undef X
+#define X(NT, KPL) CK(cudaFuncSetAttribute(k_score_chain<2, NT, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
+                   CK(cudaFuncSetAttribute(k_score_chain<4, NT, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+    AHS_FOR_EACH_SC(X)
+#undef X
 }
-template <int BITS> static void fused_launch(int nt, int per, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
-#define X(NT, PER) if (nt == NT && per == PER) { k_score_cluster<BITS, NT, cc_kpl(NT, PER), PER><<<grid, NT, smem, st>>>(d, list, len, nmax, counter); return; }
+static void cluster_launch(int nt, int per, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
+#define X(NT, PER) if (nt == NT && per == PER) { k_cluster_chain<NT, PER><<<grid, NT, smem, st>>>(d, list, len, nmax, counter); return; }
     AHS_FOR_EACH_NT(X)
 #undef X
-    throw ArgFail{"fused_launch: no kernel for this block size"};
+    throw ArgFail{"cluster_launch: no kernel for this block size"};
 }
+template <int BITS> static void score_launch(int nt, int kpl, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
+#define X(NT, KPL) if (nt == NT && kpl == KPL) { k_score_chain<BITS, NT, KPL><<<grid, NT, smem, st>>>(d, list, len, nmax, counter); return; }
+    AHS_FOR_EACH_SC(X)
+#undef X
+    throw ArgFail{"score_launch: no kernel for this block size"};
+}
+static int score_class(int n) { for (int k = 0; k < N_SCORE; k++) if (n <= kScore[k].nmax) return k; return -1; }
 // class of a chain with n final reads, -1 = HBM-resident path
 static int fused_class(int n, size_t smem_optin) {
     for (int k = 0; k < N_FUSED; k++) {
         if (n > kFused[k].nmax) continue;
         if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) return -1;
         if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)kFused[k].per * kFused[k].nt) return -1;
-        if (kFused[k].nmax > 32 * cc_kpl(kFused[k].nt, kFused[k].per)) return -1;
+        if (score_class(n) < 0) return -1;
         return k;
     }
     return -1;
@@ -334,7 +347,7 @@ struct Pipeline {
             h_frow_off[c + 1] = h_frow_off[c] + n; h_pos_off[c + 1] = h_pos_off[c] + np;
             h_code_off[c] = n_code_words; n_code_words += n * h_words[c];
             h_fused[c] = (n > 0 && fused_class((int)n, cx->smem_optin) >= 0) ? 1 : 0;
-            h_cw_off[c] = n_cw; if (!h_fused[c]) n_cw += n * n;
+            h_cw_off[c] = n_cw; n_cw += h_fused[c] ? n * (n - 1) / 2 : n * n;
             h_back_off[c] = h_pos_off[c] * S_max;
         }
         const int64_t NF = h_frow_off[C], NP = h_pos_off[C];
@@ -381,8 +394,24 @@ struct Pipeline {
         }
         if (nf_unfused) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (nf_unfused) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
+        // chains up to CC_MAXN reads: scoring out of shared memory, 4 B per pair to HBM (every chain of BASELINE config 2)
+        {
+            std::vector<int32_t> sl[N_SCORE];
+            for (int64_t c = 0; c < C; c++) if (h_fused[c]) sl[score_class((int)(h_frow_off[c + 1] - h_frow_off[c]))].push_back((int32_t)c);
+            int32_t* s_counters = dzero<int32_t>(N_SCORE);
+            for (int k = N_SCORE - 1; k >= 0; k--) {
+                if (sl[k].empty()) continue;
+                std::stable_sort(sl[k].begin(), sl[k].end(), [&](int32_t a, int32_t b) { return h_nfinal[a] > h_nfinal[b]; });
+                const int32_t* dl = up(sl[k].data(), (int64_t)sl[k].size());
+                const int len = (int)sl[k].size(), nt = kScore[k].nt;
+                const size_t smem = cs_smem_bytes(kScore[k].nmax);
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, 2048 / nt), (228 * 1024) / (smem + 1024)));
+                const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
+                score_launch<BITS>(nt, kScore[k].kpl, grid, smem, st, d, dl, len, kScore[k].nmax, s_counters + k); n_launches += 1;
+            }
+        }
         CK(cudaEventRecord(cx->ev[3], st));
-        // ---- fused scoring + cluster editing out of shared memory (every chain of BASELINE configs 2-4)
+        // ---- cluster editing out of shared memory
         CK(cudaEventRecord(cx->ev[10], st));
         {
             std::vector<int32_t> fl[N_FUSED];
@@ -396,7 +425,7 @@ struct Pipeline {
                 const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
                 const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
                 const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-                fused_launch<BITS>(nt, kFused[k].per, grid, smem, st, d, dl, len, kFused[k].nmax, f_counters + k); n_launches += 1;
+                cluster_launch(nt, kFused[k].per, grid, smem, st, d, dl, len, kFused[k].nmax, f_counters + k); n_launches += 1;
             }
         }
         CK(cudaEventRecord(cx->ev[11], st));
@@ -451,12 +480,7 @@ struct Pipeline {
         CK(cudaEventElapsedTime(&t, cx->ev[1], cx->ev[2])); ms[1] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[2], cx->ev[3])); ms[2] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[3], cx->ev[4])); ms[3] = t;
-        // the fused kernel does scoring and cluster editing: split its time by the in-kernel globaltimer shares
-        CK(cudaEventElapsedTime(&t, cx->ev[10], cx->ev[11])); ms_fused = t;
-        CK(cudaMemcpy(h_tphase, d.t_phase, 16, cudaMemcpyDeviceToHost));
-        const double tot = (double)h_tphase[0] + (double)h_tphase[1];
-        const float fused_score = tot > 0 ? (float)(ms_fused * ((double)h_tphase[0] / tot)) : 0.f;
-        ms[2] += fused_score; ms[3] -= fused_score; ms[7] = fused_score;
+        CK(cudaEventElapsedTime(&t, cx->ev[10], cx->ev[11])); ms_fused = t; ms[7] = t;      // shared-memory cluster editing alone
         CK(cudaEventElapsedTime(&t, cx->ev[4], cx->ev[5])); ms[4] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[5], cx->ev[6])); ms[5] = t;
         CK(cudaEventElapsedTime(&t, cx->ev[0], cx->ev[7])); ms[6] = t;

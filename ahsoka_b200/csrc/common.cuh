@@ -28,6 +28,11 @@ __device__ __forceinline__ uint32_t hash64(uint64_t k) {
     return (uint32_t)k;
 }
 
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {      // murmur3 finaliser
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+
 __device__ __forceinline__ void atomic_or_u16(uint16_t* p, uint16_t v) {
     uintptr_t a = (uintptr_t)p;
     unsigned int* w = (unsigned int*)(a & ~(uintptr_t)3);

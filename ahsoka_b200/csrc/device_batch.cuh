@@ -28,7 +28,8 @@ struct DB {
     int32_t *bubble_chain, *allele_bubble, *entry_chain, *read_chain, *rankA;
     int64_t *mrow_off;                  // [C] chain offset into mask (u16 units)
     // ---- trigger table
-    uint64_t *hkeys; int32_t *hhead; uint32_t hmask; int32_t *inc_next; uint32_t *bubble_univ;
+    unsigned long long *hslots; const int64_t *hoff; const uint32_t *hmaskc;   // per-chain hash regions (k_project.cuh)
+    int32_t *inc_next; uint32_t *bubble_univ;
     // ---- projection
     uint16_t *mask;
     uint64_t *create_key, *createA_key; uint32_t *first_entry; uint8_t *has_good;

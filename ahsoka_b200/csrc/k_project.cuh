@@ -91,6 +91,11 @@ __global__ void k_rank_a(DB d) {
 }
 
 // ---------------------------------------------------------------- K0: trigger table
+// One open-addressing table PER CHAIN (region hoff[c], size hmaskc[c] + 1 = power of two >= 2 x alleles of the
+// chain), so that all probes of a chain's entries fall into a few KB that stay in L1/L2.  Slot = (head << 32 | node
+// id); all ones = empty; head = first allele of the list of alleles triggered by the node (inc_next links).
+constexpr unsigned long long SLOT_EMPTY = ~0ull;
+
 __global__ void k_build_triggers(DB d) {
     AHS_BAIL_ON_ERR(d);
     for (int64_t ga = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ga < d.NA; ga += (int64_t)gridDim.x * blockDim.x) {
@@ -104,25 +109,33 @@ __global__ void k_build_triggers(DB d) {
         const int a = (int)(ga - d.allele_off[gb]);
         if (a >= MAX_ALLELES) { atomicOr(d.err_flags, 2); continue; }
         if (len <= 2) atomicMin(&d.bubble_univ[gb], (uint32_t)a);          // no inner node: matches every entry (A#9)
-        const int32_t trig = len >= 3 ? d.anode[o + 1] : d.anode[o];
-        const uint64_t key = ((uint64_t)(uint32_t)c << 32) | (uint32_t)trig;
-        uint32_t slot = hash64(key) & d.hmask;
+        const uint32_t trig = (uint32_t)(len >= 3 ? d.anode[o + 1] : d.anode[o]);
+        unsigned long long* tab = d.hslots + d.hoff[c];
+        const uint32_t mask = d.hmaskc[c];
+        uint32_t slot = hash32(trig) & mask;
         while (true) {
-            unsigned long long prev = atomicCAS((unsigned long long*)&d.hkeys[slot], (unsigned long long)KEY_NONE, (unsigned long long)key);
-            if (prev == KEY_NONE || prev == key) break;
-            slot = (slot + 1) & d.hmask;
+            const unsigned long long claimed = (0xfffffffeull << 32) | trig;          // head = -2: no allele linked yet
+            const unsigned long long prev = atomicCAS(&tab[slot], SLOT_EMPTY, claimed);
+            if (prev == SLOT_EMPTY || (uint32_t)prev == trig) break;
+            slot = (slot + 1) & mask;
         }
-        d.inc_next[ga] = atomicExch(&d.hhead[slot], (int32_t)ga);
+        const int32_t prev_head = atomicExch((int32_t*)&tab[slot] + 1, (int32_t)ga);  // little endian: high word = head
+        d.inc_next[ga] = prev_head == -2 ? -1 : prev_head;
     }
 }
 
 // ---------------------------------------------------------------- K1: project entries
-__device__ __forceinline__ bool entry_has(const int32_t* __restrict__ nodes, int L, int32_t v) {
-    for (int x = 0; x < L; x++) if (__ldg(nodes + x) == v) return true;
-    return false;
+// is value q among the L nodes of the entry?  (whole warp)
+__device__ __forceinline__ bool warp_entry_has(const int32_t* __restrict__ nodes, int L, int32_t q, int lane) {
+    bool f = false;
+    for (int x = lane; x < L; x += 32) f |= __ldg(nodes + x) == q;
+    return __any_sync(0xffffffffu, f);
 }
 
-// one warp per alignment entry; lanes stride over the entry's nodes
+// one warp per alignment entry; lanes stride over the entry's nodes.  A node that is the trigger of an allele path
+// (hash hit) decides the two containment tests of the reference (is_subset with and without the end nodes, :495-548).
+// Common case, decided by the lane alone: a 3-node path whose end nodes are the neighbours of the trigger in the
+// alignment.  Everything else is decided by the whole warp scanning the entry.
 __global__ void __launch_bounds__(256) k_project(DB d) {
     AHS_BAIL_ON_ERR(d);
     const int warps_per_block = blockDim.x >> 5;
@@ -137,41 +150,73 @@ __global__ void __launch_bounds__(256) k_project(DB d) {
         const uint32_t el = (uint32_t)(ge - d.entry_off[c]);
         const float ident = d.entry_identity[ge];
         const bool good = good_identity(ident);
-        if (lane == 0) { atomicMin(&d.first_entry[r], el); if (good) d.has_good[r] = 1; }
         uint16_t* mrow = d.mask + d.mrow_off[c] + (int64_t)rl * B;
         const int32_t* nodes = d.enode + d.enode_off[ge];
         const int L = (int)(d.enode_off[ge + 1] - d.enode_off[ge]);
-        for (int x = lane; x < L; x += 32) {
-            const int32_t v = __ldg(nodes + x);
-            const uint64_t key = ((uint64_t)(uint32_t)c << 32) | (uint32_t)v;
-            uint32_t slot = hash64(key) & d.hmask;
-            int32_t ga = -1;
-            while (true) {
-                const uint64_t k = d.hkeys[slot];
-                if (k == key) { ga = d.hhead[slot]; break; }
-                if (k == KEY_NONE) break;
-                slot = (slot + 1) & d.hmask;
-            }
-            for (; ga >= 0; ga = d.inc_next[ga]) {
-                const int64_t gb = d.allele_bubble[ga];
-                const int b = (int)(gb - b0);
-                const int a = (int)(ga - d.allele_off[gb]);
-                const int64_t o = d.anode_off[ga];
-                const int len = (int)(d.anode_off[ga + 1] - o);
-                bool inner_ok = len >= 3;                      // len <= 2: universal, handled in k_read_rows
-                for (int y = 2; inner_ok && y < len - 1; y++) inner_ok = entry_has(nodes, L, d.anode[o + y]);
-                bool full_ok;
-                if (len >= 3) full_ok = inner_ok && entry_has(nodes, L, d.anode[o]) && entry_has(nodes, L, d.anode[o + len - 1]);
-                else full_ok = (len == 1) || entry_has(nodes, L, d.anode[o + 1]);
-                if (inner_ok) {
-                    if (good) atomic_or_u16(&mrow[b], (uint16_t)(1u << a));
-                    atomicMin((unsigned long long*)&d.create_key[r], (unsigned long long)make_key((uint32_t)b, (uint32_t)a, el));
-                }
-                if (full_ok) {
-                    atomic_or_u16(&mrow[b], (uint16_t)0x8000u);
-                    atomicMin((unsigned long long*)&d.createA_key[r], (unsigned long long)make_key((uint32_t)d.rankA[gb], (uint32_t)a, el));
+        const unsigned long long* tab = d.hslots + d.hoff[c];
+        const uint32_t mask = d.hmaskc[c];
+        uint64_t ck = KEY_NONE, ckA = KEY_NONE;                 // smallest creation keys seen by this lane
+        for (int x0 = 0; x0 < L; x0 += 32) {
+            const int x = x0 + lane;
+            int32_t ga = -1, prev = 0, next = 0; bool has_prev = false, has_next = false;
+            if (x < L) {
+                const int32_t v = __ldg(nodes + x);
+                has_prev = x > 0; has_next = x + 1 < L;
+                if (has_prev) prev = __ldg(nodes + x - 1);
+                if (has_next) next = __ldg(nodes + x + 1);
+                uint32_t slot = hash32((uint32_t)v) & mask;
+                while (true) {
+                    const unsigned long long sl = tab[slot];
+                    if (sl == SLOT_EMPTY) break;
+                    if ((uint32_t)sl == (uint32_t)v) { ga = (int32_t)(sl >> 32); break; }
+                    slot = (slot + 1) & mask;
                 }
             }
+            while (__any_sync(0xffffffffu, ga >= 0)) {
+                const bool have = ga >= 0;
+                int64_t gb = 0, o = 0; int len = 0;
+                bool inner_ok = false, full_ok = false, slow = false;
+                if (have) {
+                    gb = d.allele_bubble[ga];
+                    o = d.anode_off[ga]; len = (int)(d.anode_off[ga + 1] - o);
+                    if (len == 3) {
+                        inner_ok = true;                                                  // the only inner node is the trigger
+                        const int32_t src = d.anode[o], snk = d.anode[o + 2];
+                        full_ok = has_prev && has_next && ((prev == src && next == snk) || (prev == snk && next == src));
+                        slow = !full_ok;                                                  // the end nodes may still be elsewhere in the entry
+                    } else slow = true;
+                }
+                for (unsigned sm = __ballot_sync(0xffffffffu, slow); sm; sm &= sm - 1) {
+                    const int src_lane = __ffs(sm) - 1;
+                    const int64_t oo = __shfl_sync(0xffffffffu, o, src_lane);
+                    const int ll = __shfl_sync(0xffffffffu, len, src_lane);
+                    bool in_ok = ll >= 3;                          // len <= 2: universal, handled in k_read_rows
+                    for (int y = 2; in_ok && y < ll - 1; y++) in_ok = warp_entry_has(nodes, L, d.anode[oo + y], lane);
+                    bool f_ok;
+                    if (ll >= 3) f_ok = in_ok && warp_entry_has(nodes, L, d.anode[oo], lane) && warp_entry_has(nodes, L, d.anode[oo + ll - 1], lane);
+                    else f_ok = (ll == 1) || warp_entry_has(nodes, L, d.anode[oo + 1], lane);
+                    if (lane == src_lane) { inner_ok = in_ok; full_ok = f_ok; }
+                }
+                if (have) {
+                    const int b = (int)(gb - b0);
+                    const int a = (int)(ga - d.allele_off[gb]);
+                    if (inner_ok) {
+                        if (good) atomic_or_u16(&mrow[b], (uint16_t)(1u << a));
+                        const uint64_t k = make_key((uint32_t)b, (uint32_t)a, el); ck = k < ck ? k : ck;
+                    }
+                    if (full_ok) {
+                        atomic_or_u16(&mrow[b], (uint16_t)0x8000u);
+                        const uint64_t k = make_key((uint32_t)d.rankA[gb], (uint32_t)a, el); ckA = k < ckA ? k : ckA;
+                    }
+                    ga = d.inc_next[ga];
+                }
+            }
+        }
+        ck = warp_min_u64(ck); ckA = warp_min_u64(ckA);
+        if (lane == 0) {
+            atomicMin(&d.first_entry[r], el); if (good) d.has_good[r] = 1;
+            if (ck != KEY_NONE) atomicMin((unsigned long long*)&d.create_key[r], (unsigned long long)ck);
+            if (ckA != KEY_NONE) atomicMin((unsigned long long*)&d.createA_key[r], (unsigned long long)ckA);
         }
     }
 }

@@ -196,7 +196,7 @@ struct Pipeline {
     std::vector<int32_t> h_status, h_nfinal, h_npos, h_words;
     std::vector<uint8_t> h_fused;
     float ms_fused = 0; unsigned long long h_tphase[2] = {0, 0};
-    int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0;
+    int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0, h_slots = 0;
     float ms[8] = {0};
     int n_launches = 0;
 
@@ -229,6 +229,16 @@ struct Pipeline {
         }
         sz.M = acc;
         d.mrow_off = (int64_t*)up(h_mrow_off.data(), C);
+        // per-chain trigger tables: power of two >= 2 x alleles of the chain
+        std::vector<int64_t> hoff(C); std::vector<uint32_t> hmaskc(C);
+        h_slots = 0;
+        for (int64_t c = 0; c < C; c++) {
+            const int64_t nal = in->allele_off[in->bubble_off[c + 1]] - in->allele_off[in->bubble_off[c]];
+            if (nal < 0 || nal > sz.NA) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
+            int64_t cap = 4; while (cap < 2 * nal) cap <<= 1;
+            hoff[c] = h_slots; hmaskc[c] = (uint32_t)(cap - 1); h_slots += cap;
+        }
+        d.hoff = up(hoff.data(), C); d.hmaskc = up(hmaskc.data(), C);
         (void)st;
     }
 
@@ -237,9 +247,7 @@ struct Pipeline {
         const int64_t C = sz.C;
         d.bubble_chain = dalloc<int32_t>(sz.NB); d.allele_bubble = dalloc<int32_t>(sz.NA); d.entry_chain = dalloc<int32_t>(sz.NE);
         d.read_chain = dalloc<int32_t>(sz.NR); d.rankA = dalloc<int32_t>(sz.NB);
-        uint64_t ts = 1024; while ((int64_t)ts < 2 * sz.NA) ts <<= 1;
-        d.hmask = (uint32_t)(ts - 1);
-        d.hkeys = dalloc<uint64_t>((int64_t)ts); d.hhead = dalloc<int32_t>((int64_t)ts); d.inc_next = dalloc<int32_t>(sz.NA);
+        d.hslots = dalloc<unsigned long long>(h_slots); d.inc_next = dalloc<int32_t>(sz.NA);
         d.bubble_univ = dalloc<uint32_t>(sz.NB);
         d.mask = dalloc<uint16_t>(sz.M + 2);
         d.create_key = dalloc<uint64_t>(sz.NR); d.createA_key = dalloc<uint64_t>(sz.NR); d.first_entry = dalloc<uint32_t>(sz.NR);
@@ -257,7 +265,7 @@ struct Pipeline {
 
     void init_phase1() {
         cudaStream_t st = cx->stream; const int64_t C = sz.C;
-        CK(cudaMemsetAsync(d.hkeys, 0xff, ((size_t)d.hmask + 1) * 8, st)); CK(cudaMemsetAsync(d.hhead, 0xff, ((size_t)d.hmask + 1) * 4, st));
+        CK(cudaMemsetAsync(d.hslots, 0xff, (size_t)std::max<int64_t>(h_slots, 1) * 8, st));
         CK(cudaMemsetAsync(d.bubble_univ, 0xff, std::max<int64_t>(sz.NB, 1) * 4, st));
         CK(cudaMemsetAsync(d.mask, 0, (sz.M + 2) * 2, st));
         CK(cudaMemsetAsync(d.create_key, 0xff, std::max<int64_t>(sz.NR, 1) * 8, st)); CK(cudaMemsetAsync(d.createA_key, 0xff, std::max<int64_t>(sz.NR, 1) * 8, st));

@@ -216,6 +216,86 @@ __global__ void __launch_bounds__(DP_THREADS) k_thread(DB d, int32_t* __restrict
     }
 }
 
+// ---------------------------------------------------------------- K4 for ploidy 2: one WARP per chain
+// At ploidy 2 a column has at most 4 x 4 = 16 states, so a warp holds the whole DP column in registers (lane = state
+// code), the per-position record (22 words) arrives as one coalesced load that is prefetched one position ahead, the
+// min over predecessors is 16 shuffles, and there is no block barrier.  Same recurrence, same tie rules (lowest
+// predecessor code, lowest final code) as k_thread / rule R3.
+static_assert(sizeof(PosRec) == 88, "k_thread2 reads PosRec as 22 words");
+
+__global__ void __launch_bounds__(256) k_thread2(DB d, int32_t* __restrict__ work_counter) {
+    const int lane = lane_id();
+    const unsigned full = 0xffffffffu;
+    while (true) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(work_counter, 1);
+        c = __shfl_sync(full, c, 0);
+        if (c >= d.C) break;
+        if (d.ch_status[c] != AHS_CHAIN_OK) continue;
+        const int64_t p0 = d.pos_off[c];
+        const int n_pos = (int)(d.pos_off[c + 1] - p0);
+        if (n_pos == 0) continue;
+        uint16_t* back = d.back + d.back_off[c];                       // 16 predecessor codes per position
+        const uint32_t* recw = (const uint32_t*)(d.rec + p0);
+        uint32_t rw = lane < 22 ? recw[lane] : 0u;
+        int Dprev = DP_INF, gp0 = -1, gp1 = -1, kp = 0;
+        for (int q = 0; q < n_pos; q++) {
+            const uint32_t rw_next = (q + 1 < n_pos && lane < 22) ? recw[(int64_t)(q + 1) * 22 + lane] : 0u;
+            const uint32_t total = __shfl_sync(full, rw, 0);
+            const int kc = (int)(__shfl_sync(full, rw, 1) & 0xffu);
+            const int S = kc * kc;
+            const bool valid = lane < S;
+            const int d0 = valid ? lane / kc : 0, d1 = valid ? lane % kc : 0;       // haplotype 0 = most significant digit
+            const int g0 = (int)__shfl_sync(full, rw, 2 + d0), g1 = (int)__shfl_sync(full, rw, 2 + d1);
+            const uint32_t c0 = __shfl_sync(full, rw, 10 + d0), c1 = __shfl_sync(full, rw, 10 + d1);
+            const int a0 = (int)((__shfl_sync(full, rw, 18 + (d0 >> 2)) >> (8 * (d0 & 3))) & 0xffu);
+            const int a1 = (int)((__shfl_sync(full, rw, 18 + (d1 >> 2)) >> (8 * (d1 & 3))) & 0xffu);
+            const bool conform = (a0 == 0 && a1 == 1) || (a0 == 1 && a1 == 0);
+            const uint64_t m = d0 == d1 ? 2 : 1;
+            int cost = 0;
+            { const uint64_t lhs = (uint64_t)c0 * 4; if (lhs < (2 * m - 1) * total || lhs > (2 * m + 1) * total) cost++; }
+            { const uint64_t lhs = (uint64_t)c1 * 4; if (lhs < (2 * m - 1) * total || lhs > (2 * m + 1) * total) cost++; }
+            const bool any = __any_sync(full, valid && conform);
+            const bool allowed = conform || !any;
+            int Dcur;
+            if (q == 0) Dcur = allowed ? cost : DP_INF;
+            else {
+                int best = INT32_MAX, arg = 0;
+                const int Sp = kp * kp;
+                for (int sidx = 0; sidx < Sp; sidx++) {
+                    const int dv = __shfl_sync(full, Dprev, sidx);
+                    const int s0 = __shfl_sync(full, gp0, sidx), s1 = __shfl_sync(full, gp1, sidx);
+                    const int sw = (s0 != g0) + (s1 != g1);
+                    const int v = dv + 32 * sw + (sw ? 8 : 0);
+                    if (v < best) { best = v; arg = sidx; }
+                }
+                Dcur = allowed ? min(best + cost, DP_INF) : DP_INF;
+                if (valid) back[(int64_t)q * 16 + lane] = (uint16_t)arg;
+            }
+            Dprev = valid ? Dcur : DP_INF; gp0 = g0; gp1 = g1; kp = kc; rw = rw_next;
+        }
+        // final minimum (lowest code) and backtrace; the rows of `back` and the records are loaded by the whole warp
+        const int fin = (lane < kp * kp) ? Dprev : INT32_MAX;
+        const int best = __reduce_min_sync(full, fin);
+        int cur = __ffs(__ballot_sync(full, fin == best)) - 1;
+        if (lane == 0) d.dp_cost[c] = (double)best;
+        __syncwarp();
+        for (int q = n_pos - 1; q >= 0; q--) {
+            const uint32_t w = lane < 22 ? recw[(int64_t)q * 22 + lane] : 0u;
+            const int brow = (q > 0 && lane < 16) ? back[(int64_t)q * 16 + lane] : 0;
+            const int kc = (int)(__shfl_sync(full, w, 1) & 0xffu);
+            const int dg = lane == 0 ? cur / kc : cur % kc;                          // lane h writes haplotype h
+            const int g = (int)__shfl_sync(full, w, 2 + (lane < 2 ? dg : 0));
+            const uint32_t cmw = __shfl_sync(full, w, 20 + (lane < 2 ? (dg >> 2) : 0));
+            if (lane < 2) {
+                d.path[(p0 + q) * 2 + lane] = g;
+                d.hap_allele[(p0 + q) * 2 + lane] = (uint8_t)((cmw >> (8 * (dg & 3))) & 0xffu);
+            }
+            cur = __shfl_sync(full, brow, cur);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- CSR cells of the final matrix
 template <int BITS>
 __global__ void __launch_bounds__(256) k_write_cells(DB d) {

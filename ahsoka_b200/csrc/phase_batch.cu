@@ -471,7 +471,8 @@ struct Pipeline {
         // ---- coverage / consensus, threading
         if (NP) k_consensus<BITS><<<grid_for(NP, 4, sms), 128, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[5], st));
-        if (NP) k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1;
+        if (NP && in->ploidy == 2) { k_thread2<<<(unsigned)std::min<int64_t>((C + 7) / 8, (int64_t)sms * 8), 256, 0, st>>>(d, counters + 1); n_launches += 1; }
+        else if (NP) { k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1; }
         CK(cudaEventRecord(cx->ev[6], st));
         // ---- CSR cells
         scan(d.fr_nv, NF, d.cell_off);

@@ -51,8 +51,7 @@ struct DB {
     uint8_t *ce_active, *ce_dirty; int32_t *ce_list, *ce_newrow, *ce_label;
     int64_t *ce_rbF, *ce_rbP; int32_t *ce_rbFarg, *ce_rbParg;
     uint64_t *key_scratch; int64_t *key_scratch_off;       // overflow buffers for reads with > 256 partners
-    uint8_t *ch_fused;                                    // [C] 1 = chain is scored + clustered by k_score_cluster (shared memory)
-    unsigned long long *t_phase;                          // [2] ns spent by k_score_cluster blocks in scoring / cluster editing
+    uint8_t *ch_fused;                                    // [C] 1 = chain is scored + clustered out of shared memory (k_chain.cuh)
     // ---- consensus / threading
     PosRec *rec; uint16_t *back; int64_t *back_off; int32_t S_max;
     int32_t *path; uint8_t *hap_allele; double *dp_cost;

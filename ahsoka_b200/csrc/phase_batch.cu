@@ -84,7 +84,8 @@ constexpr int N_SCORE = (int)(sizeof(kScore) / sizeof(kScore[0]));
 #define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8)
 #define AHS_FOR_EACH_SC(X) X(64, 1) X(128, 2) X(256, 4)
 static void fused_set_attributes(size_t optin) {
-#define X(NT, PER) CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+#define X(NT, PER) CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
+                   CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     AHS_FOR_EACH_NT(X)
 #undef X
 #define X(NT, KPL) CK(cudaFuncSetAttribute(k_score_chain<2, NT, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
@@ -105,16 +106,14 @@ template <int BITS> static void score_launch(int nt, int kpl, unsigned grid, siz
     throw ArgFail{"score_launch: no kernel for this block size"};
 }
 static int score_class(int n) { for (int k = 0; k < N_SCORE; k++) if (n <= kScore[k].nmax) return k; return -1; }
-// class of a chain with n final reads, -1 = HBM-resident path
-static int fused_class(int n, size_t smem_optin) {
+// every class must fit the device (checked once per context)
+static void check_classes(size_t smem_optin) {
     for (int k = 0; k < N_FUSED; k++) {
-        if (n > kFused[k].nmax) continue;
-        if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) return -1;
-        if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)kFused[k].per * kFused[k].nt) return -1;
-        if (score_class(n) < 0) return -1;
-        return k;
+        if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) throw LimitFail{"device shared memory too small for the cluster-editing classes"};
+        if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)kFused[k].per * kFused[k].nt) throw std::logic_error("cluster class table: slots");
     }
-    return -1;
+    if (kFused[N_FUSED - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
+    for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax) > smem_optin) throw std::logic_error("score class table");
 }
 
 static Ctx* get_ctx(int device) {
@@ -138,8 +137,8 @@ static Ctx* get_ctx(int device) {
     CK(cudaMemcpy(c->d_ln, ln.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_ln1, ln1.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * 4096 + 64));
-    CK(cudaFuncSetAttribute(k_cluster_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    check_classes(c->smem_optin);
     fused_set_attributes(c->smem_optin);
     g_ctx[device] = c;
     return c;
@@ -193,9 +192,9 @@ static inline int grid_for(int64_t items, int per_block, int sms) {
 struct Pipeline {
     Ctx* cx; const ahs_batch_in* in; Sizes sz; DB d{};
     std::vector<int64_t> h_mrow_off, h_frow_off, h_pos_off, h_code_off, h_cw_off, h_back_off;
-    std::vector<int32_t> h_status, h_nfinal, h_npos, h_words;
-    std::vector<uint8_t> h_fused;
-    float ms_fused = 0; unsigned long long h_tphase[2] = {0, 0};
+    int32_t *h_status = nullptr, *h_nfinal = nullptr, *h_npos = nullptr;      // pinned: D2H targets of sync #1
+    char *sg_h = nullptr, *sg_d = nullptr; size_t sg_cap = 0;                   // pinned / device staging block of phase 2
+    float ms_fused = 0;
     int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0, h_slots = 0;
     float ms[8] = {0};
     int n_launches = 0;
@@ -261,6 +260,9 @@ struct Pipeline {
         d.ch_nclusters = dalloc<int32_t>(C);
         d.tot_cells = dalloc<int64_t>(1); d.tot_pairs = dalloc<int64_t>(1); d.err_flags = dalloc<int32_t>(1);
         d.ln = cx->d_ln; d.ln1 = cx->d_ln1;
+        h_status = cx->pin.get<int32_t>(C); h_nfinal = cx->pin.get<int32_t>(C); h_npos = cx->pin.get<int32_t>(C);
+        sg_cap = (size_t)(C + 2) * (8 * 5 + 4 * 3 + 1) + 512;
+        sg_h = (char*)cx->pin.alloc(sg_cap); sg_d = (char*)cx->dev.alloc(sg_cap);
     }
 
     void init_phase1() {
@@ -317,11 +319,10 @@ struct Pipeline {
         k_count_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaGetLastError());
         // ---- sync #1: per-chain sizes -> offsets of the per-chain workspaces
-        h_status.resize(C); h_nfinal.resize(C); h_npos.resize(C);
         int32_t h_err = 0;
-        CK(cudaMemcpyAsync(h_status.data(), d.ch_status, C * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h_nfinal.data(), d.ch_nfinal, C * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h_npos.data(), d.ch_npos, C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_status, d.ch_status, C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_nfinal, d.ch_nfinal, C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_npos, d.ch_npos, C * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_tot_cells, d.tot_cells, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_err, d.err_flags, 4, cudaMemcpyDeviceToHost, st));
         int32_t h_maxk = 0;
@@ -336,136 +337,129 @@ struct Pipeline {
         d.bits = sz.max_k <= 3 ? 2 : 4;
     }
 
+    // pinned staging block: every per-chain array the host derives at sync #1 goes to the device in ONE copy
+    struct Stage {
+        char* h = nullptr; char* dv = nullptr; size_t used = 0;
+        template <class T> T* take(size_t n, T** dev) { used = (used + 15) & ~(size_t)15; T* p = (T*)(h + used); *dev = (T*)(dv + used); used += n * sizeof(T); return p; }
+    };
+
     template <int BITS> void run_bits() {
         cudaStream_t st = cx->stream; const int sms = cx->sms; const int64_t C = sz.C;
         const int TB = 256;
-        h_fused.assign(C, 0);
-        h_frow_off.assign(C + 1, 0); h_pos_off.assign(C + 1, 0); h_code_off.assign(C, 0); h_cw_off.assign(C, 0); h_back_off.assign(C, 0); h_words.assign(C, 0);
         const int per_word = 32 / BITS;
         int64_t S_max = 1; for (int i = 0; i < in->ploidy; i++) S_max *= 2 * in->ploidy;
         d.S_max = (int32_t)S_max;
+        Stage sg; sg.h = sg_h; sg.dv = sg_d;
+        int64_t *dv_frow, *dv_pos, *dv_code, *dv_cw, *dv_back; int32_t *dv_words, *dv_order, *dv_status; uint8_t* dv_fused;
+        int64_t* s_frow = sg.take<int64_t>(C + 1, &dv_frow); int64_t* s_pos = sg.take<int64_t>(C + 1, &dv_pos);
+        int64_t* s_code = sg.take<int64_t>(C, &dv_code); int64_t* s_cw = sg.take<int64_t>(C, &dv_cw); int64_t* s_back = sg.take<int64_t>(C, &dv_back);
+        int32_t* s_words = sg.take<int32_t>(C, &dv_words); int32_t* s_order = sg.take<int32_t>(C, &dv_order); int32_t* s_status = sg.take<int32_t>(C, &dv_status);
+        uint8_t* s_fused = sg.take<uint8_t>(C, &dv_fused);
+        if (sg.used > sg_cap) throw std::runtime_error("staging block overflow");
         n_code_words = 0; n_cw = 0;
         bool status_changed = false;
+        s_frow[0] = 0; s_pos[0] = 0;
+        int64_t nf_unfused = 0; int n_max = 0;
         for (int64_t c = 0; c < C; c++) {
             if (h_status[c] == AHS_CHAIN_OK && h_nfinal[c] > MAX_READS_CLUSTER) { h_status[c] = AHS_CHAIN_TOO_LARGE; status_changed = true; }
+            s_status[c] = h_status[c];
             const bool ok = h_status[c] == AHS_CHAIN_OK;
             const int64_t n = ok ? h_nfinal[c] : 0, np = ok ? h_npos[c] : 0;
+            h_nfinal[c] = (int32_t)n;
             const int64_t B = in->bubble_off[c + 1] - in->bubble_off[c];
-            h_words[c] = (int32_t)((B + per_word - 1) / per_word);
-            h_frow_off[c + 1] = h_frow_off[c] + n; h_pos_off[c + 1] = h_pos_off[c] + np;
-            h_code_off[c] = n_code_words; n_code_words += n * h_words[c];
-            h_fused[c] = (n > 0 && fused_class((int)n, cx->smem_optin) >= 0) ? 1 : 0;
-            h_cw_off[c] = n_cw; n_cw += h_fused[c] ? n * (n - 1) / 2 : n * n;
-            h_back_off[c] = h_pos_off[c] * S_max;
+            s_words[c] = (int32_t)((B + per_word - 1) / per_word);
+            s_frow[c + 1] = s_frow[c] + n; s_pos[c + 1] = s_pos[c] + np;
+            s_code[c] = n_code_words; n_code_words += n * s_words[c];
+            s_fused[c] = (n > 0 && n <= CC_MAXN) ? 1 : 0;
+            s_cw[c] = n_cw; n_cw += s_fused[c] ? n * (n - 1) / 2 : n * n;
+            s_back[c] = s_pos[c] * S_max;
+            if (!s_fused[c]) nf_unfused += n;
+            n_max = std::max<int>(n_max, (int)n);
         }
-        const int64_t NF = h_frow_off[C], NP = h_pos_off[C];
+        // chains by decreasing read count (counting sort): every size class is one contiguous range of `order`
+        std::vector<int32_t> start(n_max + 2, 0);
+        for (int64_t c = 0; c < C; c++) start[n_max - h_nfinal[c] + 1]++;
+        for (int x = 0; x <= n_max; x++) start[x + 1] += start[x];
+        { std::vector<int32_t> fill(start.begin(), start.end() - 1); for (int64_t c = 0; c < C; c++) s_order[fill[n_max - h_nfinal[c]]++] = (int32_t)c; }
+        auto range_of = [&](int n_lo, int n_hi, int& first, int& len) {          // chains with n_lo <= n <= n_hi
+            n_hi = std::min(n_hi, n_max); n_lo = std::max(n_lo, 0);
+            if (n_hi < n_lo) { first = 0; len = 0; return; }
+            first = start[n_max - n_hi]; len = start[n_max - n_lo + 1] - first;
+        };
+        h_frow_off.assign(s_frow, s_frow + C + 1); h_pos_off.assign(s_pos, s_pos + C + 1);
+        const int64_t NF = s_frow[C], NP = s_pos[C];
         d.NF = NF; d.NP = NP;
-        if (status_changed) CK(cudaMemcpyAsync(d.ch_status, h_status.data(), C * 4, cudaMemcpyHostToDevice, st));
-        d.frow_off = (int64_t*)up(h_frow_off.data(), C + 1); d.pos_off = (int64_t*)up(h_pos_off.data(), C + 1);
-        d.code_off = (int64_t*)up(h_code_off.data(), C); d.cw_off = (int64_t*)up(h_cw_off.data(), C); d.back_off = (int64_t*)up(h_back_off.data(), C);
-        CK(cudaMemcpyAsync(d.ch_words, h_words.data(), C * 4, cudaMemcpyHostToDevice, st));
-        d.ch_fused = (uint8_t*)up(h_fused.data(), C);
-        d.t_phase = dzero<unsigned long long>(2);
-        int64_t nf_unfused = 0;
-        for (int64_t c = 0; c < C; c++) if (!h_fused[c]) nf_unfused += h_frow_off[c + 1] - h_frow_off[c];
+        CK(cudaMemcpyAsync(sg.dv, sg.h, sg.used, cudaMemcpyHostToDevice, st));
+        d.frow_off = dv_frow; d.pos_off = dv_pos; d.code_off = dv_code; d.cw_off = dv_cw; d.back_off = dv_back;
+        d.ch_words = dv_words; d.ch_fused = dv_fused;
+        if (status_changed) CK(cudaMemcpyAsync(d.ch_status, dv_status, C * 4, cudaMemcpyDeviceToDevice, st));
         d.fr_chain = dalloc<int32_t>(NF); d.fr_first = dalloc<int32_t>(NF); d.fr_last = dalloc<int32_t>(NF); d.fr_mapq = dalloc<int32_t>(NF);
         d.fr_id = dalloc<int32_t>(NF); d.fr_nv = dalloc<int32_t>(NF); d.fr_cluster = dzero<int32_t>(NF);
         d.codes = dzero<uint32_t>(n_code_words);
         d.pos = dalloc<int32_t>(NP); d.pos_chain = dalloc<int32_t>(NP);
         d.es = dalloc<uint16_t>(NF); d.ed = dalloc<uint16_t>(NF);
-        d.W = dzero<int32_t>(n_cw); d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw);
-        d.ce_active = dalloc<uint8_t>(NF); d.ce_dirty = dalloc<uint8_t>(NF); d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
-        d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
+        d.W = dalloc<int32_t>(n_cw);
+        if (nf_unfused) {
+            // HBM-resident path (chains above CC_MAXN reads): dense n x n workspaces
+            for (int64_t c = 0; c < C; c++) if (!s_fused[c] && h_nfinal[c] > 0)
+                CK(cudaMemsetAsync(d.W + s_cw[c], 0, (size_t)h_nfinal[c] * h_nfinal[c] * 4, st));
+            d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw);
+            d.ce_active = dalloc<uint8_t>(NF); d.ce_dirty = dalloc<uint8_t>(NF); d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
+            d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
+        }
         d.rec = dalloc<PosRec>(NP); d.back = dalloc<uint16_t>(NP * S_max);
         d.path = dzero<int32_t>(NP * in->ploidy); d.hap_allele = dzero<uint8_t>(NP * in->ploidy); d.dp_cost = dzero<double>(C);
         d.cell_off = dalloc<int64_t>(NF + 1); d.cell_pos = dalloc<int32_t>(h_tot_cells); d.cell_allele = dalloc<uint8_t>(h_tot_cells);
-        int32_t* counters = dzero<int32_t>(4);
+        int32_t* counters = dzero<int32_t>(8 + N_SCORE + N_FUSED);
+        d.key_scratch = nullptr; d.key_scratch_off = nullptr;
+        if (nf_unfused) {
+            // reads of HBM-path chains with more than RATE_SMEM_KEYS candidate partners sort in HBM scratch
+            std::vector<int64_t> koff(NF + 1, 0);
+            int64_t tot = 0; bool any = false;
+            for (int64_t c = 0; c < C; c++) {
+                const int64_t n = h_nfinal[c];
+                int64_t cap = 0;
+                if (n > RATE_SMEM_KEYS && !s_fused[c]) { cap = 1; while (cap < n) cap <<= 1; any = true; }
+                for (int64_t i = 0; i < n; i++) { koff[s_frow[c] + i] = tot; tot += cap; }
+            }
+            koff[NF] = tot;
+            if (any) { d.key_scratch = dalloc<uint64_t>(tot); d.key_scratch_off = (int64_t*)up(koff.data(), NF + 1); }
+        }
         if (NF) k_owner<<<grid_for(NF, TB, sms), TB, 0, st>>>(d.frow_off, (int)C, NF, d.fr_chain); n_launches += 1;
         if (NP) k_owner<<<grid_for(NP, TB, sms), TB, 0, st>>>(d.pos_off, (int)C, NP, d.pos_chain); n_launches += 1;
         if (NF) k_pack_rows<<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[2], st));
-        // ---- scoring.  Reads with more than RATE_SMEM_KEYS candidate partners sort in HBM scratch.
-        {
-            // upper bound per read = chain size; only chains above the shared-memory capacity get scratch
-            std::vector<int64_t> koff(NF + 1, 0);
-            int64_t tot = 0; bool any = false;
-            for (int64_t c = 0; c < C; c++) {
-                const int64_t n = h_frow_off[c + 1] - h_frow_off[c];
-                int64_t cap = 0;
-                if (n > RATE_SMEM_KEYS && !h_fused[c]) { cap = 1; while (cap < n) cap <<= 1; any = true; }
-                for (int64_t i = 0; i < n; i++) { koff[h_frow_off[c] + i] = tot; tot += cap; }
-            }
-            koff[NF] = tot;
-            if (any) { d.key_scratch = dalloc<uint64_t>(tot); d.key_scratch_off = (int64_t*)up(koff.data(), NF + 1); }
-            else { d.key_scratch = nullptr; d.key_scratch_off = nullptr; }
-        }
+        // ---- scoring
         if (nf_unfused) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (nf_unfused) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         // chains up to CC_MAXN reads: scoring out of shared memory, 4 B per pair to HBM (every chain of BASELINE config 2)
-        {
-            std::vector<int32_t> sl[N_SCORE];
-            for (int64_t c = 0; c < C; c++) if (h_fused[c]) sl[score_class((int)(h_frow_off[c + 1] - h_frow_off[c]))].push_back((int32_t)c);
-            int32_t* s_counters = dzero<int32_t>(N_SCORE);
-            for (int k = N_SCORE - 1; k >= 0; k--) {
-                if (sl[k].empty()) continue;
-                std::stable_sort(sl[k].begin(), sl[k].end(), [&](int32_t a, int32_t b) { return h_nfinal[a] > h_nfinal[b]; });
-                const int32_t* dl = up(sl[k].data(), (int64_t)sl[k].size());
-                const int len = (int)sl[k].size(), nt = kScore[k].nt;
-                const size_t smem = cs_smem_bytes(kScore[k].nmax);
-                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, 2048 / nt), (228 * 1024) / (smem + 1024)));
-                const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-                score_launch<BITS>(nt, kScore[k].kpl, grid, smem, st, d, dl, len, kScore[k].nmax, s_counters + k); n_launches += 1;
-            }
+        for (int k = N_SCORE - 1; k >= 0; k--) {
+            int first, len; range_of(k ? kScore[k - 1].nmax + 1 : 1, kScore[k].nmax, first, len);
+            if (!len) continue;
+            const int nt = kScore[k].nt;
+            const size_t smem = cs_smem_bytes(kScore[k].nmax);
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, 2048 / nt), (228 * 1024) / (smem + 1024)));
+            const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
+            score_launch<BITS>(nt, kScore[k].kpl, grid, smem, st, d, dv_order + first, len, kScore[k].nmax, counters + 8 + k); n_launches += 1;
         }
         CK(cudaEventRecord(cx->ev[3], st));
         // ---- cluster editing out of shared memory
         CK(cudaEventRecord(cx->ev[10], st));
-        {
-            std::vector<int32_t> fl[N_FUSED];
-            for (int64_t c = 0; c < C; c++) if (h_fused[c]) fl[fused_class((int)(h_frow_off[c + 1] - h_frow_off[c]), cx->smem_optin)].push_back((int32_t)c);
-            int32_t* f_counters = dzero<int32_t>(N_FUSED);
-            for (int k = N_FUSED - 1; k >= 0; k--) {
-                if (fl[k].empty()) continue;
-                std::stable_sort(fl[k].begin(), fl[k].end(), [&](int32_t a, int32_t b) { return h_nfinal[a] > h_nfinal[b]; });
-                const int32_t* dl = up(fl[k].data(), (int64_t)fl[k].size());
-                const int len = (int)fl[k].size(), nt = kFused[k].nt;
-                const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
-                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
-                const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-                cluster_launch(nt, kFused[k].per, grid, smem, st, d, dl, len, kFused[k].nmax, f_counters + k); n_launches += 1;
-            }
+        for (int k = N_FUSED - 1; k >= 0; k--) {
+            int first, len; range_of(k ? kFused[k - 1].nmax + 1 : 1, kFused[k].nmax, first, len);
+            if (!len) continue;
+            const int nt = kFused[k].nt;
+            const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
+            const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
+            cluster_launch(nt, kFused[k].per, grid, smem, st, d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k); n_launches += 1;
         }
         CK(cudaEventRecord(cx->ev[11], st));
-        // ---- cluster editing
-        {
-            // size classes: chains below 128 reads run warp-per-chain out of shared memory, the rest
-            // block-per-chain out of HBM/L2
-            static const int cls_max[12] = {16, 24, 32, 40, 48, 56, 64, 72, 80, 96, 112, 127};
-            constexpr int NC = 12;
-            std::vector<int32_t> lists[NC + 1];
-            for (int64_t c = 0; c < C; c++) {
-                const int64_t n = h_frow_off[c + 1] - h_frow_off[c];
-                if (n <= 0 || h_fused[c]) continue;
-                int k = NC; for (int x = 0; x < NC; x++) if (n <= cls_max[x]) { k = x; break; }
-                lists[k].push_back((int32_t)c);
-            }
-            int32_t* ce_counters = dzero<int32_t>(NC + 1);
-            for (int k = NC; k >= 0; k--) {
-                if (lists[k].empty()) continue;
-                std::stable_sort(lists[k].begin(), lists[k].end(), [&](int32_t a, int32_t b) { return h_nfinal[a] > h_nfinal[b]; });
-                const int32_t* dl = up(lists[k].data(), (int64_t)lists[k].size());
-                const int len = (int)lists[k].size();
-                if (k < NC) {
-                    const size_t slot = cw_slot_bytes(cls_max[k]), budget = 200 * 1024;
-                    const int wpb = (int)std::max<size_t>(1, std::min<size_t>(CW_WARPS, budget / slot));
-                    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, budget / (wpb * slot)));
-                    const int64_t grid = std::min<int64_t>((len + wpb - 1) / wpb, (int64_t)sms * per_sm);
-                    k_cluster_warp<<<(unsigned)grid, wpb * 32, wpb * slot, st>>>(d, dl, len, cls_max[k], ce_counters + k); n_launches += 1;
-                } else {
-                    k_cluster_edit<<<std::min<int64_t>(len, (int64_t)sms * 4), CE_THREADS, 0, st>>>(d, dl, len, ce_counters + k); n_launches += 1;
-                }
-            }
+        // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one block per chain
+        if (nf_unfused) {
+            int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
+            if (len) { k_cluster_edit<<<std::min<int64_t>(len, (int64_t)sms * 4), CE_THREADS, 0, st>>>(d, dv_order + first, len, counters + 2); n_launches += 1; }
         }
         CK(cudaEventRecord(cx->ev[4], st));
         // ---- coverage / consensus, threading
@@ -566,7 +560,7 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     std::lock_guard<std::mutex> g(cx->mu);
     CK(cudaSetDevice(device));
     if (cx->out_busy) throw ArgFail{"previous ahs_batch_out of this device was not released with ahs_free_out"};
-    cx->dev.reset(); cx->outp.reset();
+    cx->dev.reset(); cx->outp.reset(); cx->pin.reset();
     if (sz.C == 0) { fill_empty_out(out, cx, in->ploidy); cx->out_busy = true; return; }
     Pipeline pl; pl.cx = cx; pl.in = in; pl.sz = sz;
     cudaEvent_t e0 = cx->ev[8], e1 = cx->ev[9];

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
 __host__ __device__ constexpr int cc_min_blocks(int nt, int per) {
     // registers per thread ~ 40 + 3 per slot
     return per <= 4 ? (nt <= 32 ? 32 : nt <= 64 ? 20 : nt <= 128 ? 10 : nt <= 192 ? 6 : nt <= 256 ? 5 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1)
-                    : (nt <= 32 ? 24 : nt <= 64 ? 16 : nt <= 96 ? 10 : nt <= 128 ? 8 : nt <= 192 ? 5 : nt <= 256 ? 4 : nt <= 512 ? 2 : 1);
+                    : (nt <= 32 ? 32 : nt <= 64 ? 18 : nt <= 96 ? 12 : nt <= 128 ? 9 : nt <= 192 ? 6 : nt <= 256 ? 4 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,9 +419,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 for (int k = 0; k < PER; k++) if (!(key[k] & CC_GONE) && P[k] == so.maxP) kmine = min(kmine, (int)(key[k] & 0xffffu));
                 const int kP = cc_min_key(kmine, scal + 4, tid, kphase);
                 const int a = kP >> 8, b = kP & 0xff;
-                const int old = W[a * ns + b];
-                __syncthreads();
-                if (tid == 0) { W[a * ns + b] = CC_FORB; W[b * ns + a] = CC_FORB; }
+                const int old = W[a * ns + b];                  // set to forbidden after the step's last barrier
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
                     const uint32_t kq = key[k];
@@ -439,6 +437,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 }
                 force_single = false;
                 so = cc_reduce<NT>(mine, red, tid, phase);
+                if (tid == 0) { W[a * ns + b] = CC_FORB; W[b * ns + a] = CC_FORB; }      // read next after the next step's first barrier
             } else {
                 // ------------------------------------------------ round: forbid negative candidates with icp > M at once.
                 // Forbidding a negative edge changes no icf and only raises icp values, so every such edge stays

@@ -26,6 +26,7 @@
 
 namespace ahs {
 
+constexpr int32_t AHS_OUT_MALLOCED = 0x4d414c43;
 static thread_local char g_err[512] = "";
 static void set_err(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
 
@@ -691,7 +692,7 @@ int ahs_unpin_host(const void* ptr) {
 
 void ahs_free_out(ahs_batch_out* out) {
     if (!out) return;
-    if (out->n_chains < 0) {                      // gathered multi-device result: malloc'ed
+    if (out->reserved == AHS_OUT_MALLOCED) {      // gathered multi-device result: malloc'ed
         free(out->status); free(out->read_off); free(out->read_id); free(out->read_mapq); free(out->read_cluster); free(out->cell_off);
         free(out->cell_pos); free(out->cell_allele); free(out->n_clusters); free(out->pos_off); free(out->pos); free(out->path);
         free(out->hap_allele); free(out->dp_cost); free(out->maxpos);
@@ -758,7 +759,7 @@ int ahs_phase_batch_multi(const ahs_batch_in* in, ahs_batch_out* out, const int*
             out->bytes_consensus += outs[g].bytes_consensus;
             ahs_free_out(&outs[g]);
         }
-        out->n_chains = -C;        // negative marks a malloc'ed (gathered) result for ahs_free_out; fixed below
+        out->n_chains = C; out->reserved = AHS_OUT_MALLOCED;       // tells ahs_free_out that the arrays are malloc'ed
         out->ploidy = p;
         out->status = mdup(status); out->read_off = mdup(read_off); out->read_id = mdup(read_id); out->read_mapq = mdup(read_mapq);
         out->read_cluster = mdup(read_cluster); out->cell_off = mdup(cell_off); out->cell_pos = mdup(cell_pos); out->cell_allele = mdup(cell_allele);

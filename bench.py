@@ -254,8 +254,15 @@ def main():
         stages[name] = {"ms": t[ms_key], "bound": "latency / integer pipes (not an HBM-roofline stage)"}
     dominant = max(("project", "rows", "score", "cluster_edit", "consensus", "thread_dp"), key=lambda k: stages[k]["ms"])
     sc = stages["score"]
-    roofline = {"bound": "hbm", "kernel": "score = k_read_rates + k_pair_scores (read-pair agreement scoring)",
-                "achieved": sc["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": sc["frac"], "traffic": None,
+    traffic = None                     # dram bytes of the scoring kernels from the committed `ncu --set full` capture
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and args.workload == "cfg2" and args.scale == 1.0:
+        try:
+            traffic = json.load(open(tp)).get("score_dram_bytes_per_pass")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "score = k_score_chain launches (read-pair agreement scoring, K2; one pass = all size classes)",
+                "achieved": sc["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": sc["frac"], "traffic": traffic,
                 "peak_source": peak_src, "dominant_stage_by_time": dominant, "stages": stages}
     line = {"metric": METRIC, "value": cells / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes / i32-i64 fixed point",

@@ -1,5 +1,7 @@
 """-m gpu: the CUDA path, through the C ABI, against the CPU oracle on the same seeded inputs.
 Bar: bit-exact on every output array (integer / index work; dp_cost is integer valued)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -107,3 +109,61 @@ def test_malformed_batches_are_rejected_not_mis_phased():
         api.phase_batch(_broken(b, enode_off=eo))
     # the library is still usable afterwards
     assert not api.phase_batch(b).diff(oracle_phase(b))
+
+
+def test_cfg2_full_size_against_oracle():
+    # BASELINE configs[1] at full size: 50k chains, 2M bubbles, 45.7M cells — the bench workload itself
+    b = synth.generate(synth.config("cfg2"))
+    got = api.phase_batch(b, copy=False)
+    want = oracle_phase(b, os.cpu_count() or 1)
+    try:
+        assert not got.diff(want)
+        assert got.n_chains_ok == 50000 and got.n_cells == want.n_cells
+    finally:
+        got.release()
+
+
+def test_chains_are_independent_permutation_property():
+    # size-independent property: phasing a permutation of the chains gives the permuted result
+    b = synth.generate(synth.config("cfg2", 0.02))
+    perm = np.random.default_rng(3).permutation(b.n_chains)
+    r1 = api.phase_batch(b)
+    r2 = api.phase_batch(b.select(perm))
+    assert np.array_equal(r2.status, r1.status[perm]) and np.array_equal(r2.dp_cost, r1.dp_cost[perm])
+    assert np.array_equal(r2.n_clusters, r1.n_clusters[perm])
+    for k, c in enumerate(perm[:200]):
+        a0, a1 = r1.read_off[c], r1.read_off[c + 1]
+        b0, b1 = r2.read_off[k], r2.read_off[k + 1]
+        assert np.array_equal(r1.read_cluster[a0:a1], r2.read_cluster[b0:b1])
+        p0, p1 = r1.pos_off[c] * 2, r1.pos_off[c + 1] * 2
+        q0, q1 = r2.pos_off[k] * 2, r2.pos_off[k + 1] * 2
+        assert np.array_equal(r1.hap_allele[p0:p1], r2.hap_allele[q0:q1]) and np.array_equal(r1.path[p0:p1], r2.path[q0:q1])
+
+
+def test_phasing_recovers_the_simulated_haplotypes():
+    # domain property at size: with 5 % allele error the emitted haplotypes agree with the truth at > 95 % of the
+    # covered positions of long enough chains (up to the haplotype swap)
+    b = synth.generate(synth.config("cfg2", 0.02))
+    r = api.phase_batch(b)
+    truth = b.truth["hap_allele"].reshape(-1, 2)
+    agree = tot = 0
+    for c in range(b.n_chains):
+        if r.status[c] != 0:
+            continue
+        q0, q1 = int(r.pos_off[c]), int(r.pos_off[c + 1])
+        if q1 - q0 < 10:
+            continue
+        gb = int(b.bubble_off[c]) + r.pos[q0:q1]
+        t = truth[gb]
+        h = r.hap_allele[q0 * 2:q1 * 2].reshape(-1, 2)
+        same = int((h == t).all(axis=1).sum()); swap = int((h == t[:, ::-1]).all(axis=1).sum())
+        agree += max(same, swap); tot += q1 - q0
+    assert tot > 1000 and agree / tot > 0.95
+
+
+def test_multi_device_lpt_gather():
+    if api.load_library().ahs_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    b = synth.generate(synth.config("cfg2", 0.02))
+    got = api.phase_batch(b, devices=[0, 1])
+    assert not got.diff(oracle_phase(b))

@@ -250,6 +250,10 @@ __host__ __device__ constexpr int cc_min_blocks(int nt, int per) {
                     : (nt <= 32 ? 32 : nt <= 64 ? 18 : nt <= 96 ? 12 : nt <= 128 ? 9 : nt <= 192 ? 6 : nt <= 256 ? 4 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1);
 }
 
+// lanes that share one node x in the fresh-cost pass of a merge (threads / G >= largest n of the block size's classes)
+__host__ __device__ constexpr int cc_fresh_g(int nt) { return nt <= 32 ? 1 : nt <= 192 ? 2 : nt <= 768 ? 4 : 8; }
+static_assert(CC_MAXN <= 128, "k_cluster_chain walks rows in four 32-lane strides");
+
 // ------------------------------------------------------------------------------------------------
 // cluster editing of one chain per block (rule R2)
 // ------------------------------------------------------------------------------------------------
@@ -369,23 +373,26 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                     }
                 }
                 __syncthreads();
-                // fresh induced costs of the pairs (a,x): one warp per x, lanes over the third nodes
+                // fresh induced costs of the pairs (a,x): G adjacent lanes per x share the third nodes
                 {
+                    constexpr int G = cc_fresh_g(NT);
                     const int nact = scal[0];
-                    for (int xi = wid; xi < nact; xi += NW) {
-                        const int x = alist[xi];
-                        const int w = node[x].z;
-                        if (w == 0 || w == CC_FORB) continue;
+                    const int xi = tid / G, g = tid % G;
+                    int x = 0, w = 0;
+                    if (xi < nact) { x = alist[xi]; w = node[x].z; }
+                    const bool live = w != 0 && w != CC_FORB;
+                    int f = 0, p = 0;
+                    if (live) {
                         const int32_t* rx = W + x * ns;
-                        int f = 0, p = 0;
-                        for (int vi = lane; vi < nact; vi += 32) {
+                        for (int vi = g; vi < nact; vi += G) {
                             const int v = alist[vi];
                             const int t1 = node[v].z, t2 = rx[v];
                             f += cc_tf(t1, t2); p += cc_tp(t1, t2);
                         }
-                        f = warp_sum_i32(f); p = warp_sum_i32(p);
-                        if (lane == 0) { frF[x] = f + max(w, 0); frP[x] = p + max(-w, 0); }
                     }
+#pragma unroll
+                    for (int o = G >> 1; o > 0; o >>= 1) { f += __shfl_xor_sync(0xffffffffu, f, o); p += __shfl_xor_sync(0xffffffffu, p, o); }
+                    if (live && g == 0) { frF[x] = f + max(w, 0); frP[x] = p + max(-w, 0); }
                 }
                 __syncthreads();
                 // every slot: pairs through a or b take the fresh costs (or die), all others swap the terms through
@@ -467,17 +474,22 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 for (int x = wid; x < n; x += NW) {
                     if (!nodefl[x]) continue;
                     const int32_t* rx = W + x * ns;
-                    for (int t = lane; t < n; t += 32) {
-                        const int32_t* rt = W + t * ns;
-                        int g = 0;
-                        for (int m = 0; m < mw; m++)
-                            for (uint32_t bits = fmask[x * mw + m]; bits; bits &= bits - 1) {
-                                const int bb = m * 32 + __ffs(bits) - 1;
-                                const int wtb = rt[bb];
-                                if (wtb > 0) g += max(wtb + rx[bb], 0);            // rx[bb] = weight of the forbidden edge < 0
-                            }
-                        D[x * ns + t] = g;
-                    }
+                    int g0 = 0, g1 = 0, g2 = 0, g3 = 0;            // t = lane, lane + 32, lane + 64, lane + 96  (n <= 128)
+                    for (int m = 0; m < mw; m++)
+                        for (uint32_t bits = fmask[x * mw + m]; bits; bits &= bits - 1) {      // warp-uniform
+                            const int bb = m * 32 + __ffs(bits) - 1;
+                            const int old = rx[bb];                                           // weight of the forbidden edge < 0
+                            const int32_t* rb = W + bb * ns;                                  // w_t,bb = w_bb,t: a row walk
+                            if (lane < n) g0 += max(max(rb[lane], 0) + old, 0);
+                            if (lane + 32 < n) g1 += max(max(rb[lane + 32], 0) + old, 0);
+                            if (lane + 64 < n) g2 += max(max(rb[lane + 64], 0) + old, 0);
+                            if (lane + 96 < n) g3 += max(max(rb[lane + 96], 0) + old, 0);
+                        }
+                    int32_t* dx = D + x * ns;
+                    if (lane < n) dx[lane] = g0;
+                    if (lane + 32 < n) dx[lane + 32] = g1;
+                    if (lane + 64 < n) dx[lane + 64] = g2;
+                    if (lane + 96 < n) dx[lane + 96] = g3;
                 }
                 __syncthreads();
                 // the forbidden edges leave (their old weight is parked in D[x][y], which nobody else reads), the icp of

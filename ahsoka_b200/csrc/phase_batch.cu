@@ -112,6 +112,7 @@ static void check_classes(size_t smem_optin) {
     for (int k = 0; k < N_FUSED; k++) {
         if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) throw LimitFail{"device shared memory too small for the cluster-editing classes"};
         if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)kFused[k].per * kFused[k].nt) throw std::logic_error("cluster class table: slots");
+        if (kFused[k].nmax * cc_fresh_g(kFused[k].nt) > kFused[k].nt) throw std::logic_error("cluster class table: fresh-cost lanes");
     }
     if (kFused[N_FUSED - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
     for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax) > smem_optin) throw std::logic_error("score class table");

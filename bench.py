@@ -127,7 +127,9 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     exe = os.path.join(ROOT, "oracle", "_ref", "Ahsoka_ref")
-    n_chains = args.ref_chains
+    # bounded sample: the reference-verbatim CLI costs ~2.6 s per cfg2 chain on one core (its projection is
+    # O(bubbles x alleles x entries)); keep the whole K+W run near 2-3 minutes
+    n_chains = args.ref_chains if args.ref_chains > 0 else int(max(2, min(12, 150.0 / (2.6 * (args.steps + args.warmup)))))
     prm = synth.config(args.workload, 1.0)
     prm.n_chains = n_chains
     times, cells, chains = [], 0, 0
@@ -176,7 +178,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--ref-chains", type=int, default=12)
+    ap.add_argument("--ref-chains", type=int, default=0, help="chains in the reference-arm sample (0 = sized from steps + warmup)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

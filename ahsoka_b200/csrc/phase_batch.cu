@@ -59,7 +59,7 @@ struct Pool {
 };
 
 struct Ctx {
-    int device = -1; cudaStream_t stream = nullptr; Pool dev{false}, pin{true}, outp{true};
+    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr; Pool dev{false}, pin{true}, outp{true};
     int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
     cudaEvent_t ev[12];
     size_t smem_optin = 0;
@@ -127,6 +127,8 @@ static Ctx* get_ctx(int device) {
     CK(cudaSetDevice(device));
     Ctx* c = new Ctx(); c->device = device;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_cells, cudaEventDisableTiming));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sms = prop.multiProcessorCount;
     // fixed-point log tables of rule R1 (oracle/core/phase_core.hpp): llrint(ln(x/1024) * 2^20)
@@ -197,6 +199,8 @@ struct Pipeline {
     int32_t *h_status = nullptr, *h_nfinal = nullptr, *h_npos = nullptr;      // pinned: D2H targets of sync #1
     char *sg_h = nullptr, *sg_d = nullptr; size_t sg_cap = 0;                   // pinned / device staging block of phase 2
     float ms_fused = 0;
+    bool early_out = false;                                                     // download the matrix while the clustering runs
+    int32_t *e_read_id = nullptr, *e_read_mapq = nullptr, *e_cell_pos = nullptr, *e_pos = nullptr; int64_t* e_cell_off = nullptr; uint8_t* e_cell_allele = nullptr;
     int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0, h_slots = 0;
     float ms[8] = {0};
     int n_launches = 0;
@@ -431,6 +435,15 @@ struct Pipeline {
         if (NP) k_owner<<<grid_for(NP, TB, sms), TB, 0, st>>>(d.pos_off, (int)C, NP, d.pos_chain); n_launches += 1;
         if (NF) k_pack_rows<<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        // ---- CSR cells of the final matrix; with host output they travel D2H on a second stream under the clustering
+        scan(d.fr_nv, NF, d.cell_off);
+        if (NF) k_write_cells<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (early_out) {
+            CK(cudaEventRecord(cx->ev_cells, st));
+            CK(cudaStreamWaitEvent(cx->stream2, cx->ev_cells, 0));
+            e_read_id = down2(d.fr_id, NF); e_read_mapq = down2(d.fr_mapq, NF); e_cell_off = down2(d.cell_off, NF + 1);
+            e_cell_pos = down2(d.cell_pos, h_tot_cells); e_cell_allele = down2(d.cell_allele, h_tot_cells); e_pos = down2(d.pos, NP);
+        }
         CK(cudaEventRecord(cx->ev[2], st));
         // ---- scoring
         if (nf_unfused) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
@@ -470,9 +483,6 @@ struct Pipeline {
         if (NP && in->ploidy == 2) { k_thread2<<<(unsigned)std::min<int64_t>((C + 7) / 8, (int64_t)sms * 8), 256, 0, st>>>(d, counters + 1); n_launches += 1; }
         else if (NP) { k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1; }
         CK(cudaEventRecord(cx->ev[6], st));
-        // ---- CSR cells
-        scan(d.fr_nv, NF, d.cell_off);
-        if (NF) k_write_cells<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaEventRecord(cx->ev[7], st));
         CK(cudaGetLastError());
     }
@@ -496,6 +506,11 @@ struct Pipeline {
         if (n > 0) CK(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, cx->stream));
         return h;
     }
+    template <class T> T* down2(const T* dptr, int64_t n) {
+        T* h = cx->outp.get<T>((size_t)std::max<int64_t>(n, 1));
+        if (n > 0) CK(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, cx->stream2));
+        return h;
+    }
     template <class T> T* hostcopy(const std::vector<T>& v) {
         T* h = cx->outp.get<T>(std::max<size_t>(v.size(), 1));
         if (!v.empty()) memcpy(h, v.data(), v.size() * sizeof(T));
@@ -507,17 +522,23 @@ struct Pipeline {
         out->n_chains = (int32_t)C; out->ploidy = p;
         out->status = down(d.ch_status, C);
         out->read_off = hostcopy(h_frow_off); out->pos_off = hostcopy(h_pos_off);
-        out->read_id = down(d.fr_id, NF); out->read_mapq = down(d.fr_mapq, NF); out->read_cluster = down(d.fr_cluster, NF);
-        out->cell_off = down(d.cell_off, NF + 1);
-        out->n_clusters = down(d.ch_nclusters, C); out->pos = down(d.pos, NP);
+        out->read_cluster = down(d.fr_cluster, NF);
+        out->n_clusters = down(d.ch_nclusters, C);
         out->path = down(d.path, NP * p); out->hap_allele = down(d.hap_allele, NP * p); out->dp_cost = down(d.dp_cost, C);
         out->maxpos = down(d.ch_maxpos, C);
         int64_t* h_pairs = cx->outp.get<int64_t>(1);
         CK(cudaMemcpyAsync(h_pairs, d.tot_pairs, 8, cudaMemcpyDeviceToHost, cx->stream));
+        const int64_t n_cells = h_tot_cells;
+        if (early_out) {
+            out->read_id = e_read_id; out->read_mapq = e_read_mapq; out->cell_off = e_cell_off; out->cell_pos = e_cell_pos;
+            out->cell_allele = e_cell_allele; out->pos = e_pos;
+            CK(cudaStreamSynchronize(cx->stream2));
+        } else {
+            out->read_id = down(d.fr_id, NF); out->read_mapq = down(d.fr_mapq, NF); out->cell_off = down(d.cell_off, NF + 1);
+            out->cell_pos = down(d.cell_pos, n_cells); out->cell_allele = down(d.cell_allele, n_cells); out->pos = down(d.pos, NP);
+        }
         CK(cudaStreamSynchronize(cx->stream));
-        const int64_t n_cells = out->cell_off[NF];
-        out->cell_pos = down(d.cell_pos, n_cells); out->cell_allele = down(d.cell_allele, n_cells);
-        CK(cudaStreamSynchronize(cx->stream));
+        if (out->cell_off[NF] != n_cells) throw std::runtime_error("cell count mismatch");
         out->n_cells = n_cells; out->n_pairs = *h_pairs / 2;
         int64_t ok = 0; for (int64_t c = 0; c < C; c++) ok += out->status[c] == AHS_CHAIN_OK;
         out->n_chains_ok = ok;
@@ -562,9 +583,10 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     std::lock_guard<std::mutex> g(cx->mu);
     CK(cudaSetDevice(device));
     if (cx->out_busy) throw ArgFail{"previous ahs_batch_out of this device was not released with ahs_free_out"};
+    CK(cudaStreamSynchronize(cx->stream2)); CK(cudaStreamSynchronize(cx->stream));      // nothing of a failed earlier call is in flight
     cx->dev.reset(); cx->outp.reset(); cx->pin.reset();
     if (sz.C == 0) { fill_empty_out(out, cx, in->ploidy); cx->out_busy = true; return; }
-    Pipeline pl; pl.cx = cx; pl.in = in; pl.sz = sz;
+    Pipeline pl; pl.cx = cx; pl.in = in; pl.sz = sz; pl.early_out = iters == 0;
     cudaEvent_t e0 = cx->ev[8], e1 = cx->ev[9];
     CK(cudaEventRecord(e0, cx->stream));
     pl.upload();

@@ -136,11 +136,11 @@ __device__ __forceinline__ bool warp_entry_has(const int32_t* __restrict__ nodes
 // (hash hit) decides the two containment tests of the reference (is_subset with and without the end nodes, :495-548).
 // Common case, decided by the lane alone: a 3-node path whose end nodes are the neighbours of the trigger in the
 // alignment.  Everything else is decided by the whole warp scanning the entry.
-__global__ void __launch_bounds__(256) k_project(DB d) {
+__global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t e_end) {
     AHS_BAIL_ON_ERR(d);
     const int warps_per_block = blockDim.x >> 5;
     const int lane = lane_id();
-    for (int64_t ge = blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); ge < d.NE; ge += (int64_t)gridDim.x * warps_per_block) {
+    for (int64_t ge = e_begin + blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); ge < e_end; ge += (int64_t)gridDim.x * warps_per_block) {
         const int c = d.entry_chain[ge];
         const int64_t b0 = d.bubble_off[c];
         const int B = (int)(d.bubble_off[c + 1] - b0);

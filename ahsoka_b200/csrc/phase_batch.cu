@@ -59,7 +59,7 @@ struct Pool {
 };
 
 struct Ctx {
-    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr; Pool dev{false}, pin{true}, outp{true};
+    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr, ev_en[8]; Pool dev{false}, pin{true}, outp{true};
     int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
     cudaEvent_t ev[12];
     size_t smem_optin = 0;
@@ -129,6 +129,7 @@ static Ctx* get_ctx(int device) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_cells, cudaEventDisableTiming));
+    for (auto& e : c->ev_en) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sms = prop.multiProcessorCount;
     // fixed-point log tables of rule R1 (oracle/core/phase_core.hpp): llrint(ln(x/1024) * 2^20)
@@ -200,6 +201,7 @@ struct Pipeline {
     char *sg_h = nullptr, *sg_d = nullptr; size_t sg_cap = 0;                   // pinned / device staging block of phase 2
     float ms_fused = 0;
     bool early_out = false;                                                     // download the matrix while the clustering runs
+    static constexpr int N_EN = 6; int64_t en_cut[N_EN + 1] = {0};              // entry ranges whose alignment nodes are uploaded as one slice
     int32_t *e_read_id = nullptr, *e_read_mapq = nullptr, *e_cell_pos = nullptr, *e_pos = nullptr; int64_t* e_cell_off = nullptr; uint8_t* e_cell_allele = nullptr;
     int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0, h_slots = 0;
     float ms[8] = {0};
@@ -209,6 +211,12 @@ struct Pipeline {
         T* p = cx->dev.get<T>((size_t)std::max<int64_t>(n, 1));
         if (n > 0) CK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, cx->stream));
         return p;
+    }
+    // host-derived arrays go through pinned staging: an async copy from pageable memory would first drain the stream
+    template <class T> const T* up_pinned(const T* h, int64_t n) {
+        T* stage = cx->pin.get<T>((size_t)std::max<int64_t>(n, 1));
+        if (n > 0) memcpy(stage, h, n * sizeof(T));
+        return up(stage, n);
     }
     template <class T> T* dalloc(int64_t n) { return cx->dev.get<T>((size_t)std::max<int64_t>(n, 1)); }
     template <class T> T* dzero(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0, std::max<int64_t>(n, 1) * sizeof(T), cx->stream)); return p; }
@@ -221,7 +229,25 @@ struct Pipeline {
         d.NB = sz.NB; d.NA = sz.NA; d.NAN_ = sz.NAN_; d.NR = sz.NR; d.NE = sz.NE; d.NEN = sz.NEN;
         d.bubble_off = up(in->bubble_off, C + 1); d.allele_off = up(in->allele_off, sz.NB + 1); d.anode_off = up(in->anode_off, sz.NA + 1);
         d.read_off = up(in->read_off, C + 1); d.entry_off = up(in->entry_off, C + 1); d.enode_off = up(in->enode_off, sz.NE + 1);
-        d.anode = up(in->anode, sz.NAN_); d.enode = up(in->enode, sz.NEN); d.entry_read = up(in->entry_read, sz.NE);
+        // the alignment nodes are 3/4 of the batch: they go up in N_EN slices on the second stream, and the projection of
+        // slice i runs under the upload of slice i+1
+        {
+            int32_t* en = cx->dev.get<int32_t>((size_t)std::max<int64_t>(sz.NEN, 1));
+            d.enode = en;
+            for (int i = 0; i <= N_EN; i++) {
+                const int64_t target = sz.NEN / N_EN * i;
+                en_cut[i] = i == N_EN ? sz.NE : (int64_t)(std::lower_bound(in->enode_off, in->enode_off + sz.NE, target) - in->enode_off);
+            }
+            en_cut[0] = 0;
+            for (int i = 0; i < N_EN; i++) {
+                en_cut[i + 1] = std::max(en_cut[i + 1], en_cut[i]);
+                const int64_t o0 = std::min<int64_t>(std::max<int64_t>(in->enode_off[en_cut[i]], 0), sz.NEN);
+                const int64_t o1 = i + 1 == N_EN ? sz.NEN : std::min<int64_t>(std::max<int64_t>(in->enode_off[en_cut[i + 1]], o0), sz.NEN);
+                if (o1 > o0) CK(cudaMemcpyAsync(en + o0, in->enode + o0, (size_t)(o1 - o0) * 4, cudaMemcpyHostToDevice, cx->stream2));
+                CK(cudaEventRecord(cx->ev_en[i], cx->stream2));
+            }
+        }
+        d.anode = up(in->anode, sz.NAN_); d.entry_read = up(in->entry_read, sz.NE);
         d.entry_identity = up(in->entry_identity, sz.NE);
         d.stage_a_order = in->stage_a_order ? up(in->stage_a_order, sz.NB) : nullptr;
         h_mrow_off.assign(C, 0);
@@ -233,7 +259,7 @@ struct Pipeline {
             if (acc & 1) acc++;                                    // keep chain bases 4-byte aligned for the 32-bit atomics
         }
         sz.M = acc;
-        d.mrow_off = (int64_t*)up(h_mrow_off.data(), C);
+        d.mrow_off = (int64_t*)up_pinned(h_mrow_off.data(), C);
         // per-chain trigger tables: power of two >= 2 x alleles of the chain
         std::vector<int64_t> hoff(C); std::vector<uint32_t> hmaskc(C);
         h_slots = 0;
@@ -243,7 +269,7 @@ struct Pipeline {
             int64_t cap = 4; while (cap < 2 * nal) cap <<= 1;
             hoff[c] = h_slots; hmaskc[c] = (uint32_t)(cap - 1); h_slots += cap;
         }
-        d.hoff = up(hoff.data(), C); d.hmaskc = up(hmaskc.data(), C);
+        d.hoff = up_pinned(hoff.data(), C); d.hmaskc = up_pinned(hmaskc.data(), C);
         (void)st;
     }
 
@@ -314,7 +340,11 @@ struct Pipeline {
         if (sz.NB && d.stage_a_order) { k_validate_perm<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d); n_launches += 1;
         // ---- projection
-        if (sz.NE) k_project<<<grid_for(sz.NE, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        for (int i = 0; i < N_EN; i++) {
+            CK(cudaStreamWaitEvent(st, cx->ev_en[i], 0));
+            const int64_t ne = en_cut[i + 1] - en_cut[i];
+            if (ne > 0) { k_project<<<grid_for(ne, 8, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]); n_launches += 1; }
+        }
         CK(cudaEventRecord(cx->ev[1], st));
         if (sz.NR) k_read_stage_a<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;

@@ -59,7 +59,7 @@ struct Pool {
 };
 
 struct Ctx {
-    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr, ev_en[8]; Pool dev{false}, pin{true}, outp{true};
+    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr, ev_en[8], ev_fork = nullptr, ev_join[4]; cudaStream_t side[4]; Pool dev{false}, pin{true}, outp{true};
     int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
     cudaEvent_t ev[12];
     size_t smem_optin = 0;
@@ -130,6 +130,9 @@ static Ctx* get_ctx(int device) {
     CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_cells, cudaEventDisableTiming));
     for (auto& e : c->ev_en) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (auto& e : c->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& t : c->side) CK(cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking));
     for (auto& e : c->ev) CK(cudaEventCreate(&e));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sms = prop.multiProcessorCount;
     // fixed-point log tables of rule R1 (oracle/core/phase_core.hpp): llrint(ln(x/1024) * 2^20)
@@ -491,15 +494,19 @@ struct Pipeline {
         CK(cudaEventRecord(cx->ev[3], st));
         // ---- cluster editing out of shared memory
         CK(cudaEventRecord(cx->ev[10], st));
-        for (int k = N_FUSED - 1; k >= 0; k--) {
+        // the size classes run on four side streams so that the tail of one class overlaps the bulk of the next
+        CK(cudaEventRecord(cx->ev_fork, st));
+        for (auto& t : cx->side) CK(cudaStreamWaitEvent(t, cx->ev_fork, 0));
+        for (int k = N_FUSED - 1, q = 0; k >= 0; k--) {
             int first, len; range_of(k ? kFused[k - 1].nmax + 1 : 1, kFused[k].nmax, first, len);
             if (!len) continue;
             const int nt = kFused[k].nt;
             const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
             const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-            cluster_launch(nt, kFused[k].per, grid, smem, st, d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k); n_launches += 1;
+            cluster_launch(nt, kFused[k].per, grid, smem, cx->side[q++ & 3], d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k); n_launches += 1;
         }
+        for (int i = 0; i < 4; i++) { CK(cudaEventRecord(cx->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, cx->ev_join[i], 0)); }
         CK(cudaEventRecord(cx->ev[11], st));
         // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one block per chain
         if (nf_unfused) {

@@ -59,7 +59,7 @@ struct Pool {
 };
 
 struct Ctx {
-    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr, ev_en[8], ev_fork = nullptr, ev_join[4]; cudaStream_t side[4]; Pool dev{false}, pin{true}, outp{true};
+    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr, ev_en[8], ev_fork = nullptr, ev_join[8]; cudaStream_t side[8]; Pool dev{false}, pin{true}, outp{true};
     int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
     cudaEvent_t ev[12];
     size_t smem_optin = 0;
@@ -504,9 +504,9 @@ struct Pipeline {
             const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
             const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-            cluster_launch(nt, kFused[k].per, grid, smem, cx->side[q++ & 3], d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k); n_launches += 1;
+            cluster_launch(nt, kFused[k].per, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k); n_launches += 1;
         }
-        for (int i = 0; i < 4; i++) { CK(cudaEventRecord(cx->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, cx->ev_join[i], 0)); }
+        for (int i = 0; i < 8; i++) { CK(cudaEventRecord(cx->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, cx->ev_join[i], 0)); }
         CK(cudaEventRecord(cx->ev[11], st));
         // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one block per chain
         if (nf_unfused) {

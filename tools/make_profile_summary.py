@@ -1,0 +1,112 @@
+"""Turn the scratch ncu exports in gpurun_out/ into the committed evidence under profiles/.
+usage: python tools/make_profile_summary.py <tag>   (reads gpurun_out/<tag>_launches_cfg2.csv, <tag>_full_raw.csv,
+<tag>_bench_cfg2.json; writes profiles/<tag>_*.{csv,json,md} and profiles/traffic.json)"""
+import collections
+import csv
+import json
+import os
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+KEEP = ["ID", "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "sm__inst_executed.avg.per_cycle_elapsed",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
+
+
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def main():
+    shutil.copy(os.path.join(G, f"{tag}_launches_cfg2.csv"), os.path.join(P, f"{tag}_launches_cfg2.csv"))
+    shutil.copy(os.path.join(G, f"{tag}_bench_cfg2.json"), os.path.join(P, f"{tag}_bench_cfg2.json"))
+    rows = list(csv.reader(open(os.path.join(G, f"{tag}_full_raw.csv"))))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    stall = [h for h in hdr if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h]
+    cols = [h for h in KEEP if h in hdr] + stall
+    idx = [hdr.index(h) for h in cols]
+    with open(os.path.join(P, f"{tag}_ncu_full_metrics.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([c.replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active.ratio", "") for c in cols])
+        w.writerow([units[i] for i in idx])
+        for r in data:
+            w.writerow([r[i] for i in idx])
+    # launch list -> per kernel totals of one pass
+    lr = [r for r in csv.reader(l for l in open(os.path.join(G, f"{tag}_launches_cfg2.csv")) if not l.startswith("=="))]
+    lh = lr[0]
+    iN, iV = lh.index("Kernel Name"), lh.index("Metric Value")
+    seq = [(r[iN].split("(")[0], float(r[iV].replace(",", "")) / 1e3) for r in lr[1:]]
+    passes, cur = [], []
+    for n, t in seq:
+        if n == "k_validate" and cur:
+            passes.append(cur); cur = []
+        cur.append((n, t))
+    passes.append(cur)
+    p = passes[min(4, len(passes) - 2)] if len(passes) > 2 else passes[0]      # a warm resident pass
+    agg = collections.OrderedDict()
+    for n, t in p:
+        a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += t
+    tot = sum(t for _, t in p)
+    bench = json.load(open(os.path.join(G, f"{tag}_bench_cfg2.json")))
+    # scoring traffic per pass from the full capture
+    iK, iR, iWt = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    score_traffic = sum(to_bytes(r[iR], units[iR]) + to_bytes(r[iWt], units[iWt]) for r in data if "k_score_chain" in r[iK])
+    n_score = sum(1 for r in data if "k_score_chain" in r[iK])
+    n_per_pass = sum(1 for n, _ in p if n.startswith("void k_score_chain"))
+    if n_score and n_per_pass:
+        score_traffic *= n_per_pass / n_score
+    json.dump({"score_dram_bytes_per_pass": int(score_traffic), "source": f"profiles/{tag}_ncu_full_metrics.csv (k_score_chain rows)"},
+              open(os.path.join(P, "traffic.json"), "w"))
+    with open(os.path.join(P, f"{tag}_summary.md"), "w") as f:
+        f.write(f"# Round 1, snapshot {tag[-1]} — cfg2 (50k chains, 2.0 M bubbles, 45.7 M cells, 56.9 M pairs), one B200\n\n")
+        f.write("Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 1 --warmup 3 "
+                f"--no-cpu-baseline` -> `{tag}_launches_cfg2.csv` (per-launch times are serialised and cold-cache; the SHARES are what to compare).\n"
+                "One warm pass over the batch:\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
+        for n, (k, t) in agg.items():
+            f.write(f"| `{n}` | {k} | {t:.1f} | {100 * t / tot:.1f}% |\n")
+        f.write(f"| **sum** | {len(p)} | {tot:.1f} | |\n\n")
+        st = bench["roofline"]["stages"]
+        f.write(f"Same build, `python bench.py --steps 3 --warmup 3` without ncu (`{tag}_bench_cfg2.json`): "
+                f"**{bench['ms_per_step']:.2f} ms/step = {bench['value']:.3e} cells/s** device-resident, "
+                f"**{bench['e2e']['ms_per_step']:.2f} ms = {bench['e2e']['value']:.3e} cells/s** end to end (H2D {bench['e2e']['h2d_bytes_per_step'] / 1e6:.0f} MB, "
+                f"D2H {bench['e2e']['d2h_bytes_per_step'] / 1e6:.0f} MB inside the call); CPU oracle port on {bench.get('cpu_baseline', {}).get('cores', '?')} threads: "
+                f"{bench.get('cpu_baseline', {}).get('value', 0):.3e} cells/s.\n\n| stage | ms | algorithmic bytes | GB/s | frac of {bench['roofline']['peak']:.0f} GB/s |\n|---|---|---|---|---|\n")
+        for k, v in st.items():
+            if "algorithmic_bytes" in v:
+                f.write(f"| {k} | {v['ms']:.2f} | {v['algorithmic_bytes']} | {v['achieved_gbs']:.1f} | {v['frac']:.4f} |\n")
+            else:
+                f.write(f"| {k} | {v['ms']:.2f} | - | - | - |\n")
+        f.write(f"\n(The cluster classes run on eight side streams, so the stage time is below the sum of its serialised launches.)\n\n"
+                f"`ncu --set full --clock-control none` of the per-chain kernels (`{tag}_ncu_full_metrics.csv`, one row per launch):\n\n"
+                "| kernel | grid x block | ms | IPC | lanes/inst | warps active % | regs | dram R+W MB | top stalls (cycles per issue) |\n|---|---|---|---|---|---|---|---|---|\n")
+        iT, iI, iL, iWA, iRG, iGr, iBl = (hdr.index(x) for x in ("gpu__time_duration.sum", "sm__inst_executed.avg.per_cycle_elapsed",
+                                                                     "smsp__thread_inst_executed_per_inst_executed.ratio",
+                                                                     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+                                                                     "Grid Size", "Block Size"))
+        seen = set()
+        for r in data:
+            name = r[iK].split("(")[0].replace("void ", "")
+            keyk = (name, r[iBl])
+            if keyk in seen and "k_cluster_chain" not in name:
+                continue
+            seen.add(keyk)
+            st_ = sorted(((float(r[hdr.index(h)]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")) for h in stall
+                          if "selected" not in h or "not_selected" in h), reverse=True)[:3]
+            mb = (to_bytes(r[iR], units[iR]) + to_bytes(r[iWt], units[iWt])) / 1e6
+            f.write(f"| `{name}` | {r[iGr]} x {r[iBl]} | {float(r[iT]):.3f} | {float(r[iI]):.2f} | {float(r[iL]):.1f} | {float(r[iWA]):.0f} | {r[iRG]} | {mb:.1f} | "
+                    + ", ".join(f"{n} {v:.1f}" for v, n in st_) + " |\n")
+
+
+if __name__ == "__main__":
+    main()

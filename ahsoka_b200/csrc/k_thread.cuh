@@ -50,18 +50,19 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
                 if (lastp[i] >= b && cl[i] > cur && get_code(rows + (int64_t)i * words, b, BITS)) nxt = min(nxt, cl[i]);
             nxt = warp_min_i32(nxt);
             if (nxt == INT32_MAX) break;
-            uint32_t ac[MAX_ALLELES];
+            constexpr int NA_MAX = BITS == 2 ? 3 : MAX_ALLELES;       // 2-bit codes hold at most 3 alleles
+            uint32_t ac[NA_MAX];
 #pragma unroll
-            for (int a = 0; a < MAX_ALLELES; a++) ac[a] = 0;
+            for (int a = 0; a < NA_MAX; a++) ac[a] = 0;
             for (int i = lo + lane; i <= hi; i += 32)
                 if (lastp[i] >= b && cl[i] == nxt) {
                     const uint32_t code = get_code(rows + (int64_t)i * words, b, BITS);
 #pragma unroll
-                    for (int a = 0; a < MAX_ALLELES; a++) ac[a] += (code == (uint32_t)(a + 1)) ? 1u : 0u;
+                    for (int a = 0; a < NA_MAX; a++) ac[a] += (code == (uint32_t)(a + 1)) ? 1u : 0u;
                 }
             uint32_t cnt = 0, best = 0; int cons = 0;
 #pragma unroll
-            for (int a = 0; a < MAX_ALLELES; a++) if (a < K) {
+            for (int a = 0; a < NA_MAX; a++) if (a < K) {
                 const uint32_t v = (uint32_t)warp_sum_i32((int)ac[a]);
                 cnt += v;
                 if (v > best) { best = v; cons = a; }               // ties -> smallest allele (:633-649, A#13)

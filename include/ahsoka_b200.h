@@ -112,7 +112,7 @@ typedef struct ahs_batch_out {
     float     ms_h2d, ms_project, ms_rows, ms_score, ms_cluster, ms_consensus, ms_thread, ms_d2h;
     float     ms_total_device;   /* first kernel start -> last kernel end, inputs resident */
     int32_t   n_launches;        /* kernels launched per pass over the batch */
-    int32_t   reserved;
+    int32_t   reserved;          /* library-private (how ahs_free_out releases this result); do not touch */
     /* Algorithmic byte counts of the last call (SURVEY.md §8d formulas), for roofline reports. */
     int64_t   bytes_project, bytes_score, bytes_consensus;
 } ahs_batch_out;

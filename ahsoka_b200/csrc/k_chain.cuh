@@ -110,9 +110,9 @@ __host__ __device__ inline size_t cs_smem_bytes(int nmax) {
     return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15) & ~(size_t)15;
 }
 
-// ascending bitonic sort of 32*KPL 64-bit keys held KPL per lane (element e = s*32 + lane)
-template <int KPL>
-__device__ __forceinline__ void warp_sort_u64(uint64_t (&v)[KPL], int lane) {
+// ascending bitonic sort of 32*KPL keys (uint32_t or uint64_t) held KPL per lane (element e = s*32 + lane)
+template <int KPL, class T>
+__device__ __forceinline__ void warp_sort(T (&v)[KPL], int lane) {
 #pragma unroll
     for (int kk = 2; kk <= 32 * KPL; kk <<= 1) {
 #pragma unroll
@@ -123,7 +123,7 @@ __device__ __forceinline__ void warp_sort_u64(uint64_t (&v)[KPL], int lane) {
                     if ((s & (jj >> 5)) == 0) {
                         const int s2 = s | (jj >> 5);
                         const bool up = ((s * 32) & kk) == 0;          // lane bits are below jj >= 32 <= kk/2
-                        const uint64_t a = v[s], b = v[s2];
+                        const T a = v[s], b = v[s2];
                         if ((a > b) == up) { v[s] = b; v[s2] = a; }
                     }
                 }
@@ -131,7 +131,7 @@ __device__ __forceinline__ void warp_sort_u64(uint64_t (&v)[KPL], int lane) {
 #pragma unroll
                 for (int s = 0; s < KPL; s++) {
                     const bool up = ((s * 32 + lane) & kk) == 0;
-                    const uint64_t other = __shfl_xor_sync(0xffffffffu, v[s], jj);
+                    const T other = __shfl_xor_sync(0xffffffffu, v[s], jj);
                     const bool keep_min = ((lane & jj) == 0) == up;
                     v[s] = keep_min ? (other < v[s] ? other : v[s]) : (other > v[s] ? other : v[s]);
                 }
@@ -197,29 +197,54 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
         }
         __syncthreads();
         // local rates per read (one warp per read): the partners' Hamming rates are sorted in registers, the
-        // cut = max(1, m/p) lowest are pooled as same-haplotype pairs, the rest as different-haplotype pairs
+        // cut = max(1, m/p) lowest are pooled as same-haplotype pairs, the rest as different-haplotype pairs.
+        // A chain of at most 255 bubbles has overlaps n <= 255: (floor(65535 k / n), n, k) then fits 32 bits and
+        // orders exactly like the 62-bit key (two distinct rates with denominators <= 255 differ by > 1/65535).
         {
             int pl = 0;
+            const bool narrow = d.bubble_off[c + 1] - d.bubble_off[c] <= 255;
             for (int i = wid; i < n; i += NW) {
-                uint64_t kk[KPL];
-                int m = 0;
+                int m = 0, Ks = 0, Ns = 0, Kd = 0, Nd = 0;
+                if (narrow) {
+                    uint32_t kk[KPL];
 #pragma unroll
-                for (int s = 0; s < KPL; s++) {
-                    const int j = s * 32 + lane;
-                    const int nk = j < n ? W[i * ns + j] : 0;
-                    kk[s] = nk ? rate_key(nk >> 16, nk & 0xffff) : ~0ull;
-                    m += __popc(__ballot_sync(0xffffffffu, nk != 0));
+                    for (int s = 0; s < KPL; s++) {
+                        const int j = s * 32 + lane;
+                        const int nk = j < n ? W[i * ns + j] : 0;
+                        const uint32_t nq = (uint32_t)nk >> 16, kq = (uint32_t)nk & 0xffffu;
+                        kk[s] = nk ? (((kq * 65535u) / nq) << 16) | (nq << 8) | kq : 0xffffffffu;
+                        m += __popc(__ballot_sync(0xffffffffu, nk != 0));
+                    }
+                    if (m > 0) {
+                        warp_sort<KPL>(kk, lane);
+                        const int cut = max(1, m / d.ploidy);
+#pragma unroll
+                        for (int s = 0; s < KPL; s++) if (kk[s] != 0xffffffffu) {
+                            const int kq = (int)(kk[s] & 0xffu), nq = (int)((kk[s] >> 8) & 0xffu);
+                            if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
+                        }
+                    }
+                } else {
+                    uint64_t kk[KPL];
+#pragma unroll
+                    for (int s = 0; s < KPL; s++) {
+                        const int j = s * 32 + lane;
+                        const int nk = j < n ? W[i * ns + j] : 0;
+                        kk[s] = nk ? rate_key(nk >> 16, nk & 0xffff) : ~0ull;
+                        m += __popc(__ballot_sync(0xffffffffu, nk != 0));
+                    }
+                    if (m > 0) {
+                        warp_sort<KPL>(kk, lane);
+                        const int cut = max(1, m / d.ploidy);
+#pragma unroll
+                        for (int s = 0; s < KPL; s++) if (kk[s] != ~0ull) {
+                            const int kq = (int)(kk[s] & 0x7fff), nq = (int)((kk[s] >> 15) & 0x7fff);
+                            if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
+                        }
+                    }
                 }
                 uint32_t es_i = 0, ed_i = 0;
                 if (m > 0) {
-                    warp_sort_u64<KPL>(kk, lane);
-                    const int cut = max(1, m / d.ploidy);
-                    int Ks = 0, Ns = 0, Kd = 0, Nd = 0;
-#pragma unroll
-                    for (int s = 0; s < KPL; s++) if (kk[s] != ~0ull) {
-                        const int kq = (int)(kk[s] & 0x7fff), nq = (int)((kk[s] >> 15) & 0x7fff);
-                        if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
-                    }
                     Ks = warp_sum_i32(Ks); Ns = warp_sum_i32(Ns); Kd = warp_sum_i32(Kd); Nd = warp_sum_i32(Nd);
                     es_i = (uint32_t)(((int64_t)Ks * 1024 + Ns / 2) / Ns);
                     ed_i = Nd > 0 ? (uint32_t)(((int64_t)Kd * 1024 + Nd / 2) / Nd) : es_i;

@@ -33,6 +33,12 @@ def test_diploid_mid_and_big_chains(mean_len, n_chains, seed):
     assert got.n_chains_ok == n_chains
 
 
+def test_long_chains_low_depth_wide_rate_keys():
+    # ~400 bubbles, ~70 final reads per chain: shared-memory scoring with the 62-bit rate keys (overlaps may exceed 255)
+    got = _check(synth.generate(synth.params(2, 8, 1, 400, depth=4.0, seed=73)))
+    assert got.n_chains_ok == 8
+
+
 def test_cfg2_sample():
     got = _check(synth.generate(synth.config("cfg2", 0.01)))
     assert got.n_chains_ok > 400

@@ -20,6 +20,7 @@ CASES = {
     "fourbit": synth.params(2, 20, 1, 20, depth=30.0, max_alleles=6, seed=51),
     "dip_mid": synth.params(2, 30, 1, 80, depth=30.0, seed=71),
     "dip_big": synth.params(2, 12, 1, 140, depth=30.0, seed=72),
+    "long_lowdepth": synth.params(2, 8, 1, 400, depth=4.0, seed=73),
     "cfg2_small": synth.config("cfg2", 0.01),
     "cfg1": synth.config("cfg1"),
 }

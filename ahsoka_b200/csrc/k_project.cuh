@@ -221,20 +221,34 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
     }
 }
 
+// ---------------------------------------------------------------- sub-warp groups
+// The per-read kernels below are latency bound (a chain of dependent metadata loads per read, then a row of ~40
+// cells): G lanes per read and 32/G reads in flight per warp multiply the memory-level parallelism.  Every
+// collective uses the group's own lane mask, so groups of one warp proceed independently.
+template <int G> __device__ __forceinline__ unsigned grp_mask() { return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G)); }
+template <int G> __device__ __forceinline__ uint64_t grp_min_u64(uint64_t v, unsigned m) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(m, v, o); v = t < v ? t : v; }
+    return v;
+}
+
 // ---------------------------------------------------------------- K1b: stage-A statistics per read
 // count / first / last fully contained bubble and the stage-A mapq (:146-165, :173-182)
+template <int G>
 __global__ void __launch_bounds__(256) k_read_stage_a(DB d) {
     AHS_BAIL_ON_ERR(d);
-    const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < d.NR; r += (int64_t)gridDim.x * wpb) {
+    const unsigned gm = grp_mask<G>();
+    const int gl = lane_id() % G;
+    const int64_t gpb = blockDim.x / G, g0 = blockIdx.x * gpb + threadIdx.x / G;
+    for (int64_t r = g0; r < d.NR; r += (int64_t)gridDim.x * gpb) {
         const int c = d.read_chain[r];
         const int B = (int)(d.bubble_off[c + 1] - d.bubble_off[c]);
         if (B <= 1) continue;
         const uint16_t* mrow = d.mask + d.mrow_off[c] + (r - d.read_off[c]) * B;
         int cnt = 0, first = INT32_MAX, last = -1;
-        for (int b = lane; b < B; b += 32) if (mrow[b] & 0x8000u) { cnt++; first = min(first, b); last = max(last, b); }
-        cnt = warp_sum_i32(cnt); first = warp_min_i32(first); last = warp_max_i32(last);
-        if (lane == 0) {
+        for (int b = gl; b < B; b += G) if (mrow[b] & 0x8000u) { cnt++; first = min(first, b); last = max(last, b); }
+        cnt = __reduce_add_sync(gm, cnt); first = __reduce_min_sync(gm, first); last = __reduce_max_sync(gm, last);
+        if (gl == 0) {
             int mapq = 0;
             if (cnt > 0) {
                 const uint32_t el = (uint32_t)(d.createA_key[r] & 0xffffffffu);
@@ -282,12 +296,15 @@ __global__ void k_chain_T(DB d) {
 }
 
 // ---------------------------------------------------------------- K1d: final rows per read (stage B + filter)
+template <int G>
 __global__ void __launch_bounds__(256) k_read_rows(DB d) {
     AHS_BAIL_ON_ERR(d);
-    const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int64_t r = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); r < d.NR; r += (int64_t)gridDim.x * wpb) {
+    const unsigned gm = grp_mask<G>();
+    const int gl = lane_id() % G;
+    const int64_t gpb = blockDim.x / G, g0 = blockIdx.x * gpb + threadIdx.x / G;
+    for (int64_t r = g0; r < d.NR; r += (int64_t)gridDim.x * gpb) {
         const int c = d.read_chain[r];
-        if (lane == 0) d.rd_pass[r] = 0;
+        if (gl == 0) d.rd_pass[r] = 0;
         if (d.ch_status[c] != AHS_CHAIN_OK) continue;
         const int64_t b0g = d.bubble_off[c];
         const int B = (int)(d.bubble_off[c + 1] - b0g);
@@ -298,16 +315,16 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
         const bool hg = d.has_good[r] != 0;
         // creation triple: minimum (position, allele, entry) over all matches, universal alleles included
         uint64_t ck = d.create_key[r];
-        if (has_entry) for (int b = lane; b < T; b += 32) {
+        if (has_entry) for (int b = gl; b < T; b += G) {
             const uint32_t u = d.bubble_univ[b0g + b];
             if (u != 0xffffffffu) { uint64_t k = make_key((uint32_t)b, u, fe); ck = k < ck ? k : ck; }
         }
-        ck = warp_min_u64(ck);
+        ck = grp_min_u64<G>(ck, gm);
         const int bc = (ck == KEY_NONE) ? INT32_MAX : (int)(ck >> 40);
         int nv = 0, last = -1;
         if (bc < T) {
             const int ac = (int)((ck >> 32) & 0xff);
-            for (int b = lane; b < B; b += 32) {
+            for (int b = gl; b < B; b += G) {
                 uint32_t code = 0;
                 if (b < T) {
                     uint32_t m = mrow[b] & 0x7fffu;
@@ -319,15 +336,16 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
                 mrow[b] = (uint16_t)code;
                 if (code) { nv++; last = max(last, b); }
             }
-            nv = warp_sum_i32(nv); last = warp_max_i32(last);
+            nv = __reduce_add_sync(gm, nv); last = __reduce_max_sync(gm, last);
         }
         int mapq = 0; bool pass = false;
         if (bc < T) {
             mapq = mapq_of(d.entry_identity[d.entry_off[c] + (uint32_t)(ck & 0xffffffffu)]);
             pass = nv > 1 && mapq >= 93;                                    // :270
         }
-        if (pass) for (int b = lane; b < T; b += 32) if (mrow[b]) d.poscov[b0g + b] = 1;
-        if (lane == 0) {
+        __syncwarp(gm);                                                     // the group's codes are written
+        if (pass) for (int b = gl; b < T; b += G) if (mrow[b]) d.poscov[b0g + b] = 1;
+        if (gl == 0) {
             d.rd_nv[r] = nv; d.rd_first[r] = bc; d.rd_last[r] = last; d.rd_mapq[r] = mapq; d.rd_pass[r] = pass ? 1 : 0;
             d.create_key[r] = ck;
             if (pass) { atomicAdd(&d.ch_nfinal[c], 1); atomicAdd((unsigned long long*)d.tot_cells, (unsigned long long)nv); }
@@ -471,11 +489,15 @@ __global__ void k_compact_pos(DB d) {
 }
 
 // ---------------------------------------------------------------- K1f: pack final rows
-// one warp per final read: mask row (u16 codes) -> packed 2/4-bit codes, dense by bubble id
+// G lanes per final read: mask row (u16 codes) -> packed 2/4-bit codes, dense by bubble id.  Lanes read consecutive
+// codes (coalesced), shift them into place and OR them together across the group, one word at a time.
+template <int G>
 __global__ void __launch_bounds__(256) k_pack_rows(DB d) {
-    const int wpb = blockDim.x >> 5, lane = lane_id();
+    const unsigned gm = grp_mask<G>();
+    const int gl = lane_id() % G;
+    const int64_t gpb = blockDim.x / G, g0 = blockIdx.x * gpb + threadIdx.x / G;
     const int bits = d.bits, per_word = 32 / bits;
-    for (int64_t f = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); f < d.NF; f += (int64_t)gridDim.x * wpb) {
+    for (int64_t f = g0; f < d.NF; f += (int64_t)gridDim.x * gpb) {
         const int c = d.fr_chain[f];
         const int B = (int)(d.bubble_off[c + 1] - d.bubble_off[c]);
         const int i = (int)(f - d.frow_off[c]);
@@ -484,12 +506,13 @@ __global__ void __launch_bounds__(256) k_pack_rows(DB d) {
         const uint16_t* mrow = d.mask + d.mrow_off[c] + (int64_t)rl * B;
         uint32_t* row = d.codes + d.code_off[c] + (int64_t)i * d.ch_words[c];
         const int first = d.rd_first[r], last = d.rd_last[r];
-        for (int w = first / per_word + lane; w <= last / per_word; w += 32) {
+        for (int w = first / per_word; w <= last / per_word; w++) {
             uint32_t word = 0;
-            for (int x = 0; x < per_word; x++) { int b = w * per_word + x; if (b < B) word |= (uint32_t)mrow[b] << (x * bits); }
-            row[w] = word;
+            for (int x = gl; x < per_word; x += G) { const int b = w * per_word + x; if (b < B) word |= (uint32_t)mrow[b] << (x * bits); }
+            word = __reduce_or_sync(gm, word);
+            if (gl == 0) row[w] = word;
         }
-        if (lane == 0) {
+        if (gl == 0) {
             d.fr_first[f] = first; d.fr_last[f] = last; d.fr_mapq[f] = d.rd_mapq[r]; d.fr_id[f] = rl; d.fr_nv[f] = d.rd_nv[r];
             atomicMax(&d.ch_maxspan[c], last - first);
         }

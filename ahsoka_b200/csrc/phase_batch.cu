@@ -349,10 +349,11 @@ struct Pipeline {
             if (ne > 0) { k_project<<<grid_for(ne, 8, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]); n_launches += 1; }
         }
         CK(cudaEventRecord(cx->ev[1], st));
-        if (sz.NR) k_read_stage_a<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        const bool small_rows = sz.NB <= 96 * C;        // short chains: 8 lanes per read, 4 reads in flight per warp
+        if (sz.NR) { if (small_rows) k_read_stage_a<8><<<grid_for(sz.NR, 32, sms), TB, 0, st>>>(d); else k_read_stage_a<32><<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
         k_chain_T<<<grid_for(C, TB, sms), TB, 0, st>>>(d); n_launches += 1;
-        if (sz.NR) k_read_rows<<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (sz.NR) { if (small_rows) k_read_rows<8><<<grid_for(sz.NR, 32, sms), TB, 0, st>>>(d); else k_read_rows<32><<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (sz.NR) k_read_rank<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
         k_chain_sort<<<grid_for(C, 64, sms), 64, 0, st>>>(d); n_launches += 1;
         k_count_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
@@ -466,7 +467,7 @@ struct Pipeline {
         }
         if (NF) k_owner<<<grid_for(NF, TB, sms), TB, 0, st>>>(d.frow_off, (int)C, NF, d.fr_chain); n_launches += 1;
         if (NP) k_owner<<<grid_for(NP, TB, sms), TB, 0, st>>>(d.pos_off, (int)C, NP, d.pos_chain); n_launches += 1;
-        if (NF) k_pack_rows<<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (NF) { if (sz.NB <= 96 * C) k_pack_rows<8><<<grid_for(NF, 32, sms), TB, 0, st>>>(d); else k_pack_rows<32><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         // ---- CSR cells of the final matrix; with host output they travel D2H on a second stream under the clustering
         scan(d.fr_nv, NF, d.cell_off);

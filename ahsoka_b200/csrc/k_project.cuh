@@ -124,23 +124,37 @@ __global__ void k_build_triggers(DB d) {
     }
 }
 
-// ---------------------------------------------------------------- K1: project entries
-// is value q among the L nodes of the entry?  (whole warp)
-__device__ __forceinline__ bool warp_entry_has(const int32_t* __restrict__ nodes, int L, int32_t q, int lane) {
-    bool f = false;
-    for (int x = lane; x < L; x += 32) f |= __ldg(nodes + x) == q;
-    return __any_sync(0xffffffffu, f);
+// ---------------------------------------------------------------- sub-warp groups
+// The per-read kernels below are latency bound (a chain of dependent metadata loads per read, then a row of ~40
+// cells): G lanes per read and 32/G reads in flight per warp multiply the memory-level parallelism.  Every
+// collective uses the group's own lane mask, so groups of one warp proceed independently.
+template <int G> __device__ __forceinline__ unsigned grp_mask() { return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G)); }
+template <int G> __device__ __forceinline__ uint64_t grp_min_u64(uint64_t v, unsigned m) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(m, v, o); v = t < v ? t : v; }
+    return v;
 }
 
-// one warp per alignment entry; lanes stride over the entry's nodes.  A node that is the trigger of an allele path
-// (hash hit) decides the two containment tests of the reference (is_subset with and without the end nodes, :495-548).
-// Common case, decided by the lane alone: a 3-node path whose end nodes are the neighbours of the trigger in the
-// alignment.  Everything else is decided by the whole warp scanning the entry.
+// ---------------------------------------------------------------- K1: project entries
+// is value q among the L nodes of the entry?  (whole lane group)
+template <int G>
+__device__ __forceinline__ bool grp_entry_has(const int32_t* __restrict__ nodes, int L, int32_t q, int gl, unsigned gm) {
+    bool f = false;
+    for (int x = gl; x < L; x += G) f |= __ldg(nodes + x) == q;
+    return __any_sync(gm, f);
+}
+
+// one group of G lanes per alignment entry; lanes stride over the entry's nodes.  A node that is the trigger of an
+// allele path (hash hit) decides the two containment tests of the reference (is_subset with and without the end
+// nodes, :495-548).  Common case, decided by the lane alone: a 3-node path whose end nodes are the neighbours of
+// the trigger in the alignment.  Everything else is decided by the whole group scanning the entry.
+template <int G>
 __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t e_end) {
     AHS_BAIL_ON_ERR(d);
-    const int warps_per_block = blockDim.x >> 5;
-    const int lane = lane_id();
-    for (int64_t ge = e_begin + blockIdx.x * (int64_t)warps_per_block + (threadIdx.x >> 5); ge < e_end; ge += (int64_t)gridDim.x * warps_per_block) {
+    const unsigned gm = grp_mask<G>();
+    const int lane = lane_id(), gl = lane % G;
+    const int64_t gpb = blockDim.x / G, g0 = blockIdx.x * gpb + threadIdx.x / G;
+    for (int64_t ge = e_begin + g0; ge < e_end; ge += (int64_t)gridDim.x * gpb) {
         const int c = d.entry_chain[ge];
         const int64_t b0 = d.bubble_off[c];
         const int B = (int)(d.bubble_off[c + 1] - b0);
@@ -156,8 +170,8 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
         const unsigned long long* tab = d.hslots + d.hoff[c];
         const uint32_t mask = d.hmaskc[c];
         uint64_t ck = KEY_NONE, ckA = KEY_NONE;                 // smallest creation keys seen by this lane
-        for (int x0 = 0; x0 < L; x0 += 32) {
-            const int x = x0 + lane;
+        for (int x0 = 0; x0 < L; x0 += G) {
+            const int x = x0 + gl;
             int32_t ga = -1, prev = 0, next = 0; bool has_prev = false, has_next = false;
             if (x < L) {
                 const int32_t v = __ldg(nodes + x);
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
                     slot = (slot + 1) & mask;
                 }
             }
-            while (__any_sync(0xffffffffu, ga >= 0)) {
+            while (__any_sync(gm, ga >= 0)) {
                 const bool have = ga >= 0;
                 int64_t gb = 0, o = 0; int len = 0;
                 bool inner_ok = false, full_ok = false, slow = false;
@@ -186,15 +200,15 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
                         slow = !full_ok;                                                  // the end nodes may still be elsewhere in the entry
                     } else slow = true;
                 }
-                for (unsigned sm = __ballot_sync(0xffffffffu, slow); sm; sm &= sm - 1) {
-                    const int src_lane = __ffs(sm) - 1;
-                    const int64_t oo = __shfl_sync(0xffffffffu, o, src_lane);
-                    const int ll = __shfl_sync(0xffffffffu, len, src_lane);
+                for (unsigned sm = __ballot_sync(gm, slow); sm; sm &= sm - 1) {
+                    const int src_lane = __ffs(sm) - 1;                                   // absolute lane, inside this group
+                    const int64_t oo = __shfl_sync(gm, o, src_lane);
+                    const int ll = __shfl_sync(gm, len, src_lane);
                     bool in_ok = ll >= 3;                          // len <= 2: universal, handled in k_read_rows
-                    for (int y = 2; in_ok && y < ll - 1; y++) in_ok = warp_entry_has(nodes, L, d.anode[oo + y], lane);
+                    for (int y = 2; in_ok && y < ll - 1; y++) in_ok = grp_entry_has<G>(nodes, L, d.anode[oo + y], gl, gm);
                     bool f_ok;
-                    if (ll >= 3) f_ok = in_ok && warp_entry_has(nodes, L, d.anode[oo], lane) && warp_entry_has(nodes, L, d.anode[oo + ll - 1], lane);
-                    else f_ok = (ll == 1) || warp_entry_has(nodes, L, d.anode[oo + 1], lane);
+                    if (ll >= 3) f_ok = in_ok && grp_entry_has<G>(nodes, L, d.anode[oo], gl, gm) && grp_entry_has<G>(nodes, L, d.anode[oo + ll - 1], gl, gm);
+                    else f_ok = (ll == 1) || grp_entry_has<G>(nodes, L, d.anode[oo + 1], gl, gm);
                     if (lane == src_lane) { inner_ok = in_ok; full_ok = f_ok; }
                 }
                 if (have) {
@@ -212,24 +226,13 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
                 }
             }
         }
-        ck = warp_min_u64(ck); ckA = warp_min_u64(ckA);
-        if (lane == 0) {
+        ck = grp_min_u64<G>(ck, gm); ckA = grp_min_u64<G>(ckA, gm);
+        if (gl == 0) {
             atomicMin(&d.first_entry[r], el); if (good) d.has_good[r] = 1;
             if (ck != KEY_NONE) atomicMin((unsigned long long*)&d.create_key[r], (unsigned long long)ck);
             if (ckA != KEY_NONE) atomicMin((unsigned long long*)&d.createA_key[r], (unsigned long long)ckA);
         }
     }
-}
-
-// ---------------------------------------------------------------- sub-warp groups
-// The per-read kernels below are latency bound (a chain of dependent metadata loads per read, then a row of ~40
-// cells): G lanes per read and 32/G reads in flight per warp multiply the memory-level parallelism.  Every
-// collective uses the group's own lane mask, so groups of one warp proceed independently.
-template <int G> __device__ __forceinline__ unsigned grp_mask() { return G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G)); }
-template <int G> __device__ __forceinline__ uint64_t grp_min_u64(uint64_t v, unsigned m) {
-#pragma unroll
-    for (int o = G >> 1; o > 0; o >>= 1) { const uint64_t t = __shfl_xor_sync(m, v, o); v = t < v ? t : v; }
-    return v;
 }
 
 // ---------------------------------------------------------------- K1b: stage-A statistics per read

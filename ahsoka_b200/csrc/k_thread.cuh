@@ -23,13 +23,15 @@ namespace ahs {
 
 constexpr int K3_CAP = 128;      // clusters per position held in shared memory
 
-template <int BITS>
+template <int BITS, int G>
 __global__ void __launch_bounds__(128) k_consensus(DB d) {
-    __shared__ int32_t s_id[4][K3_CAP], s_cnt[4][K3_CAP], s_key[4][K3_CAP], s_idx[4][K3_CAP];
-    __shared__ uint8_t s_cons[4][K3_CAP];
-    const int wpb = blockDim.x >> 5, lane = lane_id(), wib = threadIdx.x >> 5;
+    constexpr int NG = 128 / G;                                       // position groups per block
+    __shared__ int32_t s_id[NG][K3_CAP], s_cnt[NG][K3_CAP], s_key[NG][K3_CAP], s_idx[NG][K3_CAP];
+    __shared__ uint8_t s_cons[NG][K3_CAP];
+    const unsigned gm = grp_mask<G>();
+    const int gl = lane_id() % G, wib = threadIdx.x / G;
     const int p = d.ploidy;
-    for (int64_t gp = blockIdx.x * (int64_t)wpb + wib; gp < d.NP; gp += (int64_t)gridDim.x * wpb) {
+    for (int64_t gp = blockIdx.x * (int64_t)NG + wib; gp < d.NP; gp += (int64_t)gridDim.x * NG) {
         const int c = d.pos_chain[gp];
         const int b = d.pos[gp];
         const int64_t f0 = d.frow_off[c];
@@ -46,15 +48,15 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
         int cur = -1, ncl = 0; uint32_t total = 0; bool overflow = false;
         while (true) {
             int nxt = INT32_MAX;
-            for (int i = lo + lane; i <= hi; i += 32)
+            for (int i = lo + gl; i <= hi; i += G)
                 if (lastp[i] >= b && cl[i] > cur && get_code(rows + (int64_t)i * words, b, BITS)) nxt = min(nxt, cl[i]);
-            nxt = warp_min_i32(nxt);
+            nxt = __reduce_min_sync(gm, nxt);
             if (nxt == INT32_MAX) break;
             constexpr int NA_MAX = BITS == 2 ? 3 : MAX_ALLELES;       // 2-bit codes hold at most 3 alleles
             uint32_t ac[NA_MAX];
 #pragma unroll
             for (int a = 0; a < NA_MAX; a++) ac[a] = 0;
-            for (int i = lo + lane; i <= hi; i += 32)
+            for (int i = lo + gl; i <= hi; i += G)
                 if (lastp[i] >= b && cl[i] == nxt) {
                     const uint32_t code = get_code(rows + (int64_t)i * words, b, BITS);
 #pragma unroll
@@ -63,17 +65,17 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
             uint32_t cnt = 0, best = 0; int cons = 0;
 #pragma unroll
             for (int a = 0; a < NA_MAX; a++) if (a < K) {
-                const uint32_t v = (uint32_t)warp_sum_i32((int)ac[a]);
+                const uint32_t v = (uint32_t)__reduce_add_sync(gm, (int)ac[a]);
                 cnt += v;
                 if (v > best) { best = v; cons = a; }               // ties -> smallest allele (:633-649, A#13)
             }
-            if (ncl < K3_CAP) { if (lane == 0) { s_id[wib][ncl] = nxt; s_cnt[wib][ncl] = (int32_t)cnt; s_cons[wib][ncl] = (uint8_t)cons; } }
+            if (ncl < K3_CAP) { if (gl == 0) { s_id[wib][ncl] = nxt; s_cnt[wib][ncl] = (int32_t)cnt; s_cons[wib][ncl] = (uint8_t)cons; } }
             else overflow = true;
             ncl++; total += cnt; cur = nxt;
         }
-        __syncwarp();
-        if (overflow) { if (lane == 0) atomicMax(&d.ch_status[c], AHS_CHAIN_TOO_LARGE); continue; }
-        if (lane == 0) {
+        __syncwarp(gm);
+        if (overflow) { if (gl == 0) atomicMax(&d.ch_status[c], AHS_CHAIN_TOO_LARGE); continue; }
+        if (gl == 0) {
             PosRec r;
             r.total = total; r.pad[0] = r.pad[1] = r.pad[2] = 0;
             for (int x = 0; x < ncl; x++) { s_key[wib][x] = s_cnt[wib][x]; s_idx[wib][x] = x; }
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
             for (int l = 0; l < k; l++) r.cons_asc[l] = s_cons[wib][sel[l]];
             d.rec[gp] = r;
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 }
 

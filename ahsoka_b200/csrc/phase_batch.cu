@@ -346,7 +346,11 @@ struct Pipeline {
         for (int i = 0; i < N_EN; i++) {
             CK(cudaStreamWaitEvent(st, cx->ev_en[i], 0));
             const int64_t ne = en_cut[i + 1] - en_cut[i];
-            if (ne > 0) { k_project<<<grid_for(ne, 8, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]); n_launches += 1; }
+            if (ne > 0) {
+                if (sz.NEN <= 48 * sz.NE) k_project<16><<<grid_for(ne, 16, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]);      // short alignments
+                else k_project<32><<<grid_for(ne, 8, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]);
+                n_launches += 1;
+            }
         }
         CK(cudaEventRecord(cx->ev[1], st));
         const bool small_rows = sz.NB <= 96 * C;        // short chains: 8 lanes per read, 4 reads in flight per warp
@@ -516,7 +520,10 @@ struct Pipeline {
         }
         CK(cudaEventRecord(cx->ev[4], st));
         // ---- coverage / consensus, threading
-        if (NP) k_consensus<BITS><<<grid_for(NP, 4, sms), 128, 0, st>>>(d); n_launches += 1;
+        if (NP) {                                          // 16 lanes per position while the depth (reads per chain) is small
+            if (NF <= 96 * C) k_consensus<BITS, 16><<<grid_for(NP, 8, sms), 128, 0, st>>>(d); else k_consensus<BITS, 32><<<grid_for(NP, 4, sms), 128, 0, st>>>(d);
+            n_launches += 1;
+        }
         CK(cudaEventRecord(cx->ev[5], st));
         if (NP && in->ploidy == 2) { k_thread2<<<(unsigned)std::min<int64_t>((C + 7) / 8, (int64_t)sms * 8), 256, 0, st>>>(d, counters + 1); n_launches += 1; }
         else if (NP) { k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1; }

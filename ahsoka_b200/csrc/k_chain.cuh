@@ -66,12 +66,13 @@ __device__ __forceinline__ int cc_tf(int x, int y) { return max(min(x, y), 0); }
 __device__ __forceinline__ int cc_tp(int x, int y) { const int lo = min(x, y), hi = max(x, y); return max(min(hi, -lo), 0); }
 
 struct CCBest {          // running maxima of one thread / of the block: max icf, max icp, max icp over positive edges
-    int M, maxP, maxPpos;
-    __device__ __forceinline__ void clear() { M = -1; maxP = -1; maxPpos = -1; }
+    int M, maxP, maxPpos, live;                         // live: slots seen by this thread (not reduced)
+    __device__ __forceinline__ void clear() { M = -1; maxP = -1; maxPpos = -1; live = 0; }
     __device__ __forceinline__ void consider(uint32_t key, int f, int p) {
         M = max(M, f); maxP = max(maxP, p);
         const int pos = (int)key >> 31;                 // all ones for a positive edge
         maxPpos = max(maxPpos, (p & pos) | ~pos);       // p, or -1 for a negative edge
+        live++;
     }
 };
 
@@ -284,7 +285,7 @@ static_assert(CC_MAXN <= 128, "k_cluster_chain walks rows in four 32-lane stride
 // ------------------------------------------------------------------------------------------------
 template <int NT, int PER>
 __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
-                                                                         int32_t* __restrict__ work_counter) {
+                                                                         int32_t* __restrict__ work_counter, int32_t* __restrict__ scratch) {
     extern __shared__ __align__(16) unsigned char cc_sm[];
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -304,6 +305,8 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
     }
     int phase = 0, kphase = 0;
     uint32_t key[PER]; int F[PER], P[PER];
+    int32_t* scr = scratch + ((size_t)blockIdx.x * NW + wid) * (32 * PER * 3);       // this warp's packing area (global, L2)
+    const unsigned lt = (1u << lane) - 1u;
     while (true) {
         __syncthreads();
         if (tid == 0) scal[3] = atomicAdd(work_counter, 1);
@@ -375,13 +378,14 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
         }
         CCBest so = cc_reduce<NT>(mine, red, tid, phase);
         bool force_single = false;
+        int wk = PER;                                       // slot indices below wk may be live in this warp
         while (so.M >= 0) {
             mine.clear();
             if (so.M >= so.maxP) {
                 // ------------------------------------------------ merge (a,b) into a: the pair with the largest icf
                 int kmine = 0xffff;
 #pragma unroll
-                for (int k = 0; k < PER; k++) if (!(key[k] & CC_GONE) && F[k] == so.M) kmine = min(kmine, (int)(key[k] & 0xffffu));
+                for (int k = 0; k < PER; k++) if (k < wk && !(key[k] & CC_GONE) && F[k] == so.M) kmine = min(kmine, (int)(key[k] & 0xffffu));
                 const int kF = cc_min_key(kmine, scal + 4, tid, kphase);
                 const int a = kF >> 8, b = kF & 0xff;
                 for (int t = tid; t < n; t += NT) {
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 // a and b for the term through the merged node
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
+                    if (k >= wk) break;                            // warp-uniform: slots beyond wk are empty since the last packing
                     const uint32_t kq = key[k];
                     if (kq & CC_GONE) continue;
                     const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
@@ -443,17 +448,41 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                     mine.consider(key[k], F[k], P[k]);
                 }
                 force_single = false;
+                const int wlive = __reduce_add_sync(0xffffffffu, mine.live);
                 so = cc_reduce<NT>(mine, red, tid, phase);
+                // slots only die: once half of a warp's slot rows could be dropped, its survivors are packed row-major
+                // into the first rows (lane = j % 32 keeps neighbouring pairs in neighbouring lanes), through this warp's
+                // scratch in L2; no other warp is involved
+                if (((wlive + 31) >> 5) * 2 <= wk && wk > 1) {
+                    int base = 0;
+#pragma unroll
+                    for (int k = 0; k < PER; k++) {
+                        const bool lv = k < wk && !(key[k] & CC_GONE);
+                        const unsigned bal = __ballot_sync(0xffffffffu, lv);
+                        if (lv) { const int pos = base + __popc(bal & lt); __stcg(scr + pos, (int)key[k]); __stcg(scr + 32 * PER + pos, F[k]); __stcg(scr + 64 * PER + pos, P[k]); }
+                        base += __popc(bal);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < PER; k++) {
+                        const int j = k * 32 + lane;
+                        if (j < base) { key[k] = (uint32_t)__ldcg(scr + j); F[k] = __ldcg(scr + 32 * PER + j); P[k] = __ldcg(scr + 64 * PER + j); }
+                        else key[k] = CC_DEAD;
+                    }
+                    wk = (base + 31) >> 5;
+                    __syncwarp();
+                }
             } else if (force_single || so.maxPpos > so.M) {
                 // ------------------------------------------------ one sequential forbid: the edge with the largest icp
                 int kmine = 0xffff;
 #pragma unroll
-                for (int k = 0; k < PER; k++) if (!(key[k] & CC_GONE) && P[k] == so.maxP) kmine = min(kmine, (int)(key[k] & 0xffffu));
+                for (int k = 0; k < PER; k++) if (k < wk && !(key[k] & CC_GONE) && P[k] == so.maxP) kmine = min(kmine, (int)(key[k] & 0xffffu));
                 const int kP = cc_min_key(kmine, scal + 4, tid, kphase);
                 const int a = kP >> 8, b = kP & 0xff;
                 const int old = W[a * ns + b];                  // set to forbidden after the step's last barrier
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
+                    if (k >= wk) break;                            // warp-uniform: slots beyond wk are empty since the last packing
                     const uint32_t kq = key[k];
                     if (kq & CC_GONE) continue;
                     const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
@@ -482,6 +511,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 int nfl = 0;
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
+                    if (k >= wk) break;                            // warp-uniform: slots beyond wk are empty since the last packing
                     const uint32_t kq = key[k];
                     if (kq & CC_FLAG) { key[k] = CC_DEAD; continue; }          // forbidden for good in an earlier round
                     if ((kq & (CC_DEAD | CC_POS)) || P[k] <= M) continue;
@@ -521,6 +551,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 // the others grows
 #pragma unroll
                 for (int k = 0; k < PER; k++) {
+                    if (k >= wk) break;                            // warp-uniform: slots beyond wk are empty since the last packing
                     const uint32_t kq = key[k];
                     if (kq & CC_DEAD) continue;
                     const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);
@@ -537,6 +568,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                     force_single = true;
 #pragma unroll
                     for (int k = 0; k < PER; k++) {
+                        if (k >= wk) break;
                         const uint32_t kq = key[k];
                         if (kq & CC_DEAD) continue;
                         const int x = (int)((kq >> 8) & 0xff), y = (int)(kq & 0xff);

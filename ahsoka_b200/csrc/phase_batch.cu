@@ -94,8 +94,8 @@ static void fused_set_attributes(size_t optin) {
     AHS_FOR_EACH_SC(X)
 #undef X
 }
-static void cluster_launch(int nt, int per, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
-#define X(NT, PER) if (nt == NT && per == PER) { k_cluster_chain<NT, PER><<<grid, NT, smem, st>>>(d, list, len, nmax, counter); return; }
+static void cluster_launch(int nt, int per, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter, int32_t* scratch) {
+#define X(NT, PER) if (nt == NT && per == PER) { k_cluster_chain<NT, PER><<<grid, NT, smem, st>>>(d, list, len, nmax, counter, scratch); return; }
     AHS_FOR_EACH_NT(X)
 #undef X
     throw ArgFail{"cluster_launch: no kernel for this block size"};
@@ -509,7 +509,8 @@ struct Pipeline {
             const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
             const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-            cluster_launch(nt, kFused[k].per, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k); n_launches += 1;
+            int32_t* scratch = dalloc<int32_t>((int64_t)grid * nt * kFused[k].per * 3);     // slot-packing areas, one per warp
+            cluster_launch(nt, kFused[k].per, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k, scratch); n_launches += 1;
         }
         for (int i = 0; i < 8; i++) { CK(cudaEventRecord(cx->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, cx->ev_join[i], 0)); }
         CK(cudaEventRecord(cx->ev[11], st));

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 // slots only die: once half of a warp's slot rows could be dropped, its survivors are packed row-major
                 // into the first rows (lane = j % 32 keeps neighbouring pairs in neighbouring lanes), through this warp's
                 // scratch in L2; no other warp is involved
-                if (((wlive + 31) >> 5) * 2 <= wk && wk > 1) {
+                if (((wlive + 31) >> 5) < wk) {
                     int base = 0;
 #pragma unroll
                     for (int k = 0; k < PER; k++) {

@@ -173,3 +173,12 @@ def test_multi_device_lpt_gather():
     b = synth.generate(synth.config("cfg2", 0.02))
     got = api.phase_batch(b, devices=[0, 1])
     assert not got.diff(oracle_phase(b))
+
+
+def test_randomised_shapes_twice_each():
+    # chain length 3..120, depth 3..90, ploidy 2..4, up to 12 alleles, duplicated read names, error / missing rates:
+    # every case bit-identical to the oracle, in two consecutive runs (a data race would show up as a flaky diff)
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(api.ROOT, "tools", "stress_gpu.py"), "30", "4242"], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]

@@ -77,7 +77,7 @@ def main():
             f.write(f"| `{n}` | {k} | {t:.1f} | {100 * t / tot:.1f}% |\n")
         f.write(f"| **sum** | {len(p)} | {tot:.1f} | |\n\n")
         st = bench["roofline"]["stages"]
-        f.write(f"Same build, `python bench.py --steps 3 --warmup 3` without ncu (`{tag}_bench_cfg2.json`): "
+        f.write(f"Same build, `python bench.py --steps {bench['steps']} --warmup {bench['warmup']}` without ncu (`{tag}_bench_cfg2.json`): "
                 f"**{bench['ms_per_step']:.2f} ms/step = {bench['value']:.3e} cells/s** device-resident, "
                 f"**{bench['e2e']['ms_per_step']:.2f} ms = {bench['e2e']['value']:.3e} cells/s** end to end (H2D {bench['e2e']['h2d_bytes_per_step'] / 1e6:.0f} MB, "
                 f"D2H {bench['e2e']['d2h_bytes_per_step'] / 1e6:.0f} MB inside the call); CPU oracle port on {bench.get('cpu_baseline', {}).get('cores', '?')} threads: "

@@ -47,7 +47,7 @@ struct DB {
     // ---- scoring / cluster editing
     uint16_t *es, *ed;
     const int64_t *ln, *ln1;                              // log tables, 1025 entries each
-    int32_t *W; int64_t *F, *P;
+    int32_t *W; int64_t *F, *P; uint32_t *big_key;        // F, P, big_key: workspaces of k_cluster_big (n x n per chain above CC_MAXN)
     uint8_t *ce_active, *ce_dirty; int32_t *ce_list, *ce_newrow, *ce_label;
     int64_t *ce_rbF, *ce_rbP; int32_t *ce_rbFarg, *ce_rbParg;
     uint64_t *key_scratch; int64_t *key_scratch_off;       // overflow buffers for reads with > 256 partners

@@ -22,6 +22,7 @@
 #include "k_score.cuh"
 #include "k_cluster.cuh"
 #include "k_chain.cuh"
+#include "k_cluster_big.cuh"
 #include "k_thread.cuh"
 
 namespace ahs {
@@ -35,7 +36,7 @@ struct CudaFail { cudaError_t e; const char* what; int line; };
 struct LimitFail { std::string msg; };
 struct ArgFail { std::string msg; };
 
-constexpr int MAX_READS_CLUSTER = 8192;
+constexpr int MAX_READS_CLUSTER = 8191;        // 13-bit node ids in the slot keys of k_cluster_big
 constexpr int MAX_POSITIONS = 32767;
 
 // ------------------------------------------------------------------ memory pools (persist per device)
@@ -147,6 +148,7 @@ static Ctx* get_ctx(int device) {
     CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * 4096 + 64));
     c->smem_optin = prop.sharedMemPerBlockOptin;
     check_classes(c->smem_optin);
+    CK(cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     fused_set_attributes(c->smem_optin);
     g_ctx[device] = c;
     return c;
@@ -447,7 +449,7 @@ struct Pipeline {
             // HBM-resident path (chains above CC_MAXN reads): dense n x n workspaces
             for (int64_t c = 0; c < C; c++) if (!s_fused[c] && h_nfinal[c] > 0)
                 CK(cudaMemsetAsync(d.W + s_cw[c], 0, (size_t)h_nfinal[c] * h_nfinal[c] * 4, st));
-            d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw);
+            d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw); d.big_key = dalloc<uint32_t>(n_cw);
             d.ce_active = dalloc<uint8_t>(NF); d.ce_dirty = dalloc<uint8_t>(NF); d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
             d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
         }
@@ -517,7 +519,12 @@ struct Pipeline {
         // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one block per chain
         if (nf_unfused) {
             int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
-            if (len) { k_cluster_edit<<<std::min<int64_t>(len, (int64_t)sms * 4), CE_THREADS, 0, st>>>(d, dv_order + first, len, counters + 2); n_launches += 1; }
+            if (len) {
+                const int nbig = std::min<int>(n_max, 8191);
+                if (getenv("AHS_OLD_BIG")) k_cluster_edit<<<std::min<int64_t>(len, (int64_t)sms * 4), CE_THREADS, 0, st>>>(d, dv_order + first, len, counters + 2);
+                else k_cluster_big<<<(unsigned)std::min<int64_t>(len, sms), CB_THREADS, cb_smem_bytes(nbig), st>>>(d, dv_order + first, len, nbig, counters + 2);
+                n_launches += 1;
+            }
         }
         CK(cudaEventRecord(cx->ev[4], st));
         // ---- coverage / consensus, threading

@@ -5,8 +5,6 @@
 
 namespace ahs {
 
-constexpr int32_t  FORB        = INT32_MIN;          // forbidden edge (-inf), cluster editing
-constexpr int64_t  INF64       = (int64_t)1 << 60;
 constexpr uint64_t KEY_NONE    = ~0ull;
 constexpr int32_t  W_CLAMP     = 1 << 17;
 constexpr int      MAX_ALLELES = 15;                 // mask bits 0..14, bit 15 = full-containment flag

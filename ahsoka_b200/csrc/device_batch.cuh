@@ -48,8 +48,8 @@ struct DB {
     uint16_t *es, *ed;
     const int64_t *ln, *ln1;                              // log tables, 1025 entries each
     int32_t *W; int64_t *F, *P; uint32_t *big_key;        // F, P, big_key: workspaces of k_cluster_big (n x n per chain above CC_MAXN)
-    uint8_t *ce_active, *ce_dirty; int32_t *ce_list, *ce_newrow, *ce_label;
-    int64_t *ce_rbF, *ce_rbP; int32_t *ce_rbFarg, *ce_rbParg;
+    int32_t *ce_list, *ce_newrow, *ce_label;              // per-node scratch of k_cluster_big: old weights to a / b, merged weight
+    int64_t *ce_rbF, *ce_rbP; int32_t *ce_rbFarg, *ce_rbParg;   //   fresh icf / icp, first / last non-zero column of a row
     uint64_t *key_scratch; int64_t *key_scratch_off;       // overflow buffers for reads with > 256 partners
     uint8_t *ch_fused;                                    // [C] 1 = chain is scored + clustered out of shared memory (k_chain.cuh)
     // ---- consensus / threading

@@ -20,7 +20,6 @@
 #include "device_batch.cuh"
 #include "k_project.cuh"
 #include "k_score.cuh"
-#include "k_cluster.cuh"
 #include "k_chain.cuh"
 #include "k_cluster_big.cuh"
 #include "k_thread.cuh"
@@ -450,7 +449,7 @@ struct Pipeline {
             for (int64_t c = 0; c < C; c++) if (!s_fused[c] && h_nfinal[c] > 0)
                 CK(cudaMemsetAsync(d.W + s_cw[c], 0, (size_t)h_nfinal[c] * h_nfinal[c] * 4, st));
             d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw); d.big_key = dalloc<uint32_t>(n_cw);
-            d.ce_active = dalloc<uint8_t>(NF); d.ce_dirty = dalloc<uint8_t>(NF); d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
+            d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
             d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
         }
         d.rec = dalloc<PosRec>(NP); d.back = dalloc<uint16_t>(NP * S_max);
@@ -516,13 +515,12 @@ struct Pipeline {
         }
         for (int i = 0; i < 8; i++) { CK(cudaEventRecord(cx->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, cx->ev_join[i], 0)); }
         CK(cudaEventRecord(cx->ev[11], st));
-        // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one block per chain
+        // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one 1024-thread block per chain
         if (nf_unfused) {
             int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
             if (len) {
                 const int nbig = std::min<int>(n_max, 8191);
-                if (getenv("AHS_OLD_BIG")) k_cluster_edit<<<std::min<int64_t>(len, (int64_t)sms * 4), CE_THREADS, 0, st>>>(d, dv_order + first, len, counters + 2);
-                else k_cluster_big<<<(unsigned)std::min<int64_t>(len, sms), CB_THREADS, cb_smem_bytes(nbig), st>>>(d, dv_order + first, len, nbig, counters + 2);
+                k_cluster_big<<<(unsigned)std::min<int64_t>(len, sms), CB_THREADS, cb_smem_bytes(nbig), st>>>(d, dv_order + first, len, nbig, counters + 2);
                 n_launches += 1;
             }
         }

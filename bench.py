@@ -273,7 +273,7 @@ def main():
             "e2e": {"value": cells / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch.nbytes(), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(t["n_launches"]) * args.steps, "roofline": roofline, "clocks": clocks}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_port_baseline(batch)
     print(json.dumps(line))
     if dist is not None:

@@ -29,13 +29,6 @@ __global__ void k_owner(const int64_t* __restrict__ off, int n_owner, int64_t n_
         out[x] = owner_of(off, n_owner, x);
 }
 
-__global__ void k_fill_u64(uint64_t* p, uint64_t v, int64_t n) {
-    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) p[x] = v;
-}
-__global__ void k_fill_i32(int32_t* p, int32_t v, int64_t n) {
-    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) p[x] = v;
-}
-
 // ---------------------------------------------------------------- input validation (first kernel of every pass)
 // err_flags bits: 1 empty allele path, 2 more than 15 alleles, 4 offsets not monotone, 8 entry_read out of
 // range, 16 stage_a_order is not a permutation.  Every later kernel of phase 1 returns at once if a bit is set,
@@ -305,6 +298,7 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
     const unsigned gm = grp_mask<G>();
     const int gl = lane_id() % G;
     const int64_t gpb = blockDim.x / G, g0 = blockIdx.x * gpb + threadIdx.x / G;
+    long long cells_local = 0;
     for (int64_t r = g0; r < d.NR; r += (int64_t)gridDim.x * gpb) {
         const int c = d.read_chain[r];
         if (gl == 0) d.rd_pass[r] = 0;
@@ -351,9 +345,13 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
         if (gl == 0) {
             d.rd_nv[r] = nv; d.rd_first[r] = bc; d.rd_last[r] = last; d.rd_mapq[r] = mapq; d.rd_pass[r] = pass ? 1 : 0;
             d.create_key[r] = ck;
-            if (pass) { atomicAdd(&d.ch_nfinal[c], 1); atomicAdd((unsigned long long*)d.tot_cells, (unsigned long long)nv); }
+            if (pass) { atomicAdd(&d.ch_nfinal[c], 1); cells_local += nv; }
         }
     }
+    // one atomic per warp on the batch-wide cell counter (a per-read atomic on one address serialises in L2)
+    __syncwarp();
+    for (int o = 16; o > 0; o >>= 1) cells_local += __shfl_xor_sync(0xffffffffu, cells_local, o);
+    if (lane_id() == 0 && cells_local) atomicAdd((unsigned long long*)d.tot_cells, (unsigned long long)cells_local);
 }
 
 // ---------------------------------------------------------------- K1e: read order

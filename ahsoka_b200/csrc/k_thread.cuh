@@ -21,7 +21,8 @@
 
 namespace ahs {
 
-constexpr int K3_CAP = 128;      // clusters per position held in shared memory
+constexpr int K3_CAP = 128;      // clusters per position held in shared memory (k_consensus)
+constexpr int K3C_CAP = 16;      // clusters per chain handled by the warp-per-chain kernel (k_consensus_chain)
 
 template <int BITS, int G>
 __global__ void __launch_bounds__(128) k_consensus(DB d) {
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
     const int p = d.ploidy;
     for (int64_t gp = blockIdx.x * (int64_t)NG + wib; gp < d.NP; gp += (int64_t)gridDim.x * NG) {
         const int c = d.pos_chain[gp];
+        if (BITS == 2 && d.ch_nclusters[c] <= K3C_CAP) continue;      // done by k_consensus_chain
         const int b = d.pos[gp];
         const int64_t f0 = d.frow_off[c];
         const int n_c = (int)(d.frow_off[c + 1] - f0);
@@ -93,6 +95,69 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
             d.rec[gp] = r;
         }
         __syncwarp(gm);
+    }
+}
+
+// ---------------------------------------------------------------- K3, common case: one warp per chain
+// 2-bit codes (<= 3 alleles) and at most K3C_CAP clusters in the chain: one lane per covered position walks the
+// chain's reads once and counts (cluster, allele) in a small shared-memory table; the selection of covMap, the
+// consensus and the re-packing are the same statements as in k_consensus, executed by 32 positions at a time.
+__global__ void __launch_bounds__(128) k_consensus_chain(DB d) {
+    __shared__ uint16_t s_cnt[4][32][K3C_CAP][3];                      // [warp][position lane][cluster][allele]
+    __shared__ int32_t s_key[4][32][K3C_CAP], s_idx[4][32][K3C_CAP];
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const int p = d.ploidy;
+    for (int c = blockIdx.x * 4 + wib; c < d.C; c += gridDim.x * 4) {
+        if (d.ch_status[c] != AHS_CHAIN_OK) continue;
+        const int ncl = d.ch_nclusters[c];
+        if (ncl > K3C_CAP) continue;                                   // k_consensus takes this chain
+        const int64_t f0 = d.frow_off[c], p0 = d.pos_off[c];
+        const int n_c = (int)(d.frow_off[c + 1] - f0), n_pos = (int)(d.pos_off[c + 1] - p0);
+        const int32_t* first = d.fr_first + f0; const int32_t* lastp = d.fr_last + f0; const int32_t* cl = d.fr_cluster + f0;
+        const int words = d.ch_words[c];
+        const uint32_t* rows = d.codes + d.code_off[c];
+        for (int q0 = 0; q0 < n_pos; q0 += 32) {
+            const int q = q0 + lane;
+            const bool live = q < n_pos;
+            const int b = live ? d.pos[p0 + q] : -1;
+            uint16_t (*cnt)[3] = s_cnt[wib][lane];
+            for (int k = 0; k < ncl; k++) { cnt[k][0] = 0; cnt[k][1] = 0; cnt[k][2] = 0; }
+            if (live) for (int i = 0; i < n_c; i++) {
+                if (first[i] > b) break;                                // reads are sorted by first position
+                if (lastp[i] < b) continue;
+                const uint32_t code = get_code(rows + (int64_t)i * words, b, 2);
+                if (code) cnt[cl[i]][code - 1]++;
+            }
+            if (live) {
+                const int64_t gb = d.bubble_off[c] + b;
+                const int K = (int)(d.allele_off[gb + 1] - d.allele_off[gb]);
+                // clusters present at this position, ascending id (= the order k_consensus discovers them in)
+                int32_t* key = s_key[wib][lane]; int32_t* idx = s_idx[wib][lane];
+                int ids[K3C_CAP]; uint8_t cons[K3C_CAP]; int cn[K3C_CAP];
+                int m = 0; uint32_t total = 0;
+#pragma unroll
+                for (int k = 0; k < K3C_CAP; k++) if (k < ncl) {
+                    uint32_t tot = 0, best = 0; int best_a = 0;
+                    for (int a = 0; a < 3; a++) if (a < K) { const uint32_t v = cnt[k][a]; tot += v; if (v > best) { best = v; best_a = a; } }   // ties -> smallest allele
+                    if (tot > 0) { ids[m] = k; cn[m] = (int)tot; cons[m] = (uint8_t)best_a; key[m] = (int)tot; idx[m] = m; m++; total += tot; }
+                }
+                PosRec r;
+                r.total = total; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                KV kv; kv.k = key; kv.v = idx;
+                kv_std_sort<true>(kv, m);                              // std::sort(A, cmp) on coverage, descending (:720)
+                int k = min(m, 2 * p);
+                for (int i = p; i < min(m, 2 * p); i++)
+                    if ((uint64_t)cn[idx[i]] * (uint64_t)(8 * p) < (uint64_t)total) { k = i; break; }          // cov < 1/(8p), :768
+                r.k = (uint8_t)k;
+                int sel[MAX_K];
+                for (int l = 0; l < MAX_K; l++) { r.gid[l] = -1; r.cnt_asc[l] = 0; r.cons_asc[l] = 0; r.cons_cm[l] = 0; }
+                for (int l = 0; l < k; l++) { sel[l] = idx[l]; r.gid[l] = ids[sel[l]]; r.cons_cm[l] = cons[sel[l]]; r.cnt_asc[l] = (uint32_t)cn[l]; }
+                for (int x = 1; x < k; x++) { int v = sel[x], y = x - 1; while (y >= 0 && sel[y] > v) { sel[y + 1] = sel[y]; y--; } sel[y + 1] = v; }
+                for (int l = 0; l < k; l++) r.cons_asc[l] = cons[sel[l]];
+                d.rec[p0 + q] = r;
+            }
+            __syncwarp();
+        }
     }
 }
 

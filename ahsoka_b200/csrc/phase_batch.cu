@@ -526,7 +526,8 @@ struct Pipeline {
         }
         CK(cudaEventRecord(cx->ev[4], st));
         // ---- coverage / consensus, threading
-        if (NP) {                                          // 16 lanes per position while the depth (reads per chain) is small
+        if (NP && BITS == 2) { k_consensus_chain<<<grid_for(C, 4, sms), 128, 0, st>>>(d); n_launches += 1; }      // chains with <= 16 clusters
+        if (NP) {                                          // the rest: 16 lanes per position while the depth (reads per chain) is small
             if (NF <= 96 * C) k_consensus<BITS, 16><<<grid_for(NP, 8, sms), 128, 0, st>>>(d); else k_consensus<BITS, 32><<<grid_for(NP, 4, sms), 128, 0, st>>>(d);
             n_launches += 1;
         }

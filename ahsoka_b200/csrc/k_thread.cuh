@@ -365,19 +365,21 @@ __global__ void __launch_bounds__(256) k_thread2(DB d, int32_t* __restrict__ wor
 }
 
 // ---------------------------------------------------------------- CSR cells of the final matrix
-template <int BITS>
+template <int BITS, int G>
 __global__ void __launch_bounds__(256) k_write_cells(DB d) {
-    const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int64_t f = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); f < d.NF; f += (int64_t)gridDim.x * wpb) {
+    const unsigned gm = grp_mask<G>();
+    const int lane = lane_id(), gl = lane % G;
+    const int64_t gpb = blockDim.x / G, g0 = blockIdx.x * gpb + threadIdx.x / G;
+    for (int64_t f = g0; f < d.NF; f += (int64_t)gridDim.x * gpb) {
         const int c = d.fr_chain[f];
         const int i = (int)(f - d.frow_off[c]);
         const uint32_t* row = d.codes + d.code_off[c] + (int64_t)i * d.ch_words[c];
         const int first = d.fr_first[f], last = d.fr_last[f];
         int64_t base = d.cell_off[f];
-        for (int bb = first; bb <= last; bb += 32) {
-            const int b = bb + lane;
+        for (int bb = first; bb <= last; bb += G) {
+            const int b = bb + gl;
             const uint32_t code = b <= last ? get_code(row, b, BITS) : 0u;
-            const unsigned m = __ballot_sync(0xffffffffu, code != 0);
+            const unsigned m = __ballot_sync(gm, code != 0);                 // bits of this group's lanes only
             if (code) { const int64_t o = base + __popc(m & ((1u << lane) - 1u)); d.cell_pos[o] = b; d.cell_allele[o] = (uint8_t)(code - 1); }
             base += __popc(m);
         }
@@ -401,8 +403,23 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_local(const int32_t* __rest
     if (x < n) out[x] = s[threadIdx.x] - v;
     if (threadIdx.x == SCAN_BLOCK - 1) block_sum[blockIdx.x] = s[threadIdx.x];
 }
-__global__ void k_scan_blocks(int64_t* block_sum, int64_t nb, int64_t* total) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { int64_t acc = 0; for (int64_t x = 0; x < nb; x++) { int64_t v = block_sum[x]; block_sum[x] = acc; acc += v; } *total = acc; }
+// exclusive scan of the block sums in place, one block: every thread owns a contiguous run
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(int64_t* block_sum, int64_t nb, int64_t* total) {
+    __shared__ int64_t s[SCAN_BLOCK];
+    const int64_t per = (nb + SCAN_BLOCK - 1) / SCAN_BLOCK, lo = threadIdx.x * per, hi = lo + per < nb ? lo + per : nb;
+    int64_t acc = 0;
+    for (int64_t x = lo; x < hi; x++) acc += block_sum[x];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 1; o < SCAN_BLOCK; o <<= 1) {
+        const int64_t t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int64_t run = s[threadIdx.x] - acc;
+    for (int64_t x = lo; x < hi; x++) { const int64_t v = block_sum[x]; block_sum[x] = run; run += v; }
+    if (threadIdx.x == SCAN_BLOCK - 1) *total = s[threadIdx.x];
 }
 __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(int64_t* out, int64_t n, const int64_t* __restrict__ block_sum, const int64_t* __restrict__ total) {
     const int64_t x = blockIdx.x * (int64_t)SCAN_BLOCK + threadIdx.x;

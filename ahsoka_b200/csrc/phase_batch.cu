@@ -320,7 +320,7 @@ struct Pipeline {
         const int64_t nb = std::max<int64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
         int64_t* bs = dalloc<int64_t>(nb + 1);
         k_scan_local<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(in32, n, out, bs); n_launches += 1;
-        k_scan_blocks<<<1, 32, 0, st>>>(bs, nb, bs + nb); n_launches += 1;
+        k_scan_blocks<<<1, SCAN_BLOCK, 0, st>>>(bs, nb, bs + nb); n_launches += 1;
         k_scan_add<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(out, n, bs, bs + nb); n_launches += 1;
         CK(cudaGetLastError());
     }
@@ -476,7 +476,7 @@ struct Pipeline {
         k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         // ---- CSR cells of the final matrix; with host output they travel D2H on a second stream under the clustering
         scan(d.fr_nv, NF, d.cell_off);
-        if (NF) k_write_cells<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1;
+        if (NF) { if (sz.NB <= 96 * C) k_write_cells<BITS, 8><<<grid_for(NF, 32, sms), TB, 0, st>>>(d); else k_write_cells<BITS, 32><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (early_out) {
             CK(cudaEventRecord(cx->ev_cells, st));
             CK(cudaStreamWaitEvent(cx->stream2, cx->ev_cells, 0));

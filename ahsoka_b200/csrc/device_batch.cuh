@@ -29,7 +29,7 @@ struct DB {
     int64_t *mrow_off;                  // [C] chain offset into mask (u16 units)
     // ---- trigger table
     unsigned long long *hslots; const int64_t *hoff; const uint32_t *hmaskc;   // per-chain hash regions (k_project.cuh)
-    int32_t *inc_next; uint32_t *bubble_univ;
+    int32_t *inc_next; uint32_t *bubble_univ; int4 *arec;                      // arec: per-allele record read by k_project
     // ---- projection
     uint16_t *mask;
     uint64_t *create_key, *createA_key; uint32_t *first_entry; uint8_t *has_good;

@@ -101,6 +101,10 @@ __global__ void k_build_triggers(DB d) {
         if (d.bubble_off[c + 1] - d.bubble_off[c] <= 1) continue;          // trivial chain: never phased (:86)
         const int a = (int)(ga - d.allele_off[gb]);
         if (a >= MAX_ALLELES) { atomicOr(d.err_flags, 2); continue; }
+        // everything k_project needs about a 3-node path in one 16-byte record: bubble (chain-local) | allele << 20 |
+        // simple-path flag << 31, end nodes, stage-A rank
+        d.arec[ga] = make_int4((int)((uint32_t)(gb - d.bubble_off[c]) | ((uint32_t)a << 20) | (len == 3 ? 0x80000000u : 0u)),
+                               len == 3 ? d.anode[o] : 0, len == 3 ? d.anode[o + 2] : 0, d.rankA[gb]);
         if (len <= 2) atomicMin(&d.bubble_univ[gb], (uint32_t)a);          // no inner node: matches every entry (A#9)
         const uint32_t trig = (uint32_t)(len >= 3 ? d.anode[o + 1] : d.anode[o]);
         unsigned long long* tab = d.hslots + d.hoff[c];
@@ -183,15 +187,15 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
                 const bool have = ga >= 0;
                 int64_t gb = 0, o = 0; int len = 0;
                 bool inner_ok = false, full_ok = false, slow = false;
+                int4 rec = make_int4(0, 0, 0, 0);
                 if (have) {
-                    gb = d.allele_bubble[ga];
-                    o = d.anode_off[ga]; len = (int)(d.anode_off[ga + 1] - o);
-                    if (len == 3) {
+                    rec = d.arec[ga];
+                    if (rec.x < 0) {                                                      // 3-node path
                         inner_ok = true;                                                  // the only inner node is the trigger
-                        const int32_t src = d.anode[o], snk = d.anode[o + 2];
-                        full_ok = has_prev && has_next && ((prev == src && next == snk) || (prev == snk && next == src));
+                        full_ok = has_prev && has_next && ((prev == rec.y && next == rec.z) || (prev == rec.z && next == rec.y));
                         slow = !full_ok;                                                  // the end nodes may still be elsewhere in the entry
                     } else slow = true;
+                    if (slow) { gb = d.allele_bubble[ga]; o = d.anode_off[ga]; len = (int)(d.anode_off[ga + 1] - o); }
                 }
                 for (unsigned sm = __ballot_sync(gm, slow); sm; sm &= sm - 1) {
                     const int src_lane = __ffs(sm) - 1;                                   // absolute lane, inside this group
@@ -205,15 +209,15 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
                     if (lane == src_lane) { inner_ok = in_ok; full_ok = f_ok; }
                 }
                 if (have) {
-                    const int b = (int)(gb - b0);
-                    const int a = (int)(ga - d.allele_off[gb]);
+                    const int b = (int)((uint32_t)rec.x & 0xfffffu);
+                    const int a = (int)(((uint32_t)rec.x >> 20) & 0xffu);
                     if (inner_ok) {
                         if (good) atomic_or_u16(&mrow[b], (uint16_t)(1u << a));
                         const uint64_t k = make_key((uint32_t)b, (uint32_t)a, el); ck = k < ck ? k : ck;
                     }
                     if (full_ok) {
                         atomic_or_u16(&mrow[b], (uint16_t)0x8000u);
-                        const uint64_t k = make_key((uint32_t)d.rankA[gb], (uint32_t)a, el); ckA = k < ckA ? k : ckA;
+                        const uint64_t k = make_key((uint32_t)rec.w, (uint32_t)a, el); ckA = k < ckA ? k : ckA;
                     }
                     ga = d.inc_next[ga];
                 }

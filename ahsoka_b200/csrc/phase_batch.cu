@@ -282,7 +282,7 @@ struct Pipeline {
         const int64_t C = sz.C;
         d.bubble_chain = dalloc<int32_t>(sz.NB); d.allele_bubble = dalloc<int32_t>(sz.NA); d.entry_chain = dalloc<int32_t>(sz.NE);
         d.read_chain = dalloc<int32_t>(sz.NR); d.rankA = dalloc<int32_t>(sz.NB);
-        d.hslots = dalloc<unsigned long long>(h_slots); d.inc_next = dalloc<int32_t>(sz.NA);
+        d.hslots = dalloc<unsigned long long>(h_slots); d.inc_next = dalloc<int32_t>(sz.NA); d.arec = dalloc<int4>(sz.NA);
         d.bubble_univ = dalloc<uint32_t>(sz.NB);
         d.mask = dalloc<uint16_t>(sz.M + 2);
         d.create_key = dalloc<uint64_t>(sz.NR); d.createA_key = dalloc<uint64_t>(sz.NR); d.first_entry = dalloc<uint32_t>(sz.NR);

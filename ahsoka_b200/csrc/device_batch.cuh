@@ -57,6 +57,7 @@ struct DB {
     int32_t *path; uint8_t *hap_allele; double *dp_cost;
     // ---- CSR cells out
     int64_t *cell_off; int32_t *cell_pos; uint8_t *cell_allele;
+    int64_t cell_base;                                    // cells of the chunks before this one: cell_off is global, cell_pos / cell_allele are local
 };
 
 }  // namespace ahs

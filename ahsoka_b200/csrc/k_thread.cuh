@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) k_write_cells(DB d) {
         const int i = (int)(f - d.frow_off[c]);
         const uint32_t* row = d.codes + d.code_off[c] + (int64_t)i * d.ch_words[c];
         const int first = d.fr_first[f], last = d.fr_last[f];
-        int64_t base = d.cell_off[f];
+        int64_t base = d.cell_off[f] - d.cell_base;
         for (int bb = first; bb <= last; bb += G) {
             const int b = bb + gl;
             const uint32_t code = b <= last ? get_code(row, b, BITS) : 0u;
@@ -421,10 +421,15 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(int64_t* block_sum, 
     for (int64_t x = lo; x < hi; x++) { const int64_t v = block_sum[x]; block_sum[x] = run; run += v; }
     if (threadIdx.x == SCAN_BLOCK - 1) *total = s[threadIdx.x];
 }
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(int64_t* out, int64_t n, const int64_t* __restrict__ block_sum, const int64_t* __restrict__ total) {
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(int64_t* out, int64_t n, const int64_t* __restrict__ block_sum, const int64_t* __restrict__ total, int64_t base) {
     const int64_t x = blockIdx.x * (int64_t)SCAN_BLOCK + threadIdx.x;
-    if (x < n) out[x] += block_sum[blockIdx.x];
-    if (x == 0) out[n] = *total;
+    if (x < n) out[x] += block_sum[blockIdx.x] + base;
+    if (x == 0) out[n] = *total + base;
+}
+
+// offsets of a chunk of chains, uploaded as a raw slice of the caller's array: make them start at 0
+__global__ void k_rebase(int64_t* p, int64_t n, int64_t base) {
+    for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) p[x] -= base;
 }
 
 }  // namespace ahs

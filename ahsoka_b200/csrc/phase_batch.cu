@@ -58,10 +58,17 @@ struct Pool {
     void release() { for (auto& c : chunks) { if (host) cudaFreeHost(c.p); else cudaFree(c.p); } chunks.clear(); }
 };
 
+// streams and events of one pipeline in flight (a call phases its chains in up to N_LANES chunks, chunk k+1 uploading
+// and projecting while chunk k clusters)
+struct Lane {
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev[12], ev_cells = nullptr, ev_en[8], ev_fork = nullptr, ev_join[8];
+};
+constexpr int N_LANES = 4;
+
 struct Ctx {
-    int device = -1; cudaStream_t stream = nullptr, stream2 = nullptr; cudaEvent_t ev_cells = nullptr, ev_en[8], ev_fork = nullptr, ev_join[8]; cudaStream_t side[8]; Pool dev{false}, pin{true}, outp{true};
+    int device = -1; Lane lanes[N_LANES]; cudaStream_t side[8]; Pool dev{false}, pin{true}, outp{true};
     int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
-    cudaEvent_t ev[12];
     size_t smem_optin = 0;
     std::mutex mu;
 };
@@ -126,14 +133,16 @@ static Ctx* get_ctx(int device) {
     if (device >= n) throw ArgFail{"no such CUDA device"};
     CK(cudaSetDevice(device));
     Ctx* c = new Ctx(); c->device = device;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&c->ev_cells, cudaEventDisableTiming));
-    for (auto& e : c->ev_en) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    for (auto& e : c->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& ln : c->lanes) {
+        CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ln.stream2, cudaStreamNonBlocking));
+        for (auto& e : ln.ev) CK(cudaEventCreate(&e));
+        CK(cudaEventCreateWithFlags(&ln.ev_cells, cudaEventDisableTiming));
+        for (auto& e : ln.ev_en) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming));
+        for (auto& e : ln.ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     for (auto& t : c->side) CK(cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking));
-    for (auto& e : c->ev) CK(cudaEventCreate(&e));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device)); c->sms = prop.multiProcessorCount;
     // fixed-point log tables of rule R1 (oracle/core/phase_core.hpp): llrint(ln(x/1024) * 2^20)
     std::vector<int64_t> ln(1025, 0), ln1(1025, 0);
@@ -158,7 +167,7 @@ struct Sizes { int64_t C, NB, NA, NAN_, NR, NE, NEN, M; int max_k; };
 
 // Host side: O(chains) checks only.  Everything per bubble / allele / entry is checked on the device by
 // k_validate* (first kernels of the pass) and reported after sync #1.
-static Sizes validate(const ahs_batch_in* in) {
+static Sizes validate(const ahs_batch_in* in, bool is_view = false) {
     if (!in) throw ArgFail{"null batch"};
     if (in->n_chains < 0) throw ArgFail{"n_chains < 0"};
     if (in->ploidy < 1 || in->ploidy > MAX_PLOIDY) throw LimitFail{"ploidy outside [1," + std::to_string(MAX_PLOIDY) + "]"};
@@ -169,11 +178,11 @@ static Sizes validate(const ahs_batch_in* in) {
         if (off[0] != 0) throw ArgFail{std::string(name) + "[0] != 0"};
         for (int64_t i = 0; i < n; i++) if (off[i + 1] < off[i]) throw ArgFail{std::string(name) + " not monotone"};
     };
-    auto ends = [&](const int64_t* off, int64_t n, const char* name) -> int64_t {
+    auto ends = [&](const int64_t* off, int64_t n, const char* name) -> int64_t {      // a view (chunk of chains) starts at its base
         if (!off) throw ArgFail{std::string(name) + " is null"};
-        if (off[0] != 0) throw ArgFail{std::string(name) + "[0] != 0"};
-        if (off[n] < 0) throw ArgFail{std::string(name) + " not monotone"};
-        return off[n];
+        if (!is_view && off[0] != 0) throw ArgFail{std::string(name) + "[0] != 0"};
+        if (off[n] < off[0]) throw ArgFail{std::string(name) + " not monotone"};
+        return off[n] - off[0];
     };
     mono(in->bubble_off, s.C, "bubble_off"); s.NB = in->bubble_off[s.C];
     s.NA = ends(in->allele_off, s.NB, "allele_off");
@@ -199,21 +208,22 @@ static inline int grid_for(int64_t items, int per_block, int sms) {
 
 // ------------------------------------------------------------------ the pipeline
 struct Pipeline {
-    Ctx* cx; const ahs_batch_in* in; Sizes sz; DB d{};
+    Ctx* cx; Lane* ln; const ahs_batch_in* in; Sizes sz; DB d{};
     std::vector<int64_t> h_mrow_off, h_frow_off, h_pos_off, h_code_off, h_cw_off, h_back_off;
     int32_t *h_status = nullptr, *h_nfinal = nullptr, *h_npos = nullptr;      // pinned: D2H targets of sync #1
     char *sg_h = nullptr, *sg_d = nullptr; size_t sg_cap = 0;                   // pinned / device staging block of phase 2
     float ms_fused = 0;
     bool early_out = false;                                                     // download the matrix while the clustering runs
+    int64_t base_allele = 0, base_anode = 0, base_enode = 0;                    // first elements of the three big offset arrays (chunk views)
+    int64_t cell_base = 0;                                                      // cells of the chunks before this one (cell_off is global)
     static constexpr int N_EN = 6; int64_t en_cut[N_EN + 1] = {0};              // entry ranges whose alignment nodes are uploaded as one slice
-    int32_t *e_read_id = nullptr, *e_read_mapq = nullptr, *e_cell_pos = nullptr, *e_pos = nullptr; int64_t* e_cell_off = nullptr; uint8_t* e_cell_allele = nullptr;
     int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0, h_slots = 0;
     float ms[8] = {0};
     int n_launches = 0;
 
     template <class T> const T* up(const T* h, int64_t n) {
         T* p = cx->dev.get<T>((size_t)std::max<int64_t>(n, 1));
-        if (n > 0) CK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, cx->stream));
+        if (n > 0) CK(cudaMemcpyAsync(p, h, n * sizeof(T), cudaMemcpyHostToDevice, ln->stream));
         return p;
     }
     // host-derived arrays go through pinned staging: an async copy from pageable memory would first drain the stream
@@ -223,32 +233,37 @@ struct Pipeline {
         return up(stage, n);
     }
     template <class T> T* dalloc(int64_t n) { return cx->dev.get<T>((size_t)std::max<int64_t>(n, 1)); }
-    template <class T> T* dzero(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0, std::max<int64_t>(n, 1) * sizeof(T), cx->stream)); return p; }
-    template <class T> T* dfill_ff(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0xff, std::max<int64_t>(n, 1) * sizeof(T), cx->stream)); return p; }
+    template <class T> T* dzero(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0, std::max<int64_t>(n, 1) * sizeof(T), ln->stream)); return p; }
+    template <class T> T* dfill_ff(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0xff, std::max<int64_t>(n, 1) * sizeof(T), ln->stream)); return p; }
 
     void upload() {
-        cudaStream_t st = cx->stream;
+        cudaStream_t st = ln->stream;
         const int64_t C = sz.C;
         d.C = (int32_t)C; d.ploidy = in->ploidy; d.bits = 2;      // code width is decided at sync #1 (largest allele count)
         d.NB = sz.NB; d.NA = sz.NA; d.NAN_ = sz.NAN_; d.NR = sz.NR; d.NE = sz.NE; d.NEN = sz.NEN;
         d.bubble_off = up(in->bubble_off, C + 1); d.allele_off = up(in->allele_off, sz.NB + 1); d.anode_off = up(in->anode_off, sz.NA + 1);
         d.read_off = up(in->read_off, C + 1); d.entry_off = up(in->entry_off, C + 1); d.enode_off = up(in->enode_off, sz.NE + 1);
+        base_allele = in->allele_off[0]; base_anode = in->anode_off[0]; base_enode = in->enode_off[0];
+        if (base_allele) k_rebase<<<grid_for(sz.NB + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.allele_off, sz.NB + 1, base_allele);
+        if (base_anode) k_rebase<<<grid_for(sz.NA + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.anode_off, sz.NA + 1, base_anode);
+        if (base_enode) k_rebase<<<grid_for(sz.NE + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.enode_off, sz.NE + 1, base_enode);
         // the alignment nodes are 3/4 of the batch: they go up in N_EN slices on the second stream, and the projection of
         // slice i runs under the upload of slice i+1
+        base_enode = in->enode_off[0];
         {
             int32_t* en = cx->dev.get<int32_t>((size_t)std::max<int64_t>(sz.NEN, 1));
             d.enode = en;
             for (int i = 0; i <= N_EN; i++) {
-                const int64_t target = sz.NEN / N_EN * i;
+                const int64_t target = base_enode + sz.NEN / N_EN * i;
                 en_cut[i] = i == N_EN ? sz.NE : (int64_t)(std::lower_bound(in->enode_off, in->enode_off + sz.NE, target) - in->enode_off);
             }
             en_cut[0] = 0;
             for (int i = 0; i < N_EN; i++) {
                 en_cut[i + 1] = std::max(en_cut[i + 1], en_cut[i]);
-                const int64_t o0 = std::min<int64_t>(std::max<int64_t>(in->enode_off[en_cut[i]], 0), sz.NEN);
-                const int64_t o1 = i + 1 == N_EN ? sz.NEN : std::min<int64_t>(std::max<int64_t>(in->enode_off[en_cut[i + 1]], o0), sz.NEN);
-                if (o1 > o0) CK(cudaMemcpyAsync(en + o0, in->enode + o0, (size_t)(o1 - o0) * 4, cudaMemcpyHostToDevice, cx->stream2));
-                CK(cudaEventRecord(cx->ev_en[i], cx->stream2));
+                const int64_t o0 = std::min<int64_t>(std::max<int64_t>(in->enode_off[en_cut[i]] - base_enode, 0), sz.NEN);
+                const int64_t o1 = i + 1 == N_EN ? sz.NEN : std::min<int64_t>(std::max<int64_t>(in->enode_off[en_cut[i + 1]] - base_enode, o0), sz.NEN);
+                if (o1 > o0) CK(cudaMemcpyAsync(en + o0, in->enode + o0, (size_t)(o1 - o0) * 4, cudaMemcpyHostToDevice, ln->stream2));
+                CK(cudaEventRecord(ln->ev_en[i], ln->stream2));
             }
         }
         d.anode = up(in->anode, sz.NAN_); d.entry_read = up(in->entry_read, sz.NE);
@@ -302,7 +317,7 @@ struct Pipeline {
     }
 
     void init_phase1() {
-        cudaStream_t st = cx->stream; const int64_t C = sz.C;
+        cudaStream_t st = ln->stream; const int64_t C = sz.C;
         CK(cudaMemsetAsync(d.hslots, 0xff, (size_t)std::max<int64_t>(h_slots, 1) * 8, st));
         CK(cudaMemsetAsync(d.bubble_univ, 0xff, std::max<int64_t>(sz.NB, 1) * 4, st));
         CK(cudaMemsetAsync(d.mask, 0, (sz.M + 2) * 2, st));
@@ -315,22 +330,22 @@ struct Pipeline {
         CK(cudaMemsetAsync(d.tot_cells, 0, 8, st)); CK(cudaMemsetAsync(d.tot_pairs, 0, 8, st)); CK(cudaMemsetAsync(d.err_flags, 0, 4, st));
     }
 
-    void scan(const int32_t* in32, int64_t n, int64_t* out) {       // out[n+1]
-        cudaStream_t st = cx->stream;
+    void scan(const int32_t* in32, int64_t n, int64_t* out, int64_t base) {       // out[n+1] = base + exclusive prefix sums
+        cudaStream_t st = ln->stream;
         const int64_t nb = std::max<int64_t>(1, (n + SCAN_BLOCK - 1) / SCAN_BLOCK);
         int64_t* bs = dalloc<int64_t>(nb + 1);
         k_scan_local<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(in32, n, out, bs); n_launches += 1;
         k_scan_blocks<<<1, SCAN_BLOCK, 0, st>>>(bs, nb, bs + nb); n_launches += 1;
-        k_scan_add<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(out, n, bs, bs + nb); n_launches += 1;
+        k_scan_add<<<(unsigned)nb, SCAN_BLOCK, 0, st>>>(out, n, bs, bs + nb, base); n_launches += 1;
         CK(cudaGetLastError());
     }
 
     // phase 1: validation, projection, final rows per read, read order; ends with sync #1 (per-chain sizes)
     void run_phase1() {
-        cudaStream_t st = cx->stream; const int sms = cx->sms; const int64_t C = sz.C;
+        cudaStream_t st = ln->stream; const int sms = cx->sms; const int64_t C = sz.C;
         const int TB = 256;
         n_launches = 0;
-        CK(cudaEventRecord(cx->ev[0], st));
+        CK(cudaEventRecord(ln->ev[0], st));
         init_phase1();
         int32_t* d_maxk = dzero<int32_t>(1);
         k_validate<<<grid_for(std::max(sz.NE, std::max(sz.NA, sz.NB)), TB, sms), TB, 0, st>>>(d, d_maxk); n_launches += 1;
@@ -345,7 +360,7 @@ struct Pipeline {
         if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d); n_launches += 1;
         // ---- projection
         for (int i = 0; i < N_EN; i++) {
-            CK(cudaStreamWaitEvent(st, cx->ev_en[i], 0));
+            CK(cudaStreamWaitEvent(st, ln->ev_en[i], 0));
             const int64_t ne = en_cut[i + 1] - en_cut[i];
             if (ne > 0) {
                 if (sz.NEN <= 48 * sz.NE) k_project<16><<<grid_for(ne, 16, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]);      // short alignments
@@ -353,7 +368,7 @@ struct Pipeline {
                 n_launches += 1;
             }
         }
-        CK(cudaEventRecord(cx->ev[1], st));
+        CK(cudaEventRecord(ln->ev[1], st));
         const bool small_rows = sz.NB <= 96 * C;        // short chains: 8 lanes per read, 4 reads in flight per warp
         if (sz.NR) { if (small_rows) k_read_stage_a<8><<<grid_for(sz.NR, 32, sms), TB, 0, st>>>(d); else k_read_stage_a<32><<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
@@ -389,7 +404,7 @@ struct Pipeline {
     };
 
     template <int BITS> void run_bits() {
-        cudaStream_t st = cx->stream; const int sms = cx->sms; const int64_t C = sz.C;
+        cudaStream_t st = ln->stream; const int sms = cx->sms; const int64_t C = sz.C;
         const int TB = 256;
         const int per_word = 32 / BITS;
         int64_t S_max = 1; for (int i = 0; i < in->ploidy; i++) S_max *= 2 * in->ploidy;
@@ -475,15 +490,11 @@ struct Pipeline {
         if (NF) { if (sz.NB <= 96 * C) k_pack_rows<8><<<grid_for(NF, 32, sms), TB, 0, st>>>(d); else k_pack_rows<32><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         k_compact_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         // ---- CSR cells of the final matrix; with host output they travel D2H on a second stream under the clustering
-        scan(d.fr_nv, NF, d.cell_off);
+        d.cell_base = cell_base;
+        scan(d.fr_nv, NF, d.cell_off, cell_base);
         if (NF) { if (sz.NB <= 96 * C) k_write_cells<BITS, 8><<<grid_for(NF, 32, sms), TB, 0, st>>>(d); else k_write_cells<BITS, 32><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
-        if (early_out) {
-            CK(cudaEventRecord(cx->ev_cells, st));
-            CK(cudaStreamWaitEvent(cx->stream2, cx->ev_cells, 0));
-            e_read_id = down2(d.fr_id, NF); e_read_mapq = down2(d.fr_mapq, NF); e_cell_off = down2(d.cell_off, NF + 1);
-            e_cell_pos = down2(d.cell_pos, h_tot_cells); e_cell_allele = down2(d.cell_allele, h_tot_cells); e_pos = down2(d.pos, NP);
-        }
-        CK(cudaEventRecord(cx->ev[2], st));
+        if (early_out) CK(cudaEventRecord(ln->ev_cells, st));          // the matrix part of the result is final: see copy_matrix()
+        CK(cudaEventRecord(ln->ev[2], st));
         // ---- scoring
         if (nf_unfused) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (nf_unfused) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
@@ -497,12 +508,12 @@ struct Pipeline {
             const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
             score_launch<BITS>(nt, kScore[k].kpl, grid, smem, st, d, dv_order + first, len, kScore[k].nmax, counters + 8 + k); n_launches += 1;
         }
-        CK(cudaEventRecord(cx->ev[3], st));
+        CK(cudaEventRecord(ln->ev[3], st));
         // ---- cluster editing out of shared memory
-        CK(cudaEventRecord(cx->ev[10], st));
+        CK(cudaEventRecord(ln->ev[10], st));
         // the size classes run on four side streams so that the tail of one class overlaps the bulk of the next
-        CK(cudaEventRecord(cx->ev_fork, st));
-        for (auto& t : cx->side) CK(cudaStreamWaitEvent(t, cx->ev_fork, 0));
+        CK(cudaEventRecord(ln->ev_fork, st));
+        for (auto& t : cx->side) CK(cudaStreamWaitEvent(t, ln->ev_fork, 0));
         for (int k = N_FUSED - 1, q = 0; k >= 0; k--) {
             int first, len; range_of(k ? kFused[k - 1].nmax + 1 : 1, kFused[k].nmax, first, len);
             if (!len) continue;
@@ -513,8 +524,8 @@ struct Pipeline {
             int32_t* scratch = dalloc<int32_t>((int64_t)grid * nt * kFused[k].per * 3);     // slot-packing areas, one per warp
             cluster_launch(nt, kFused[k].per, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k, scratch); n_launches += 1;
         }
-        for (int i = 0; i < 8; i++) { CK(cudaEventRecord(cx->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, cx->ev_join[i], 0)); }
-        CK(cudaEventRecord(cx->ev[11], st));
+        for (int i = 0; i < 8; i++) { CK(cudaEventRecord(ln->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, ln->ev_join[i], 0)); }
+        CK(cudaEventRecord(ln->ev[11], st));
         // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one 1024-thread block per chain
         if (nf_unfused) {
             int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
@@ -524,18 +535,18 @@ struct Pipeline {
                 n_launches += 1;
             }
         }
-        CK(cudaEventRecord(cx->ev[4], st));
+        CK(cudaEventRecord(ln->ev[4], st));
         // ---- coverage / consensus, threading
         if (NP && BITS == 2) { k_consensus_chain<<<grid_for(C, 4, sms), 128, 0, st>>>(d); n_launches += 1; }      // chains with <= 16 clusters
         if (NP) {                                          // the rest: 16 lanes per position while the depth (reads per chain) is small
             if (NF <= 96 * C) k_consensus<BITS, 16><<<grid_for(NP, 8, sms), 128, 0, st>>>(d); else k_consensus<BITS, 32><<<grid_for(NP, 4, sms), 128, 0, st>>>(d);
             n_launches += 1;
         }
-        CK(cudaEventRecord(cx->ev[5], st));
+        CK(cudaEventRecord(ln->ev[5], st));
         if (NP && in->ploidy == 2) { k_thread2<<<(unsigned)std::min<int64_t>((C + 7) / 8, (int64_t)sms * 8), 256, 0, st>>>(d, counters + 1); n_launches += 1; }
         else if (NP) { k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1; }
-        CK(cudaEventRecord(cx->ev[6], st));
-        CK(cudaEventRecord(cx->ev[7], st));
+        CK(cudaEventRecord(ln->ev[6], st));
+        CK(cudaEventRecord(ln->ev[7], st));
         CK(cudaGetLastError());
     }
 
@@ -543,57 +554,38 @@ struct Pipeline {
 
     void collect_times() {
         float t;
-        CK(cudaEventElapsedTime(&t, cx->ev[0], cx->ev[1])); ms[0] = t;
-        CK(cudaEventElapsedTime(&t, cx->ev[1], cx->ev[2])); ms[1] = t;
-        CK(cudaEventElapsedTime(&t, cx->ev[2], cx->ev[3])); ms[2] = t;
-        CK(cudaEventElapsedTime(&t, cx->ev[3], cx->ev[4])); ms[3] = t;
-        CK(cudaEventElapsedTime(&t, cx->ev[10], cx->ev[11])); ms_fused = t; ms[7] = t;      // shared-memory cluster editing alone
-        CK(cudaEventElapsedTime(&t, cx->ev[4], cx->ev[5])); ms[4] = t;
-        CK(cudaEventElapsedTime(&t, cx->ev[5], cx->ev[6])); ms[5] = t;
-        CK(cudaEventElapsedTime(&t, cx->ev[0], cx->ev[7])); ms[6] = t;
+        CK(cudaEventElapsedTime(&t, ln->ev[0], ln->ev[1])); ms[0] = t;
+        CK(cudaEventElapsedTime(&t, ln->ev[1], ln->ev[2])); ms[1] = t;
+        CK(cudaEventElapsedTime(&t, ln->ev[2], ln->ev[3])); ms[2] = t;
+        CK(cudaEventElapsedTime(&t, ln->ev[3], ln->ev[4])); ms[3] = t;
+        CK(cudaEventElapsedTime(&t, ln->ev[10], ln->ev[11])); ms_fused = t; ms[7] = t;      // shared-memory cluster editing alone
+        CK(cudaEventElapsedTime(&t, ln->ev[4], ln->ev[5])); ms[4] = t;
+        CK(cudaEventElapsedTime(&t, ln->ev[5], ln->ev[6])); ms[5] = t;
+        CK(cudaEventElapsedTime(&t, ln->ev[0], ln->ev[7])); ms[6] = t;
     }
 
-    template <class T> T* down(const T* dptr, int64_t n) {
-        T* h = cx->outp.get<T>((size_t)std::max<int64_t>(n, 1));
-        if (n > 0) CK(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, cx->stream));
-        return h;
+    // where this pipeline's results go inside the arrays of ahs_batch_out (a chunk writes a slice)
+    struct Slices {
+        int32_t *status, *read_id, *read_mapq, *read_cluster, *cell_pos, *n_clusters, *pos, *path, *maxpos;
+        int64_t* cell_off; uint8_t *cell_allele, *hap_allele; double* dp_cost; bool first_chunk;
+    };
+    template <class T> void cp(T* h, const T* dptr, int64_t n, cudaStream_t st) {
+        if (n > 0) CK(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, st));
     }
-    template <class T> T* down2(const T* dptr, int64_t n) {
-        T* h = cx->outp.get<T>((size_t)std::max<int64_t>(n, 1));
-        if (n > 0) CK(cudaMemcpyAsync(h, dptr, n * sizeof(T), cudaMemcpyDeviceToHost, cx->stream2));
-        return h;
+    // the allele matrix and the read order are final after k_write_cells: they travel on the second stream while the
+    // clustering runs (early_out), or with the rest
+    void copy_matrix(const Slices& o, cudaStream_t st) {
+        const int64_t NF = d.NF, NP = d.NP;
+        cp(o.read_id, d.fr_id, NF, st); cp(o.read_mapq, d.fr_mapq, NF, st);
+        if (o.first_chunk) cp(o.cell_off, d.cell_off, NF + 1, st); else cp(o.cell_off + 1, d.cell_off + 1, NF, st);   // entry 0 = the previous chunk's last
+        cp(o.cell_pos, d.cell_pos, h_tot_cells, st); cp(o.cell_allele, d.cell_allele, h_tot_cells, st); cp(o.pos, d.pos, NP, st);
     }
-    template <class T> T* hostcopy(const std::vector<T>& v) {
-        T* h = cx->outp.get<T>(std::max<size_t>(v.size(), 1));
-        if (!v.empty()) memcpy(h, v.data(), v.size() * sizeof(T));
-        return h;
-    }
-
-    void download(ahs_batch_out* out) {
+    void copy_rest(const Slices& o, int64_t* h_pairs) {
         const int64_t C = sz.C, NF = d.NF, NP = d.NP; const int p = in->ploidy;
-        out->n_chains = (int32_t)C; out->ploidy = p;
-        out->status = down(d.ch_status, C);
-        out->read_off = hostcopy(h_frow_off); out->pos_off = hostcopy(h_pos_off);
-        out->read_cluster = down(d.fr_cluster, NF);
-        out->n_clusters = down(d.ch_nclusters, C);
-        out->path = down(d.path, NP * p); out->hap_allele = down(d.hap_allele, NP * p); out->dp_cost = down(d.dp_cost, C);
-        out->maxpos = down(d.ch_maxpos, C);
-        int64_t* h_pairs = cx->outp.get<int64_t>(1);
-        CK(cudaMemcpyAsync(h_pairs, d.tot_pairs, 8, cudaMemcpyDeviceToHost, cx->stream));
-        const int64_t n_cells = h_tot_cells;
-        if (early_out) {
-            out->read_id = e_read_id; out->read_mapq = e_read_mapq; out->cell_off = e_cell_off; out->cell_pos = e_cell_pos;
-            out->cell_allele = e_cell_allele; out->pos = e_pos;
-            CK(cudaStreamSynchronize(cx->stream2));
-        } else {
-            out->read_id = down(d.fr_id, NF); out->read_mapq = down(d.fr_mapq, NF); out->cell_off = down(d.cell_off, NF + 1);
-            out->cell_pos = down(d.cell_pos, n_cells); out->cell_allele = down(d.cell_allele, n_cells); out->pos = down(d.pos, NP);
-        }
-        CK(cudaStreamSynchronize(cx->stream));
-        if (out->cell_off[NF] != n_cells) throw std::runtime_error("cell count mismatch");
-        out->n_cells = n_cells; out->n_pairs = *h_pairs / 2;
-        int64_t ok = 0; for (int64_t c = 0; c < C; c++) ok += out->status[c] == AHS_CHAIN_OK;
-        out->n_chains_ok = ok;
+        cudaStream_t st = ln->stream;
+        cp(o.status, d.ch_status, C, st); cp(o.read_cluster, d.fr_cluster, NF, st); cp(o.n_clusters, d.ch_nclusters, C, st);
+        cp(o.path, d.path, NP * p, st); cp(o.hap_allele, d.hap_allele, NP * p, st); cp(o.dp_cost, d.dp_cost, C, st); cp(o.maxpos, d.ch_maxpos, C, st);
+        CK(cudaMemcpyAsync(h_pairs, d.tot_pairs, 8, cudaMemcpyDeviceToHost, st));
     }
 };
 
@@ -613,7 +605,6 @@ static void fill_empty_out(ahs_batch_out* out, Ctx* cx, int ploidy) {
     out->cell_off = cx->outp.get<int64_t>(1); out->cell_off[0] = 0;
 }
 
-// one batch on one device; iters > 0 = resident timing mode
 struct HostTrace {       // AHS_TRACE=1: wall-clock of the host-side steps of one call, on stderr
     bool on; std::chrono::steady_clock::time_point t0; std::string line;
     HostTrace() : on(getenv("AHS_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
@@ -626,6 +617,27 @@ struct HostTrace {       // AHS_TRACE=1: wall-clock of the host-side steps of on
     ~HostTrace() { if (on) fprintf(stderr, "[ahs trace]%s\n", line.c_str()); }
 };
 
+// a chunk of consecutive chains as a batch of its own: the big arrays are slices of the caller's (their offsets are
+// rebased on the device after the upload), the three per-chain offset arrays are rebased here
+struct ChainView {
+    ahs_batch_in v; std::vector<int64_t> bubble_off, read_off, entry_off;
+    void make(const ahs_batch_in* in, int64_t c0, int64_t c1) {
+        const int64_t n = c1 - c0, b0 = in->bubble_off[c0], e0 = in->entry_off[c0], a0 = in->allele_off[b0];
+        bubble_off.resize(n + 1); read_off.resize(n + 1); entry_off.resize(n + 1);
+        for (int64_t c = 0; c <= n; c++) { bubble_off[c] = in->bubble_off[c0 + c] - b0; read_off[c] = in->read_off[c0 + c] - in->read_off[c0]; entry_off[c] = in->entry_off[c0 + c] - e0; }
+        v = *in;
+        v.n_chains = (int32_t)n; v.chain_id = in->chain_id ? in->chain_id + c0 : nullptr;
+        v.bubble_off = bubble_off.data(); v.read_off = read_off.data(); v.entry_off = entry_off.data();
+        v.allele_off = in->allele_off + b0; v.anode_off = in->anode_off + a0; v.anode = in->anode + in->anode_off[a0];
+        v.stage_a_order = in->stage_a_order ? in->stage_a_order + b0 : nullptr;
+        v.enode_off = in->enode_off + e0; v.enode = in->enode + in->enode_off[e0];
+        v.entry_read = in->entry_read + e0; v.entry_identity = in->entry_identity + e0;
+    }
+};
+
+// one batch on one device; iters > 0 = resident timing mode.  A call with host output (iters == 0) and a large batch runs
+// as N_LANES chunks of chains, each a pipeline on its own streams: chunk k+1 uploads and projects under the clustering
+// of chunk k, so that most of the H2D time is hidden.
 static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int device, int warmup, int iters) {
     if (!out) throw ArgFail{"null output"};
     HostTrace tr;
@@ -635,47 +647,118 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     std::lock_guard<std::mutex> g(cx->mu);
     CK(cudaSetDevice(device));
     if (cx->out_busy) throw ArgFail{"previous ahs_batch_out of this device was not released with ahs_free_out"};
-    CK(cudaStreamSynchronize(cx->stream2)); CK(cudaStreamSynchronize(cx->stream));      // nothing of a failed earlier call is in flight
+    CK(cudaDeviceSynchronize());                          // nothing of a failed earlier call is in flight
     cx->dev.reset(); cx->outp.reset(); cx->pin.reset();
     if (sz.C == 0) { fill_empty_out(out, cx, in->ploidy); cx->out_busy = true; return; }
-    Pipeline pl; pl.cx = cx; pl.in = in; pl.sz = sz; pl.early_out = iters == 0;
-    cudaEvent_t e0 = cx->ev[8], e1 = cx->ev[9];
-    CK(cudaEventRecord(e0, cx->stream));
-    pl.upload();
-    CK(cudaEventRecord(e1, cx->stream));
-    tr.mark("upload_enqueue");
-    pl.alloc_phase1();
-    // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
-    std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
-    float acc[8] = {0};
-    const int total = iters > 0 ? warmup + iters : 1;
-    for (int it = 0; it < total; it++) {
-        for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
-        pl.run();
-        tr.mark("run_enqueue");
-        CK(cudaStreamSynchronize(cx->stream));
-        tr.mark("run_sync");
-        pl.collect_times();
-        if (iters > 0 && it >= warmup) for (int i = 0; i < 8; i++) acc[i] += pl.ms[i];
+    const int64_t C = sz.C; const int p = in->ploidy;
+    // ---- chunks: equal shares of the alignment nodes (the bulk of the upload)
+    int n_chunks = 1;
+    if (iters == 0 && C >= 4096 && sz.NEN >= (int64_t)16 << 20) {
+        n_chunks = 3;
+        if (const char* e = getenv("AHS_CHUNKS")) n_chunks = std::max(1, std::min(N_LANES, atoi(e)));       // tuning / debugging
     }
-    if (iters > 0) for (int i = 0; i < 8; i++) pl.ms[i] = acc[i] / iters;
+    std::vector<int64_t> cut(n_chunks + 1, 0); cut[n_chunks] = C;
+    for (int k = 1; k < n_chunks; k++) {
+        const int64_t target = sz.NEN / n_chunks * k;
+        int64_t lo = cut[k - 1], hi = C;                  // first chain whose entries start at or after the target
+        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (in->enode_off[in->entry_off[mid]] >= target) hi = mid; else lo = mid + 1; }
+        cut[k] = lo;
+    }
+    std::vector<ChainView> views(n_chunks); std::vector<Pipeline> pls(n_chunks);
+    std::vector<Sizes> szs(n_chunks);
+    cudaEvent_t e0 = cx->lanes[0].ev[8], e1 = cx->lanes[0].ev[9];
+    CK(cudaEventRecord(e0, cx->lanes[0].stream));
+    float acc[8] = {0};
+    int64_t tot_cells = 0, NFt = 0, NPt = 0;
+    for (int k = 0; k < n_chunks; k++) {
+        Pipeline& pl = pls[k];
+        pl.cx = cx; pl.ln = &cx->lanes[k]; pl.early_out = iters == 0;
+        if (n_chunks == 1) { pl.in = in; pl.sz = sz; }
+        else { views[k].make(in, cut[k], cut[k + 1]); pl.in = &views[k].v; pl.sz = validate(pl.in, true); }
+        szs[k] = pl.sz;
+        if (pl.sz.C == 0) continue;
+        pl.cell_base = tot_cells;
+        pl.upload();
+        if (k == 0) { CK(cudaEventRecord(e1, pl.ln->stream)); tr.mark("upload_enqueue"); }
+        pl.alloc_phase1();
+        // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
+        std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
+        const int total = iters > 0 ? warmup + iters : 1;
+        for (int it = 0; it < total; it++) {
+            if (iters > 0) for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
+            pl.run();                                     // ends with phase 2 enqueued; sync #1 inside waited for this chunk's upload only
+            tr.mark("run_enqueue");
+            if (iters > 0) {
+                CK(cudaStreamSynchronize(pl.ln->stream));
+                pl.collect_times();
+                if (it >= warmup) for (int i = 0; i < 8; i++) acc[i] += pl.ms[i];
+            }
+        }
+        tot_cells += pl.h_tot_cells; NFt += pl.d.NF; NPt += pl.d.NP;
+    }
+    // ---- output arrays (sizes are known now), then the copies
     memset(out, 0, sizeof(*out));
-    cudaEvent_t d0 = cx->ev[8];
-    float h2d = 0; CK(cudaEventElapsedTime(&h2d, e0, e1));
-    CK(cudaEventRecord(d0, cx->stream));
-    pl.download(out);
-    CK(cudaEventRecord(e1, cx->stream)); CK(cudaEventSynchronize(e1));
-    tr.mark("download");
+    out->n_chains = (int32_t)C; out->ploidy = p;
+    out->status = cx->outp.get<int32_t>(C); out->n_clusters = cx->outp.get<int32_t>(C); out->dp_cost = cx->outp.get<double>(C); out->maxpos = cx->outp.get<int32_t>(C);
+    out->read_off = cx->outp.get<int64_t>(C + 1); out->pos_off = cx->outp.get<int64_t>(C + 1);
+    out->read_id = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1)); out->read_mapq = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1));
+    out->read_cluster = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1)); out->cell_off = cx->outp.get<int64_t>(NFt + 1);
+    out->cell_pos = cx->outp.get<int32_t>(std::max<int64_t>(tot_cells, 1)); out->cell_allele = cx->outp.get<uint8_t>(std::max<int64_t>(tot_cells, 1));
+    out->pos = cx->outp.get<int32_t>(std::max<int64_t>(NPt, 1)); out->path = cx->outp.get<int32_t>(std::max<int64_t>(NPt * p, 1));
+    out->hap_allele = cx->outp.get<uint8_t>(std::max<int64_t>(NPt * p, 1));
+    out->cell_off[0] = 0;
+    int64_t* h_pairs = cx->outp.get<int64_t>(n_chunks);
+    std::vector<Pipeline::Slices> sl(n_chunks);
+    {
+        int64_t f = 0, q = 0, cells = 0;
+        out->read_off[0] = 0; out->pos_off[0] = 0;
+        for (int k = 0; k < n_chunks; k++) {
+            Pipeline& pl = pls[k];
+            const int64_t c0 = cut[k];
+            sl[k] = Pipeline::Slices{out->status + c0, out->read_id + f, out->read_mapq + f, out->read_cluster + f, out->cell_pos + cells, out->n_clusters + c0,
+                                     out->pos + q, out->path + q * p, out->maxpos + c0, out->cell_off + f, out->cell_allele + cells, out->hap_allele + q * p,
+                                     out->dp_cost + c0, k == 0};
+            h_pairs[k] = 0;
+            if (szs[k].C == 0) continue;
+            for (int64_t c = 0; c < szs[k].C; c++) { out->read_off[c0 + c + 1] = f + pl.h_frow_off[c + 1]; out->pos_off[c0 + c + 1] = q + pl.h_pos_off[c + 1]; }
+            f += pl.d.NF; q += pl.d.NP; cells += pl.h_tot_cells;
+        }
+    }
+    cudaEvent_t d0 = cx->lanes[0].ev[8];
+    float h2d = 0; CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&h2d, e0, e1));
+    CK(cudaEventRecord(d0, cx->lanes[0].stream2));
+    for (int k = 0; k < n_chunks; k++) if (szs[k].C) {
+        Pipeline& pl = pls[k];
+        if (pl.early_out) { CK(cudaStreamWaitEvent(pl.ln->stream2, pl.ln->ev_cells, 0)); pl.copy_matrix(sl[k], pl.ln->stream2); }
+        else pl.copy_matrix(sl[k], pl.ln->stream);
+        pl.copy_rest(sl[k], h_pairs + k);
+    }
+    tr.mark("copies_enqueue");
+    for (int k = 0; k < n_chunks; k++) { CK(cudaStreamSynchronize(cx->lanes[k].stream2)); CK(cudaStreamSynchronize(cx->lanes[k].stream)); }
+    tr.mark("run_sync");
+    CK(cudaEventRecord(e1, cx->lanes[0].stream)); CK(cudaEventSynchronize(e1));
     float d2h = 0; CK(cudaEventElapsedTime(&d2h, d0, e1));
-    out->ms_h2d = h2d; out->ms_project = pl.ms[0]; out->ms_rows = pl.ms[1]; out->ms_score = pl.ms[2]; out->ms_cluster = pl.ms[3];
-    out->ms_consensus = pl.ms[4]; out->ms_thread = pl.ms[5]; out->ms_total_device = pl.ms[6]; out->ms_d2h = d2h;
-    out->n_launches = pl.n_launches;
+    if (out->cell_off[NFt] != tot_cells) throw std::runtime_error("cell count mismatch");
+    out->n_cells = tot_cells;
+    for (int k = 0; k < n_chunks; k++) out->n_pairs += h_pairs[k] / 2;
+    for (int64_t c = 0; c < C; c++) out->n_chains_ok += out->status[c] == AHS_CHAIN_OK;
+    // ---- timings and byte counts
+    if (iters > 0) for (int i = 0; i < 8; i++) pls[0].ms[i] = acc[i] / iters;
+    else {
+        for (int k = 0; k < n_chunks; k++) if (szs[k].C) { pls[k].collect_times(); if (k) for (int i = 0; i < 6; i++) pls[0].ms[i] += pls[k].ms[i]; }
+        int last = 0; for (int k = 0; k < n_chunks; k++) if (szs[k].C) last = k;
+        float t = 0; CK(cudaEventElapsedTime(&t, cx->lanes[0].ev[0], cx->lanes[last].ev[7])); pls[0].ms[6] = t;      // first kernel -> last kernel
+    }
+    Pipeline& p0 = pls[0];
+    out->ms_h2d = h2d; out->ms_project = p0.ms[0]; out->ms_rows = p0.ms[1]; out->ms_score = p0.ms[2]; out->ms_cluster = p0.ms[3];
+    out->ms_consensus = p0.ms[4]; out->ms_thread = p0.ms[5]; out->ms_total_device = p0.ms[6]; out->ms_d2h = d2h;
+    for (int k = 0; k < n_chunks; k++) out->n_launches += pls[k].n_launches;
     {   // algorithmic bytes, SURVEY.md §8d: each datum crosses HBM once
-        const double code_bytes = pl.d.bits / 8.0;
-        const int64_t cells = out->n_cells, NFr = pl.d.NF;
-        out->bytes_project = 4 * sz.NEN + 4 * sz.NAN_ + 8 * sz.NE + (int64_t)(code_bytes * cells) + 12 * NFr;
-        out->bytes_score = (int64_t)(code_bytes * cells) + 12 * NFr + 4 * out->n_pairs;
-        out->bytes_consensus = (int64_t)(code_bytes * cells) + 16 * NFr + 5 * pl.d.NP * in->ploidy;   // k_pos ~ ploidy retained clusters
+        const double code_bytes = p0.d.bits / 8.0;
+        const int64_t cells = out->n_cells;
+        out->bytes_project = 4 * sz.NEN + 4 * sz.NAN_ + 8 * sz.NE + (int64_t)(code_bytes * cells) + 12 * NFt;
+        out->bytes_score = (int64_t)(code_bytes * cells) + 12 * NFt + 4 * out->n_pairs;
+        out->bytes_consensus = (int64_t)(code_bytes * cells) + 16 * NFt + 5 * NPt * p;   // k_pos ~ ploidy retained clusters
     }
     cx->out_busy = true;
 }

@@ -166,11 +166,24 @@ def run_reference_arm(args):
             "data": "synthetic", "config": {"workload": args.workload, "sample_chains": n_chains, "cells": cells},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "chains_per_s": chains / dt},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints there (NCCL's version banner,
+    torchrun notices) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -275,7 +288,7 @@ def main():
             "gpu_launches": int(t["n_launches"]) * args.steps, "roofline": roofline, "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_port_baseline(batch)
-    print(json.dumps(line))
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -93,8 +93,11 @@ def make_batch(workload, scale, rank):
     return synth.generate(prm)
 
 
+WORKLOAD_NAMES = {"cfg2": "cfg2: BASELINE.json configs[1] synthetic diploid human-scale graph"}
+
+
 def workload_desc(workload, scale, batch):
-    return {"workload": f"{workload}: BASELINE.json configs[1] synthetic diploid human-scale graph" if workload == "cfg2" else workload,
+    return {"workload": WORKLOAD_NAMES.get(workload, workload),
             "scale": scale, "chains_per_gpu": batch.n_chains, "bubbles_per_gpu": int(batch.bubble_off[-1]),
             "reads_per_gpu": int(batch.read_off[-1]), "entry_nodes_per_gpu": int(batch.enode.shape[0]), "ploidy": int(batch.ploidy),
             "l2": "inputs (%.0f MB) and per-chain workspaces exceed the 126 MB L2; no explicit flush" % (batch.nbytes() / 1e6)}
@@ -163,7 +166,7 @@ def run_reference_arm(args):
     val = cells / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64 fixed point",
-            "data": "synthetic", "config": {"workload": args.workload, "sample_chains": n_chains, "cells": cells},
+            "data": "synthetic", "config": {"workload": WORKLOAD_NAMES.get(args.workload, args.workload), "sample_chains": n_chains, "cells": cells, "ploidy": 2},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "chains_per_s": chains / dt},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     _emit(line)

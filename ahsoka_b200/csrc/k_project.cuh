@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
         if (gl == 0) {
             d.rd_nv[r] = nv; d.rd_first[r] = bc; d.rd_last[r] = last; d.rd_mapq[r] = mapq; d.rd_pass[r] = pass ? 1 : 0;
             d.create_key[r] = ck;
-            if (pass) { atomicAdd(&d.ch_nfinal[c], 1); cells_local += nv; }
+            if (pass) { atomicAdd(&d.ch_nfinal[c], 1); atomicAdd(&d.ch_cells[c], (unsigned long long)nv); cells_local += nv; }
         }
     }
     // one atomic per warp on the batch-wide cell counter (a per-read atomic on one address serialises in L2)

@@ -211,6 +211,7 @@ struct Pipeline {
     Ctx* cx; Lane* ln; const ahs_batch_in* in; Sizes sz; DB d{};
     std::vector<int64_t> h_mrow_off, h_frow_off, h_pos_off, h_code_off, h_cw_off, h_back_off;
     int32_t *h_status = nullptr, *h_nfinal = nullptr, *h_npos = nullptr;      // pinned: D2H targets of sync #1
+    unsigned long long* h_cells = nullptr;
     char *sg_h = nullptr, *sg_d = nullptr; size_t sg_cap = 0;                   // pinned / device staging block of phase 2
     float ms_fused = 0;
     bool early_out = false;                                                     // download the matrix while the clustering runs
@@ -308,10 +309,11 @@ struct Pipeline {
         d.poscov = dalloc<uint8_t>(sz.NB); d.pos_compact = dalloc<int32_t>(sz.NB);
         d.ch_status = dalloc<int32_t>(C); d.ch_maxpos = dalloc<int32_t>(C); d.ch_flags = dalloc<int32_t>(C); d.ch_T = dalloc<int32_t>(C);
         d.ch_nfinal = dalloc<int32_t>(C); d.ch_npos = dalloc<int32_t>(C); d.ch_maxspan = dalloc<int32_t>(C); d.ch_words = dalloc<int32_t>(C);
-        d.ch_nclusters = dalloc<int32_t>(C);
+        d.ch_nclusters = dalloc<int32_t>(C); d.ch_cells = dalloc<unsigned long long>(C);
         d.tot_cells = dalloc<int64_t>(1); d.tot_pairs = dalloc<int64_t>(1); d.err_flags = dalloc<int32_t>(1);
         d.ln = cx->d_ln; d.ln1 = cx->d_ln1;
         h_status = cx->pin.get<int32_t>(C); h_nfinal = cx->pin.get<int32_t>(C); h_npos = cx->pin.get<int32_t>(C);
+        h_cells = cx->pin.get<unsigned long long>(C);
         sg_cap = (size_t)(C + 2) * (8 * 5 + 4 * 3 + 1) + 512;
         sg_h = (char*)cx->pin.alloc(sg_cap); sg_d = (char*)cx->dev.alloc(sg_cap);
     }
@@ -327,6 +329,7 @@ struct Pipeline {
         CK(cudaMemsetAsync(d.rankA, 0xff, std::max<int64_t>(sz.NB, 1) * 4, st));
         CK(cudaMemsetAsync(d.ch_status, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxpos, 0xff, C * 4, st)); CK(cudaMemsetAsync(d.ch_flags, 0, C * 4, st));
         CK(cudaMemsetAsync(d.ch_nfinal, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxspan, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_nclusters, 0, C * 4, st));
+        CK(cudaMemsetAsync(d.ch_cells, 0, C * 8, st));
         CK(cudaMemsetAsync(d.tot_cells, 0, 8, st)); CK(cudaMemsetAsync(d.tot_pairs, 0, 8, st)); CK(cudaMemsetAsync(d.err_flags, 0, 4, st));
     }
 
@@ -383,6 +386,7 @@ struct Pipeline {
         CK(cudaMemcpyAsync(h_status, d.ch_status, C * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_nfinal, d.ch_nfinal, C * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_npos, d.ch_npos, C * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_cells, d.ch_cells, C * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_tot_cells, d.tot_cells, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&h_err, d.err_flags, 4, cudaMemcpyDeviceToHost, st));
         int32_t h_maxk = 0;
@@ -419,7 +423,7 @@ struct Pipeline {
         n_code_words = 0; n_cw = 0;
         bool status_changed = false;
         s_frow[0] = 0; s_pos[0] = 0;
-        int64_t nf_unfused = 0; int n_max = 0;
+        int64_t nf_unfused = 0, cells_ok = 0; int n_max = 0;
         for (int64_t c = 0; c < C; c++) {
             if (h_status[c] == AHS_CHAIN_OK && h_nfinal[c] > MAX_READS_CLUSTER) { h_status[c] = AHS_CHAIN_TOO_LARGE; status_changed = true; }
             s_status[c] = h_status[c];
@@ -435,7 +439,9 @@ struct Pipeline {
             s_back[c] = s_pos[c] * S_max;
             if (!s_fused[c]) nf_unfused += n;
             n_max = std::max<int>(n_max, (int)n);
+            if (ok) cells_ok += (int64_t)h_cells[c];
         }
+        h_tot_cells = cells_ok;                            // chains dropped above (too many reads) emit nothing
         // chains by decreasing read count (counting sort): every size class is one contiguous range of `order`
         std::vector<int32_t> start(n_max + 2, 0);
         for (int64_t c = 0; c < C; c++) start[n_max - h_nfinal[c] + 1]++;

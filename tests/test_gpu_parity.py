@@ -182,3 +182,30 @@ def test_randomised_shapes_twice_each():
     import sys
     r = subprocess.run([sys.executable, os.path.join(api.ROOT, "tools", "stress_gpu.py"), "30", "4242"], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_build_limits_are_reported_not_mis_phased():
+    import copy
+    b = synth.generate(synth.params(2, 6, 1, 12, depth=20.0, seed=97))
+    b5 = copy.copy(b); b5.ploidy = 5
+    with pytest.raises(RuntimeError, match=r"failed \(3\).*ploidy"):          # AHS_ERR_LIMIT
+        api.phase_batch(b5)
+    # a bubble with 16 alleles: more than the 4-bit codes hold
+    wide = synth.generate(synth.params(2, 4, 1, 8, depth=20.0, max_alleles=15, seed=98))
+    ao = wide.allele_off.copy(); no = wide.anode_off.copy()
+    k0 = int(np.argmax(np.diff(ao)))                                       # widen its largest bubble to 16 alleles by repeating one path
+    extra = 16 - int(ao[k0 + 1] - ao[k0])
+    a_last = int(ao[k0 + 1]) - 1
+    path = wide.anode[no[a_last]:no[a_last + 1]]
+    new_anode = np.concatenate([wide.anode[:no[a_last + 1]]] + [path] * extra + [wide.anode[no[a_last + 1]:]])
+    new_no = np.concatenate([no[:a_last + 2], no[a_last + 1] + len(path) * np.arange(1, extra + 1), no[a_last + 2:] + len(path) * extra])
+    new_ao = ao.copy(); new_ao[k0 + 1:] += extra
+    w2 = copy.copy(wide); w2.allele_off, w2.anode_off, w2.anode = new_ao, new_no.astype(np.int64), new_anode.astype(np.int32)
+    with pytest.raises(RuntimeError, match=r"failed \(3\).*15 alleles"):
+        api.phase_batch(w2)
+    # a chain with more final reads than cluster editing accepts: reported per chain, the other chains are phased
+    big = synth.generate(synth.params(2, 1, 0, 2600, depth=80.0, seed=99))
+    small = synth.generate(synth.params(2, 5, 1, 12, depth=20.0, seed=100))
+    got = api.phase_batch(big)
+    assert int(got.status[0]) == 3 and got.read_off[-1] == 0               # AHS_CHAIN_TOO_LARGE, nothing emitted for it
+    assert not api.phase_batch(small).diff(oracle_phase(small))

@@ -211,14 +211,10 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
                 if (have) {
                     const int b = (int)((uint32_t)rec.x & 0xfffffu);
                     const int a = (int)(((uint32_t)rec.x >> 20) & 0xffu);
-                    if (inner_ok) {
-                        if (good) atomic_or_u16(&mrow[b], (uint16_t)(1u << a));
-                        const uint64_t k = make_key((uint32_t)b, (uint32_t)a, el); ck = k < ck ? k : ck;
-                    }
-                    if (full_ok) {
-                        atomic_or_u16(&mrow[b], (uint16_t)0x8000u);
-                        const uint64_t k = make_key((uint32_t)rec.w, (uint32_t)a, el); ckA = k < ckA ? k : ckA;
-                    }
+                    const uint32_t bits = ((inner_ok && good) ? (1u << a) : 0u) | (full_ok ? 0x8000u : 0u);
+                    if (bits) atomic_or_u16(&mrow[b], (uint16_t)bits);                   // one atomic for both tests
+                    if (inner_ok) { const uint64_t k = make_key((uint32_t)b, (uint32_t)a, el); ck = k < ck ? k : ck; }
+                    if (full_ok) { const uint64_t k = make_key((uint32_t)rec.w, (uint32_t)a, el); ckA = k < ckA ? k : ckA; }
                     ga = d.inc_next[ga];
                 }
             }

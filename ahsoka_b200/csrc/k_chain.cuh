@@ -272,12 +272,13 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
 // resident blocks per SM the register allocation is held to (~64 registers per thread: 24 of them are the slots)
 __host__ __device__ constexpr int cc_min_blocks(int nt, int per) {
     // registers per thread ~ 40 + 3 per slot
-    return per <= 4 ? (nt <= 32 ? 32 : nt <= 64 ? 20 : nt <= 128 ? 10 : nt <= 192 ? 6 : nt <= 256 ? 5 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1)
+    return per > 8 ? (nt <= 96 ? 8 : nt <= 128 ? 6 : nt <= 192 ? 4 : nt <= 256 ? 3 : nt <= 384 ? 2 : 1)
+         : per <= 4 ? (nt <= 32 ? 32 : nt <= 64 ? 20 : nt <= 128 ? 10 : nt <= 192 ? 6 : nt <= 256 ? 5 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1)
                     : (nt <= 32 ? 32 : nt <= 64 ? 18 : nt <= 96 ? 12 : nt <= 128 ? 9 : nt <= 192 ? 6 : nt <= 256 ? 4 : nt <= 384 ? 3 : nt <= 512 ? 2 : 1);
 }
 
 // lanes that share one node x in the fresh-cost pass of a merge (threads / G >= largest n of the block size's classes)
-__host__ __device__ constexpr int cc_fresh_g(int nt) { return nt <= 32 ? 1 : nt <= 192 ? 2 : nt <= 768 ? 4 : 8; }
+__host__ __device__ constexpr int cc_fresh_g(int nt, int per = 8) { return per > 8 ? (nt <= 64 ? 1 : nt < 512 ? 2 : 4) : nt <= 32 ? 1 : nt <= 192 ? 2 : nt <= 768 ? 4 : 8; }
 static_assert(CC_MAXN <= 128, "k_cluster_chain walks rows in four 32-lane strides");
 
 // ------------------------------------------------------------------------------------------------
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 __syncthreads();
                 // fresh induced costs of the pairs (a,x): G adjacent lanes per x share the third nodes
                 {
-                    constexpr int G = cc_fresh_g(NT);
+                    constexpr int G = cc_fresh_g(NT, PER);
                     const int nact = scal[0];
                     const int xi = tid / G, g = tid % G;
                     int x = 0, w = 0;

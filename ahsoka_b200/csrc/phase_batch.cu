@@ -77,11 +77,11 @@ static Ctx* g_ctx[64] = {nullptr};
 
 // ------------------------------------------------------------------ shared-memory scoring + cluster editing: size classes
 // Cluster editing: a class = (largest n, threads per block, pair slots per thread).  The block size grows with the pair
-// triangle so that every thread owns at most `per` slots; the shared-memory footprint (two n x n int32 matrices) is
+// triangle so that every thread owns at most `per` slots (8, or 12 where measured faster: 65-78 reads); the shared-memory footprint (two n x n int32 matrices) is
 // sized by the class's largest n.
 struct FusedClass { int nmax, nt, per; };
 static const FusedClass kFused[] = {{16, 32, 8}, {23, 32, 8}, {28, 64, 8}, {32, 64, 8}, {36, 96, 8}, {39, 96, 8}, {42, 128, 8}, {45, 128, 8},
-                                    {50, 192, 8}, {55, 192, 8}, {60, 256, 8}, {64, 256, 8}, {71, 384, 8}, {78, 384, 8}, {85, 512, 8}, {91, 512, 8},
+                                    {50, 192, 8}, {55, 192, 8}, {60, 256, 8}, {64, 256, 8}, {71, 256, 12}, {78, 256, 12}, {85, 512, 8}, {91, 512, 8},
                                     {101, 768, 8}, {111, 768, 8}, {120, 1024, 8}, {128, 1024, 8}};
 constexpr int N_FUSED = (int)(sizeof(kFused) / sizeof(kFused[0]));
 // Scoring: (largest n, threads per block, sort keys per lane)
@@ -89,7 +89,7 @@ struct ScoreClass { int nmax, nt, kpl; };
 static const ScoreClass kScore[] = {{32, 64, 1}, {48, 128, 2}, {64, 128, 2}, {96, 256, 4}, {128, 256, 4}};
 constexpr int N_SCORE = (int)(sizeof(kScore) / sizeof(kScore[0]));
 
-#define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8)
+#define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8) X(256, 12)
 #define AHS_FOR_EACH_SC(X) X(64, 1) X(128, 2) X(256, 4)
 static void fused_set_attributes(size_t optin) {
 #define X(NT, PER) CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
@@ -119,7 +119,7 @@ static void check_classes(size_t smem_optin) {
     for (int k = 0; k < N_FUSED; k++) {
         if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) throw LimitFail{"device shared memory too small for the cluster-editing classes"};
         if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)kFused[k].per * kFused[k].nt) throw std::logic_error("cluster class table: slots");
-        if (kFused[k].nmax * cc_fresh_g(kFused[k].nt) > kFused[k].nt) throw std::logic_error("cluster class table: fresh-cost lanes");
+        if (kFused[k].nmax * cc_fresh_g(kFused[k].nt, kFused[k].per) > kFused[k].nt) throw std::logic_error("cluster class table: fresh-cost lanes");
     }
     if (kFused[N_FUSED - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
     for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax) > smem_optin) throw std::logic_error("score class table");

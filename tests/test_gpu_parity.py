@@ -209,3 +209,13 @@ def test_build_limits_are_reported_not_mis_phased():
     got = api.phase_batch(big)
     assert int(got.status[0]) == 3 and got.read_off[-1] == 0               # AHS_CHAIN_TOO_LARGE, nothing emitted for it
     assert not api.phase_batch(small).diff(oracle_phase(small))
+
+
+@pytest.mark.parametrize("chunks", ["1", "2", "4"])
+def test_chunked_call_is_result_identical(chunks, monkeypatch):
+    # a large call runs as several chunks of chains in flight (H2D of chunk k+1 under the clustering of chunk k):
+    # same result for every chunk count
+    b = synth.generate(synth.config("cfg2", 0.25))
+    want = oracle_phase(b, os.cpu_count() or 1)
+    monkeypatch.setenv("AHS_CHUNKS", chunks)
+    assert not api.phase_batch(b).diff(want)

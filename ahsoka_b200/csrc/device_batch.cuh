@@ -52,7 +52,7 @@ struct DB {
     int32_t *ce_list, *ce_newrow, *ce_label;              // per-node scratch of k_cluster_big: old weights to a / b, merged weight
     int64_t *ce_rbF, *ce_rbP; int32_t *ce_rbFarg, *ce_rbParg;   //   fresh icf / icp, first / last non-zero column of a row
     uint64_t *key_scratch; int64_t *key_scratch_off;       // overflow buffers for reads with > 256 partners
-    uint8_t *ch_fused;                                    // [C] 1 = chain is scored + clustered out of shared memory (k_chain.cuh)
+    uint8_t *ch_small;                                    // [C] 1 = chain is scored + clustered out of shared memory (k_chain.cuh)
     // ---- consensus / threading
     PosRec *rec; uint16_t *back; int64_t *back_off; int32_t S_max;
     int32_t *path; uint8_t *hap_allele; double *dp_cost;

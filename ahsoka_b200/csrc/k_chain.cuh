@@ -14,7 +14,7 @@
 //
 // k_cluster_chain:
 // Where the state lives
-//   registers  every thread OWNS up to CC_PER read pairs ("slots"): key = (a << 8 | b), a < b, plus
+//   registers  every thread OWNS up to PER (8 or 12) read pairs ("slots"): key = (a << 8 | b), a < b, plus
 //              the pair's induced costs icf / icp (rule R2).  Scans for the best candidate and all
 //              induced-cost updates are register arithmetic by the owner; a slot only ever dies
 //              (merge / forbid) or is relabelled in place ((b,x) becomes (a,x) when b merges into a),

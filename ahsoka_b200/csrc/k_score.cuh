@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) k_read_rates(DB d) {
     int64_t pairs_local = 0;
     for (int64_t f = blockIdx.x * (int64_t)wpb + wib; f < d.NF; f += (int64_t)gridDim.x * wpb) {
         const int c = d.fr_chain[f];
-        if (d.ch_fused[c]) continue;
+        if (d.ch_small[c]) continue;
         const int64_t f0 = d.frow_off[c];
         const int n_c = (int)(d.frow_off[c + 1] - f0), i = (int)(f - f0);
         const int32_t* first = d.fr_first + f0; const int32_t* lastp = d.fr_last + f0;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_pair_scores(DB d) {
     const int wpb = blockDim.x >> 5, lane = lane_id();
     for (int64_t f = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); f < d.NF; f += (int64_t)gridDim.x * wpb) {
         const int c = d.fr_chain[f];
-        if (d.ch_status[c] != AHS_CHAIN_OK || d.ch_fused[c]) continue;
+        if (d.ch_status[c] != AHS_CHAIN_OK || d.ch_small[c]) continue;
         const int64_t f0 = d.frow_off[c];
         const int n_c = (int)(d.frow_off[c + 1] - f0), i = (int)(f - f0);
         const int32_t* first = d.fr_first + f0; const int32_t* lastp = d.fr_last + f0;

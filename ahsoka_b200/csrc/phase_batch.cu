@@ -79,11 +79,11 @@ static Ctx* g_ctx[64] = {nullptr};
 // Cluster editing: a class = (largest n, threads per block, pair slots per thread).  The block size grows with the pair
 // triangle so that every thread owns at most `per` slots (8, or 12 where measured faster: 65-78 reads); the shared-memory footprint (two n x n int32 matrices) is
 // sized by the class's largest n.
-struct FusedClass { int nmax, nt, per; };
-static const FusedClass kFused[] = {{16, 32, 8}, {23, 32, 8}, {28, 64, 8}, {32, 64, 8}, {36, 96, 8}, {39, 96, 8}, {42, 128, 8}, {45, 128, 8},
+struct ClusterClass { int nmax, nt, per; };
+static const ClusterClass kCluster[] = {{16, 32, 8}, {23, 32, 8}, {28, 64, 8}, {32, 64, 8}, {36, 96, 8}, {39, 96, 8}, {42, 128, 8}, {45, 128, 8},
                                     {50, 192, 8}, {55, 192, 8}, {60, 256, 8}, {64, 256, 8}, {71, 256, 12}, {78, 256, 12}, {85, 512, 8}, {91, 512, 8},
                                     {101, 768, 8}, {111, 768, 8}, {120, 1024, 8}, {128, 1024, 8}};
-constexpr int N_FUSED = (int)(sizeof(kFused) / sizeof(kFused[0]));
+constexpr int N_CLUSTER = (int)(sizeof(kCluster) / sizeof(kCluster[0]));
 // Scoring: (largest n, threads per block, sort keys per lane)
 struct ScoreClass { int nmax, nt, kpl; };
 static const ScoreClass kScore[] = {{32, 64, 1}, {48, 128, 2}, {64, 128, 2}, {96, 256, 4}, {128, 256, 4}};
@@ -91,7 +91,7 @@ constexpr int N_SCORE = (int)(sizeof(kScore) / sizeof(kScore[0]));
 
 #define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8) X(256, 12)
 #define AHS_FOR_EACH_SC(X) X(64, 1) X(128, 2) X(256, 4)
-static void fused_set_attributes(size_t optin) {
+static void chain_kernel_attributes(size_t optin) {
 #define X(NT, PER) CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
                    CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     AHS_FOR_EACH_NT(X)
@@ -116,12 +116,12 @@ template <int BITS> static void score_launch(int nt, int kpl, unsigned grid, siz
 static int score_class(int n) { for (int k = 0; k < N_SCORE; k++) if (n <= kScore[k].nmax) return k; return -1; }
 // every class must fit the device (checked once per context)
 static void check_classes(size_t smem_optin) {
-    for (int k = 0; k < N_FUSED; k++) {
-        if (cc_smem_bytes(kFused[k].nmax, kFused[k].nt) > smem_optin) throw LimitFail{"device shared memory too small for the cluster-editing classes"};
-        if ((int64_t)kFused[k].nmax * (kFused[k].nmax - 1) / 2 > (int64_t)kFused[k].per * kFused[k].nt) throw std::logic_error("cluster class table: slots");
-        if (kFused[k].nmax * cc_fresh_g(kFused[k].nt, kFused[k].per) > kFused[k].nt) throw std::logic_error("cluster class table: fresh-cost lanes");
+    for (int k = 0; k < N_CLUSTER; k++) {
+        if (cc_smem_bytes(kCluster[k].nmax, kCluster[k].nt) > smem_optin) throw LimitFail{"device shared memory too small for the cluster-editing classes"};
+        if ((int64_t)kCluster[k].nmax * (kCluster[k].nmax - 1) / 2 > (int64_t)kCluster[k].per * kCluster[k].nt) throw std::logic_error("cluster class table: slots");
+        if (kCluster[k].nmax * cc_fresh_g(kCluster[k].nt, kCluster[k].per) > kCluster[k].nt) throw std::logic_error("cluster class table: fresh-cost lanes");
     }
-    if (kFused[N_FUSED - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
+    if (kCluster[N_CLUSTER - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
     for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax) > smem_optin) throw std::logic_error("score class table");
 }
 
@@ -157,7 +157,7 @@ static Ctx* get_ctx(int device) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     check_classes(c->smem_optin);
     CK(cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-    fused_set_attributes(c->smem_optin);
+    chain_kernel_attributes(c->smem_optin);
     g_ctx[device] = c;
     return c;
 }
@@ -213,7 +213,7 @@ struct Pipeline {
     int32_t *h_status = nullptr, *h_nfinal = nullptr, *h_npos = nullptr;      // pinned: D2H targets of sync #1
     unsigned long long* h_cells = nullptr;
     char *sg_h = nullptr, *sg_d = nullptr; size_t sg_cap = 0;                   // pinned / device staging block of phase 2
-    float ms_fused = 0;
+    float ms_smem_cluster = 0;
     bool early_out = false;                                                     // download the matrix while the clustering runs
     int64_t base_allele = 0, base_anode = 0, base_enode = 0;                    // first elements of the three big offset arrays (chunk views)
     int64_t cell_base = 0;                                                      // cells of the chunks before this one (cell_off is global)
@@ -414,16 +414,16 @@ struct Pipeline {
         int64_t S_max = 1; for (int i = 0; i < in->ploidy; i++) S_max *= 2 * in->ploidy;
         d.S_max = (int32_t)S_max;
         Stage sg; sg.h = sg_h; sg.dv = sg_d;
-        int64_t *dv_frow, *dv_pos, *dv_code, *dv_cw, *dv_back; int32_t *dv_words, *dv_order, *dv_status; uint8_t* dv_fused;
+        int64_t *dv_frow, *dv_pos, *dv_code, *dv_cw, *dv_back; int32_t *dv_words, *dv_order, *dv_status; uint8_t* dv_small;
         int64_t* s_frow = sg.take<int64_t>(C + 1, &dv_frow); int64_t* s_pos = sg.take<int64_t>(C + 1, &dv_pos);
         int64_t* s_code = sg.take<int64_t>(C, &dv_code); int64_t* s_cw = sg.take<int64_t>(C, &dv_cw); int64_t* s_back = sg.take<int64_t>(C, &dv_back);
         int32_t* s_words = sg.take<int32_t>(C, &dv_words); int32_t* s_order = sg.take<int32_t>(C, &dv_order); int32_t* s_status = sg.take<int32_t>(C, &dv_status);
-        uint8_t* s_fused = sg.take<uint8_t>(C, &dv_fused);
+        uint8_t* s_small = sg.take<uint8_t>(C, &dv_small);
         if (sg.used > sg_cap) throw std::runtime_error("staging block overflow");
         n_code_words = 0; n_cw = 0;
         bool status_changed = false;
         s_frow[0] = 0; s_pos[0] = 0;
-        int64_t nf_unfused = 0, cells_ok = 0; int n_max = 0;
+        int64_t nf_big = 0, cells_ok = 0; int n_max = 0;
         for (int64_t c = 0; c < C; c++) {
             if (h_status[c] == AHS_CHAIN_OK && h_nfinal[c] > MAX_READS_CLUSTER) { h_status[c] = AHS_CHAIN_TOO_LARGE; status_changed = true; }
             s_status[c] = h_status[c];
@@ -434,10 +434,10 @@ struct Pipeline {
             s_words[c] = (int32_t)((B + per_word - 1) / per_word);
             s_frow[c + 1] = s_frow[c] + n; s_pos[c + 1] = s_pos[c] + np;
             s_code[c] = n_code_words; n_code_words += n * s_words[c];
-            s_fused[c] = (n > 0 && n <= CC_MAXN) ? 1 : 0;
-            s_cw[c] = n_cw; n_cw += s_fused[c] ? n * (n - 1) / 2 : n * n;
+            s_small[c] = (n > 0 && n <= CC_MAXN) ? 1 : 0;
+            s_cw[c] = n_cw; n_cw += s_small[c] ? n * (n - 1) / 2 : n * n;
             s_back[c] = s_pos[c] * S_max;
-            if (!s_fused[c]) nf_unfused += n;
+            if (!s_small[c]) nf_big += n;
             n_max = std::max<int>(n_max, (int)n);
             if (ok) cells_ok += (int64_t)h_cells[c];
         }
@@ -457,7 +457,7 @@ struct Pipeline {
         d.NF = NF; d.NP = NP;
         CK(cudaMemcpyAsync(sg.dv, sg.h, sg.used, cudaMemcpyHostToDevice, st));
         d.frow_off = dv_frow; d.pos_off = dv_pos; d.code_off = dv_code; d.cw_off = dv_cw; d.back_off = dv_back;
-        d.ch_words = dv_words; d.ch_fused = dv_fused;
+        d.ch_words = dv_words; d.ch_small = dv_small;
         if (status_changed) CK(cudaMemcpyAsync(d.ch_status, dv_status, C * 4, cudaMemcpyDeviceToDevice, st));
         d.fr_chain = dalloc<int32_t>(NF); d.fr_first = dalloc<int32_t>(NF); d.fr_last = dalloc<int32_t>(NF); d.fr_mapq = dalloc<int32_t>(NF);
         d.fr_id = dalloc<int32_t>(NF); d.fr_nv = dalloc<int32_t>(NF); d.fr_cluster = dzero<int32_t>(NF);
@@ -465,9 +465,9 @@ struct Pipeline {
         d.pos = dalloc<int32_t>(NP); d.pos_chain = dalloc<int32_t>(NP);
         d.es = dalloc<uint16_t>(NF); d.ed = dalloc<uint16_t>(NF);
         d.W = dalloc<int32_t>(n_cw);
-        if (nf_unfused) {
+        if (nf_big) {
             // HBM-resident path (chains above CC_MAXN reads): dense n x n workspaces
-            for (int64_t c = 0; c < C; c++) if (!s_fused[c] && h_nfinal[c] > 0)
+            for (int64_t c = 0; c < C; c++) if (!s_small[c] && h_nfinal[c] > 0)
                 CK(cudaMemsetAsync(d.W + s_cw[c], 0, (size_t)h_nfinal[c] * h_nfinal[c] * 4, st));
             d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw); d.big_key = dalloc<uint32_t>(n_cw);
             d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
@@ -476,16 +476,16 @@ struct Pipeline {
         d.rec = dalloc<PosRec>(NP); d.back = dalloc<uint16_t>(NP * S_max);
         d.path = dzero<int32_t>(NP * in->ploidy); d.hap_allele = dzero<uint8_t>(NP * in->ploidy); d.dp_cost = dzero<double>(C);
         d.cell_off = dalloc<int64_t>(NF + 1); d.cell_pos = dalloc<int32_t>(h_tot_cells); d.cell_allele = dalloc<uint8_t>(h_tot_cells);
-        int32_t* counters = dzero<int32_t>(8 + N_SCORE + N_FUSED);
+        int32_t* counters = dzero<int32_t>(8 + N_SCORE + N_CLUSTER);
         d.key_scratch = nullptr; d.key_scratch_off = nullptr;
-        if (nf_unfused) {
+        if (nf_big) {
             // reads of HBM-path chains with more than RATE_SMEM_KEYS candidate partners sort in HBM scratch
             std::vector<int64_t> koff(NF + 1, 0);
             int64_t tot = 0; bool any = false;
             for (int64_t c = 0; c < C; c++) {
                 const int64_t n = h_nfinal[c];
                 int64_t cap = 0;
-                if (n > RATE_SMEM_KEYS && !s_fused[c]) { cap = 1; while (cap < n) cap <<= 1; any = true; }
+                if (n > RATE_SMEM_KEYS && !s_small[c]) { cap = 1; while (cap < n) cap <<= 1; any = true; }
                 for (int64_t i = 0; i < n; i++) { koff[s_frow[c] + i] = tot; tot += cap; }
             }
             koff[NF] = tot;
@@ -502,8 +502,8 @@ struct Pipeline {
         if (early_out) CK(cudaEventRecord(ln->ev_cells, st));          // the matrix part of the result is final: see copy_matrix()
         CK(cudaEventRecord(ln->ev[2], st));
         // ---- scoring
-        if (nf_unfused) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
-        if (nf_unfused) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
+        if (nf_big) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
+        if (nf_big) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         // chains up to CC_MAXN reads: scoring out of shared memory, 4 B per pair to HBM (every chain of BASELINE config 2)
         for (int k = N_SCORE - 1; k >= 0; k--) {
             int first, len; range_of(k ? kScore[k - 1].nmax + 1 : 1, kScore[k].nmax, first, len);
@@ -520,20 +520,20 @@ struct Pipeline {
         // the size classes run on four side streams so that the tail of one class overlaps the bulk of the next
         CK(cudaEventRecord(ln->ev_fork, st));
         for (auto& t : cx->side) CK(cudaStreamWaitEvent(t, ln->ev_fork, 0));
-        for (int k = N_FUSED - 1, q = 0; k >= 0; k--) {
-            int first, len; range_of(k ? kFused[k - 1].nmax + 1 : 1, kFused[k].nmax, first, len);
+        for (int k = N_CLUSTER - 1, q = 0; k >= 0; k--) {
+            int first, len; range_of(k ? kCluster[k - 1].nmax + 1 : 1, kCluster[k].nmax, first, len);
             if (!len) continue;
-            const int nt = kFused[k].nt;
-            const size_t smem = cc_smem_bytes(kFused[k].nmax, nt);
-            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kFused[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
+            const int nt = kCluster[k].nt;
+            const size_t smem = cc_smem_bytes(kCluster[k].nmax, nt);
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(cc_min_blocks(nt, kCluster[k].per), 2048 / nt), (228 * 1024) / (smem + 1024)));
             const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-            int32_t* scratch = dalloc<int32_t>((int64_t)grid * nt * kFused[k].per * 3);     // slot-packing areas, one per warp
-            cluster_launch(nt, kFused[k].per, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kFused[k].nmax, counters + 8 + N_SCORE + k, scratch); n_launches += 1;
+            int32_t* scratch = dalloc<int32_t>((int64_t)grid * nt * kCluster[k].per * 3);     // slot-packing areas, one per warp
+            cluster_launch(nt, kCluster[k].per, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kCluster[k].nmax, counters + 8 + N_SCORE + k, scratch); n_launches += 1;
         }
         for (int i = 0; i < 8; i++) { CK(cudaEventRecord(ln->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, ln->ev_join[i], 0)); }
         CK(cudaEventRecord(ln->ev[11], st));
         // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one 1024-thread block per chain
-        if (nf_unfused) {
+        if (nf_big) {
             int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
             if (len) {
                 const int nbig = std::min<int>(n_max, 8191);
@@ -564,7 +564,7 @@ struct Pipeline {
         CK(cudaEventElapsedTime(&t, ln->ev[1], ln->ev[2])); ms[1] = t;
         CK(cudaEventElapsedTime(&t, ln->ev[2], ln->ev[3])); ms[2] = t;
         CK(cudaEventElapsedTime(&t, ln->ev[3], ln->ev[4])); ms[3] = t;
-        CK(cudaEventElapsedTime(&t, ln->ev[10], ln->ev[11])); ms_fused = t; ms[7] = t;      // shared-memory cluster editing alone
+        CK(cudaEventElapsedTime(&t, ln->ev[10], ln->ev[11])); ms_smem_cluster = t; ms[7] = t;      // shared-memory cluster editing alone
         CK(cudaEventElapsedTime(&t, ln->ev[4], ln->ev[5])); ms[4] = t;
         CK(cudaEventElapsedTime(&t, ln->ev[5], ln->ev[6])); ms[5] = t;
         CK(cudaEventElapsedTime(&t, ln->ev[0], ln->ev[7])); ms[6] = t;

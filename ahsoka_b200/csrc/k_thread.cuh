@@ -23,6 +23,7 @@ namespace ahs {
 
 constexpr int K3_CAP = 128;      // clusters per position held in shared memory (k_consensus)
 constexpr int K3C_CAP = 16;      // clusters per chain handled by the warp-per-chain kernel (k_consensus_chain)
+constexpr int K3C_READS = 128;   // ... and final reads per chain (a lane walks all of them; longer chains go position-parallel)
 
 template <int BITS, int G>
 __global__ void __launch_bounds__(128) k_consensus(DB d) {
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
     const int p = d.ploidy;
     for (int64_t gp = blockIdx.x * (int64_t)NG + wib; gp < d.NP; gp += (int64_t)gridDim.x * NG) {
         const int c = d.pos_chain[gp];
-        if (BITS == 2 && d.ch_nclusters[c] <= K3C_CAP) continue;      // done by k_consensus_chain
+        if (BITS == 2 && d.ch_nclusters[c] <= K3C_CAP && d.frow_off[c + 1] - d.frow_off[c] <= K3C_READS) continue;      // done by k_consensus_chain
         const int b = d.pos[gp];
         const int64_t f0 = d.frow_off[c];
         const int n_c = (int)(d.frow_off[c + 1] - f0);
@@ -110,9 +111,9 @@ __global__ void __launch_bounds__(128) k_consensus_chain(DB d) {
     for (int c = blockIdx.x * 4 + wib; c < d.C; c += gridDim.x * 4) {
         if (d.ch_status[c] != AHS_CHAIN_OK) continue;
         const int ncl = d.ch_nclusters[c];
-        if (ncl > K3C_CAP) continue;                                   // k_consensus takes this chain
         const int64_t f0 = d.frow_off[c], p0 = d.pos_off[c];
         const int n_c = (int)(d.frow_off[c + 1] - f0), n_pos = (int)(d.pos_off[c + 1] - p0);
+        if (ncl > K3C_CAP || n_c > K3C_READS) continue;                // k_consensus takes this chain
         const int32_t* first = d.fr_first + f0; const int32_t* lastp = d.fr_last + f0; const int32_t* cl = d.fr_cluster + f0;
         const int words = d.ch_words[c];
         const uint32_t* rows = d.codes + d.code_off[c];

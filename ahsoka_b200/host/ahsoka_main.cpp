@@ -1,11 +1,18 @@
 // ahsoka_main.cpp — `Ahsoka phase` / `Ahsoka only-bubbles` with the phasing step behind the
 // C ABI.  Same options, same files, same stdout banners as reference src/polyassembly.cpp:22-176;
 // the reference's own translation units (graph.cpp, alignmentreader.cpp, argumentparser.cpp,
-// chainstoreadset.cpp) are linked unchanged for parsing, bubble/chain detection and allele-path
-// enumeration, exactly as BASELINE.json's north_star prescribes.  `-t N` with N > 1 runs the
+// chainstoreadset.cpp) are linked unchanged for GFA parsing and bubble/chain detection, exactly as
+// BASELINE.json's north_star prescribes.  The two stages either side of the phasing call that cannot
+// ingest a BASELINE-sized input (the GAF reader, O(L²) strings per line, and the
+// O(B²) allele-path enumeration) run through this repo's result-identical replacements
+// (gaf_reader.cpp, chain_alleles.cpp); AHSOKA_HOST=reference selects the reference's own functions
+// instead, which is how tests/test_host_parity.py compares the two.  `-t N` with N > 1 runs the
 // same single batch call (the reference's two-thread experiment, polyassembly.cpp:190-222,
 // only ever processed the ten largest chains and is not a parity target).
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <functional>
 #include <iostream>
@@ -18,12 +25,27 @@
 #include "alignmentreader.hpp"
 #include "argumentparser.hpp"
 #include "graph.hpp"
+#include "gaf_reader.hpp"
 
 using std::cerr; using std::cout; using std::endl; using std::string;
 typedef std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>> ChainAlleles;
 
 ChainAlleles ChainsToReadsetDetailed(Graph graph);     // reference src/chainstoreadset.cpp:161
 void alignmentsToReadset(AlignmentReader&, Graph&, ChainAlleles&, string, bool, std::vector<std::pair<int, int>>&, std::mutex&);
+void alignmentsToReadset(const ahs_host::GafStore&, Graph&, ChainAlleles&, string, bool, std::vector<std::pair<int, int>>&, std::mutex&);
+namespace ahs_host { ChainAlleles chain_alleles(const Graph& graph); }
+
+namespace {
+struct StageTimer {     // AHSOKA_TIMING=1: "timing: <stage> <ms>" on stderr
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char* name;
+    explicit StageTimer(const char* n) : name(n) {}
+    ~StageTimer() {
+        if (!getenv("AHSOKA_TIMING")) return;
+        cerr << "timing: " << name << " " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() << endl;
+    }
+};
+}
 
 int main(int argc, char* argv[]) {
     cerr << "Ahsoka: Haplotype assembly for diploid and polyploid genomes based on HiFi and ultra-long ONT data" << endl;
@@ -54,11 +76,14 @@ int main(int argc, char* argv[]) {
     const string alignmentfile = argparser.get_arg_parameter('a');
     const string prefix = argparser.get_arg_parameter('o');
     const int threads = std::stoi(argparser.get_arg_parameter('t'));
-    Graph graph = Graph::ReadGraph(gfafile);
+    const char* host_env = getenv("AHSOKA_HOST");
+    const bool ref_host = host_env && !strcmp(host_env, "reference");
+    Graph graph;
+    { StageTimer t("read_graph"); graph = Graph::ReadGraph(gfafile); }
     cout << "number of threads used: " << threads << endl;
     cout << "threads available: " << std::thread::hardware_concurrency() << endl;
     cout << "Step 1: Graph with " << graph.nodes.size() << " nodes read" << endl;
-    graph.findBubbles();
+    { StageTimer t("find_bubbles"); graph.findBubbles(); }
     cout << "Step 2: Bubbles read" << endl;
     cout << "Number of bubble chains: " << graph.chains.size() << endl;
     {
@@ -75,10 +100,26 @@ int main(int argc, char* argv[]) {
     if (cmd == "only-bubbles") return 0;
 
     AlignmentReader alignmentreader;
-    alignmentreader.readAlignmentfile(alignmentfile, graph);
+    ahs_host::GafStore store;
+    int64_t n_alignment_chains;
+    {
+        StageTimer t("read_alignments");
+        if (ref_host) {
+            alignmentreader.readAlignmentfile(alignmentfile, graph);
+            n_alignment_chains = (int64_t)alignmentreader.alignments.size();
+        } else {
+            string err;
+            if (ahs_host::read_gaf(alignmentfile, graph, store, err, threads > 1 ? threads : 0)) {
+                cerr << "ahsoka_b200: " << err << endl;      // the reference aborts on the same line (assert / uncaught exception)
+                return 65;
+            }
+            n_alignment_chains = (int64_t)store.by_chain.size();
+        }
+    }
     cout << "Step 3: Alignments read" << endl;
-    cout << "Number of alignments: " << alignmentreader.alignments.size() << endl;
-    ChainAlleles chainpathToAlleles = ChainsToReadsetDetailed(graph);
+    cout << "Number of alignments: " << n_alignment_chains << endl;
+    ChainAlleles chainpathToAlleles;
+    { StageTimer t("chain_alleles"); chainpathToAlleles = ref_host ? ChainsToReadsetDetailed(graph) : ahs_host::chain_alleles(graph); }
     cout << "Step 4: Chain paths computed " << endl;
     cout << "Number of chain paths: " << chainpathToAlleles.size() << endl;
     std::vector<std::pair<int, int>> size_sorting;
@@ -88,6 +129,7 @@ int main(int argc, char* argv[]) {
     cout << "single thread" << endl;
     cout << "size sorting: " << size_sorting.size() << endl;
     std::mutex g_display_mutex;
-    alignmentsToReadset(alignmentreader, graph, chainpathToAlleles, prefix, false, size_sorting, g_display_mutex);
+    if (ref_host) alignmentsToReadset(alignmentreader, graph, chainpathToAlleles, prefix, false, size_sorting, g_display_mutex);
+    else alignmentsToReadset(store, graph, chainpathToAlleles, prefix, false, size_sorting, g_display_mutex);
     return 0;
 }

@@ -14,6 +14,7 @@
 // Not reproduced: ./logfile.log and the -readset*.txt debugging dumps (third-party
 // ReadSet::toString() text), see INTEGRATION.md.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -27,8 +28,22 @@
 #include "alignmentreader.hpp"   // reference header, found through -I<reference>/src
 #include "graph.hpp"             // reference header
 #include "ahsoka_b200.h"
+#include "gaf_reader.hpp"
 
 namespace ahs_host {
+
+typedef std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>> ChainAlleles;
+
+// AHSOKA_TIMING=1: one "timing: <stage> <ms>" line per host stage on stderr
+struct StageTimer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char* name;
+    explicit StageTimer(const char* n) : name(n) {}
+    ~StageTimer() {
+        if (!getenv("AHSOKA_TIMING")) return;
+        std::cerr << "timing: " << name << " " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() << std::endl;
+    }
+};
 
 struct FlatBatch {
     std::vector<int32_t> chain_id, anode, stage_a_order, enode, entry_read;
@@ -42,29 +57,45 @@ static bool same_entry(AlignmentPath& a, AlignmentPath& b) {
     return a.name == b.name && a.id == b.id && a.startpos == b.startpos && a.endpos == b.endpos && a.nodes == b.nodes;
 }
 
-// SURVEY §8b / f1: the containers of reference src/alignmentreader.hpp:38 and
+// Alleles of one chain (reference src/polyassembly.cpp:126-140 containers), appended CSR; returns the
+// number of bubbles B the phasing sees (0 for chains of ≤1 bubble, alignmentstoreadset.cpp:86).
+static int flatten_chain_alleles(ChainAlleles& pathToAlleles, int chainid, FlatBatch& fb) {
+    // same copy the reference takes (alignmentstoreadset.cpp:76): its iteration order is stage A's
+    auto chainmap = std::make_pair(chainid, pathToAlleles[chainid]);
+    fb.chain_id.push_back(chainid);
+    int B = 0;
+    if (chainmap.second.size() > 1) for (auto& kv : chainmap.second) B = std::max(B, kv.first + 1);
+    std::vector<char> seen(B, 0);
+    for (auto& kv : chainmap.second) if (kv.first >= 0 && kv.first < B) { fb.stage_a_order.push_back(kv.first); seen[kv.first] = 1; }
+    for (int b = 0; b < B; b++) if (!seen[b]) fb.stage_a_order.push_back(b);
+    for (int b = 0; b < B; b++) {
+        auto it = chainmap.second.find(b);
+        if (it != chainmap.second.end()) for (auto& path : it->second) {
+            fb.anode.insert(fb.anode.end(), path.begin(), path.end());
+            fb.anode_off.push_back((int64_t)fb.anode.size());
+        }
+        fb.allele_off.push_back((int64_t)fb.anode_off.size() - 1);
+    }
+    fb.bubble_off.push_back((int64_t)fb.allele_off.size() - 1);
+    return B;
+}
+
+static void finish_view(FlatBatch& fb, int ploidy) {
+    ahs_batch_in& v = fb.view;
+    v.n_chains = (int32_t)fb.chain_id.size(); v.ploidy = ploidy; v.chain_id = fb.chain_id.data();
+    v.bubble_off = fb.bubble_off.data(); v.allele_off = fb.allele_off.data(); v.anode_off = fb.anode_off.data();
+    v.anode = fb.anode.data(); v.stage_a_order = fb.stage_a_order.data(); v.read_off = fb.read_off.data();
+    v.entry_off = fb.entry_off.data(); v.enode_off = fb.enode_off.data(); v.enode = fb.enode.data();
+    v.entry_read = fb.entry_read.data(); v.entry_identity = fb.entry_identity.data();
+}
+
+// SURVEY §8b: the containers of reference src/alignmentreader.hpp:38 and
 // src/polyassembly.cpp:126-140, flattened CSR-by-chain in size_sorting order.
-void flatten(AlignmentReader& reader, std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
+void flatten(AlignmentReader& reader, ChainAlleles& pathToAlleles,
              std::vector<std::pair<int, int>>& size_sorting, int ploidy, FlatBatch& fb) {
     for (auto& size : size_sorting) {
         const int chainid = size.second;
-        // same copy the reference takes (alignmentstoreadset.cpp:76): its iteration order is stage A's
-        auto chainmap = std::make_pair(chainid, pathToAlleles[chainid]);
-        fb.chain_id.push_back(chainid);
-        int B = 0;
-        if (chainmap.second.size() > 1) for (auto& kv : chainmap.second) B = std::max(B, kv.first + 1);
-        std::vector<char> seen(B, 0);
-        for (auto& kv : chainmap.second) if (kv.first >= 0 && kv.first < B) { fb.stage_a_order.push_back(kv.first); seen[kv.first] = 1; }
-        for (int b = 0; b < B; b++) if (!seen[b]) fb.stage_a_order.push_back(b);
-        for (int b = 0; b < B; b++) {
-            auto it = chainmap.second.find(b);
-            if (it != chainmap.second.end()) for (auto& path : it->second) {
-                fb.anode.insert(fb.anode.end(), path.begin(), path.end());
-                fb.anode_off.push_back((int64_t)fb.anode.size());
-            }
-            fb.allele_off.push_back((int64_t)fb.anode_off.size() - 1);
-        }
-        fb.bubble_off.push_back((int64_t)fb.allele_off.size() - 1);
+        const int B = flatten_chain_alleles(pathToAlleles, chainid, fb);
         fb.read_names.emplace_back();
         std::vector<std::string>& names = fb.read_names.back();
         if (B > 1) {
@@ -87,12 +118,38 @@ void flatten(AlignmentReader& reader, std::unordered_map<int, std::unordered_map
         fb.read_off.push_back(fb.read_off.back() + (int64_t)names.size());
         fb.entry_off.push_back((int64_t)fb.entry_read.size());
     }
-    ahs_batch_in& v = fb.view;
-    v.n_chains = (int32_t)fb.chain_id.size(); v.ploidy = ploidy; v.chain_id = fb.chain_id.data();
-    v.bubble_off = fb.bubble_off.data(); v.allele_off = fb.allele_off.data(); v.anode_off = fb.anode_off.data();
-    v.anode = fb.anode.data(); v.stage_a_order = fb.stage_a_order.data(); v.read_off = fb.read_off.data();
-    v.entry_off = fb.entry_off.data(); v.enode_off = fb.enode_off.data(); v.enode = fb.enode.data();
-    v.entry_read = fb.entry_read.data(); v.entry_identity = fb.entry_identity.data();
+    finish_view(fb, ploidy);
+}
+
+// the same batch from the native reader's store (gaf_reader.hpp) — no strings are
+// parsed or copied here, the per-chain read index is the first-appearance order of the name ids.
+void flatten_store(const GafStore& st, ChainAlleles& pathToAlleles,
+                   std::vector<std::pair<int, int>>& size_sorting, int ploidy, FlatBatch& fb) {
+    std::vector<int32_t> stamp(st.names.size(), -1), local(st.names.size(), 0);
+    int32_t c = 0;
+    for (auto& size : size_sorting) {
+        const int chainid = size.second;
+        const int B = flatten_chain_alleles(pathToAlleles, chainid, fb);
+        fb.read_names.emplace_back();
+        std::vector<std::string>& names = fb.read_names.back();
+        if (B > 1) {
+            auto it = st.by_chain.find(chainid);
+            if (it != st.by_chain.end()) {
+                for (int32_t line : it->second) {
+                    const int32_t g = st.name_id[line];
+                    if (stamp[g] != c) { stamp[g] = c; local[g] = (int32_t)names.size(); names.push_back(st.names[g]); }
+                    fb.enode.insert(fb.enode.end(), st.node_raw.begin() + st.node_off[line], st.node_raw.begin() + st.node_off[line + 1]);
+                    fb.enode_off.push_back((int64_t)fb.enode.size());
+                    fb.entry_read.push_back(local[g]);
+                    fb.entry_identity.push_back(st.identity[line]);
+                }
+            }
+        }
+        fb.read_off.push_back(fb.read_off.back() + (int64_t)names.size());
+        fb.entry_off.push_back((int64_t)fb.entry_read.size());
+        c++;
+    }
+    finish_view(fb, ploidy);
 }
 
 // Emission, semantics of reference src/alignmentstoreadset.cpp:70-83 and :411-486.
@@ -122,10 +179,17 @@ void emit(const ahs_batch_out& out, Graph& graph,
                 for (size_t ind = 0; ind + 1 < ap.size(); ind++) {
                     const int single = ap[ind], next = ap[ind + 1];
                     if (usednodes.count(single)) continue;
-                    Node first = graph.nodes.find(single)->second;       // Graph::getNode without the linear scan (f2)
-                    Node sec = graph.nodes.find(next)->second;
-                    std::pair<DirectedNode, DirectedNode> tup = graph.getEdge(first, sec);
-                    const char dir = tup.first.end == 1 ? '+' : '-';
+                    // Graph::getNode + Graph::getEdge (graph.cpp:502-512, 251-261) without the scan over all
+                    // nodes and without copying node sequences (f2): first of (single,+), (single,-) with an edge to next
+                    bool end = false;
+                    for (bool val : {true, false}) {
+                        auto eit = graph.edges.find(DirectedNode(single, val));
+                        if (eit == graph.edges.end()) continue;
+                        bool hit = false;
+                        for (auto& to : eit->second) if (to.id == next) { hit = true; break; }
+                        if (hit) { end = val; break; }
+                    }
+                    const char dir = end ? '+' : '-';
                     resfile << single << '(' << dir << ')' << ",";
                     full_output << single << '(' << dir << ')' << ",";
                     usednodes.insert(single);
@@ -146,40 +210,80 @@ void emit(const ahs_batch_out& out, Graph& graph,
 
 }  // namespace ahs_host
 
+namespace ahs_host {
+
+static void dump_batch(const FlatBatch& fb, int ploidy, const char* dump) {
+    // raw little-endian dump of the flattened batch, for the Python tests
+    FILE* f = fopen(dump, "wb");
+    if (!f) return;
+    auto w64 = [&](int64_t v) { fwrite(&v, 8, 1, f); };
+    auto wv = [&](const void* p, size_t bytes) { fwrite(p, 1, bytes, f); };
+    w64(fb.view.n_chains); w64(ploidy); w64(fb.bubble_off.back()); w64((int64_t)fb.anode_off.size() - 1); w64((int64_t)fb.anode.size());
+    w64((int64_t)fb.entry_read.size()); w64((int64_t)fb.enode.size());
+    wv(fb.chain_id.data(), 4 * fb.chain_id.size()); wv(fb.bubble_off.data(), 8 * fb.bubble_off.size());
+    wv(fb.allele_off.data(), 8 * fb.allele_off.size()); wv(fb.anode_off.data(), 8 * fb.anode_off.size());
+    wv(fb.anode.data(), 4 * fb.anode.size()); wv(fb.stage_a_order.data(), 4 * fb.stage_a_order.size());
+    wv(fb.read_off.data(), 8 * fb.read_off.size()); wv(fb.entry_off.data(), 8 * fb.entry_off.size());
+    wv(fb.enode_off.data(), 8 * fb.enode_off.size()); wv(fb.enode.data(), 4 * fb.enode.size());
+    wv(fb.entry_read.data(), 4 * fb.entry_read.size()); wv(fb.entry_identity.data(), 4 * fb.entry_identity.size());
+    fclose(f);
+}
+
+static int ploidy_from_env() {
+    const char* pl = getenv("AHSOKA_PLOIDY");                 // reference: hard-coded 2 (:306)
+    return pl ? atoi(pl) : 2;
+}
+
+static void phase_and_emit(FlatBatch& fb, int ploidy, Graph& graph, ChainAlleles& pathToAlleles, const std::string& prefix,
+                           std::vector<std::pair<int, int>>& size_sorting) {
+    if (const char* dump = getenv("AHSOKA_DUMP_BATCH")) dump_batch(fb, ploidy, dump);
+    ahs_batch_out out;
+    const char* dv = getenv("AHSOKA_DEVICE");
+    int rc;
+    {
+        StageTimer t("phase_batch");
+        rc = ahs_phase_batch(&fb.view, &out, dv ? atoi(dv) : 0);
+    }
+    if (rc != AHS_OK) {
+        std::cerr << "ahsoka_b200: phasing failed (" << rc << "): " << ahs_last_error() << std::endl;
+        exit(70);                                             // fail loudly: no CPU path behind the ABI
+    }
+    {
+        StageTimer t("emit");
+        emit(out, graph, pathToAlleles, size_sorting, prefix);
+    }
+    ahs_free_out(&out);
+}
+
+}  // namespace ahs_host
+
 void alignmentsToReadset(AlignmentReader& alignmentreader, Graph& graph,
                          std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
                          std::string readsetfile, bool shell_logging, std::vector<std::pair<int, int>>& size_sorting,
                          std::mutex& g_display_mutex) {
     std::lock_guard<std::mutex> guard(g_display_mutex);
     (void)shell_logging;
-    const char* pl = getenv("AHSOKA_PLOIDY");                 // reference: hard-coded 2 (:306)
-    const int ploidy = pl ? atoi(pl) : 2;
+    const int ploidy = ahs_host::ploidy_from_env();
     ahs_host::FlatBatch fb;
-    ahs_host::flatten(alignmentreader, pathToAlleles, size_sorting, ploidy, fb);
-    if (const char* dump = getenv("AHSOKA_DUMP_BATCH")) {
-        // raw little-endian dump of the flattened batch, for the Python tests
-        FILE* f = fopen(dump, "wb");
-        if (f) {
-            auto w64 = [&](int64_t v) { fwrite(&v, 8, 1, f); };
-            auto wv = [&](const void* p, size_t bytes) { fwrite(p, 1, bytes, f); };
-            w64(fb.view.n_chains); w64(ploidy); w64(fb.bubble_off.back()); w64((int64_t)fb.anode_off.size() - 1); w64((int64_t)fb.anode.size());
-            w64((int64_t)fb.entry_read.size()); w64((int64_t)fb.enode.size());
-            wv(fb.chain_id.data(), 4 * fb.chain_id.size()); wv(fb.bubble_off.data(), 8 * fb.bubble_off.size());
-            wv(fb.allele_off.data(), 8 * fb.allele_off.size()); wv(fb.anode_off.data(), 8 * fb.anode_off.size());
-            wv(fb.anode.data(), 4 * fb.anode.size()); wv(fb.stage_a_order.data(), 4 * fb.stage_a_order.size());
-            wv(fb.read_off.data(), 8 * fb.read_off.size()); wv(fb.entry_off.data(), 8 * fb.entry_off.size());
-            wv(fb.enode_off.data(), 8 * fb.enode_off.size()); wv(fb.enode.data(), 4 * fb.enode.size());
-            wv(fb.entry_read.data(), 4 * fb.entry_read.size()); wv(fb.entry_identity.data(), 4 * fb.entry_identity.size());
-            fclose(f);
-        }
+    {
+        ahs_host::StageTimer t("flatten");
+        ahs_host::flatten(alignmentreader, pathToAlleles, size_sorting, ploidy, fb);
     }
-    ahs_batch_out out;
-    const char* dv = getenv("AHSOKA_DEVICE");
-    int rc = ahs_phase_batch(&fb.view, &out, dv ? atoi(dv) : 0);
-    if (rc != AHS_OK) {
-        std::cerr << "ahsoka_b200: phasing failed (" << rc << "): " << ahs_last_error() << std::endl;
-        exit(70);                                             // fail loudly: no CPU path behind the ABI
+    ahs_host::phase_and_emit(fb, ploidy, graph, pathToAlleles, readsetfile, size_sorting);
+}
+
+// Same call for a host that reads its alignments with ahs_host::read_gaf.
+void alignmentsToReadset(const ahs_host::GafStore& store, Graph& graph,
+                         std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
+                         std::string readsetfile, bool shell_logging, std::vector<std::pair<int, int>>& size_sorting,
+                         std::mutex& g_display_mutex) {
+    std::lock_guard<std::mutex> guard(g_display_mutex);
+    (void)shell_logging;
+    const int ploidy = ahs_host::ploidy_from_env();
+    ahs_host::FlatBatch fb;
+    {
+        ahs_host::StageTimer t("flatten");
+        ahs_host::flatten_store(store, pathToAlleles, size_sorting, ploidy, fb);
     }
-    ahs_host::emit(out, graph, pathToAlleles, size_sorting, readsetfile);
-    ahs_free_out(&out);
+    ahs_host::phase_and_emit(fb, ploidy, graph, pathToAlleles, readsetfile, size_sorting);
 }

@@ -1,0 +1,209 @@
+"""Host rows either side of the phasing call: the native GAF reader
+(ahsoka_b200/host/gaf_reader.cpp) and allele-path enumeration (chain_alleles.cpp) against the
+reference's own functions.
+
+oracle/_ref/Ahsoka_flat_oracle links BOTH: the reference translation units alignmentreader.cpp /
+chainstoreadset.cpp compiled where they lie, and this repo's replacements; AHSOKA_HOST=reference
+selects the former.  Everything observable must be byte-identical between the two: the flattened
+batch handed to ahs_phase_batch (AHSOKA_DUMP_BATCH), the <gaf stem>-alignment_identities.txt side
+file, -result.txt, -bubbleinfo.txt and stdout.  Nothing here reads /root/reference at run time.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+EXE = os.path.join(ROOT, "oracle", "_ref", "Ahsoka_flat_oracle")
+CASES = [c for c in json.load(open(os.path.join(GOLDEN, "index.json")))["cases"] if "ref_result" in c]
+
+pytestmark = pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/Ahsoka_flat_oracle not built (needs /root/reference at build time)")
+
+
+def _run(td, tag, gfa_text, gaf_bytes, host, ploidy=2, expect_ok=True):
+    d = os.path.join(td, tag)
+    os.makedirs(d)
+    open(os.path.join(d, "g.gfa"), "w").write(gfa_text)
+    open(os.path.join(d, "reads.gaf"), "wb").write(gaf_bytes)
+    env = dict(os.environ, AHSOKA_DUMP_BATCH=os.path.join(d, "batch.bin"), AHSOKA_PLOIDY=str(ploidy))
+    if host == "reference":
+        env["AHSOKA_HOST"] = "reference"
+    else:
+        env.pop("AHSOKA_HOST", None)
+    r = subprocess.run([EXE, "phase", "-g", "g.gfa", "-a", "reads.gaf", "-o", "out", "-t", "1"], cwd=d,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=env)
+    if not expect_ok:
+        return r
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = {"stdout": r.stdout}
+    for f in ("batch.bin", "reads-alignment_identities.txt", "out-result.txt", "out-bubbleinfo.txt"):
+        out[f] = open(os.path.join(d, f), "rb").read()
+    return out
+
+
+def _both(gfa_text, gaf_bytes, ploidy=2):
+    with tempfile.TemporaryDirectory() as td:
+        ref = _run(td, "ref", gfa_text, gaf_bytes, "reference", ploidy)
+        nat = _run(td, "nat", gfa_text, gaf_bytes, "native", ploidy)
+    for k in ref:
+        assert ref[k] == nat[k], "native host differs from the reference's functions in " + k
+    return nat
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_native_host_matches_reference_functions_on_golden_inputs(case):
+    gfa = open(os.path.join(GOLDEN, case["gfa"])).read()
+    gaf = open(os.path.join(GOLDEN, case["gaf"]), "rb").read()
+    out = _both(gfa, gaf)
+    # ... and the result is still the reference-verbatim binary's
+    assert out["out-result.txt"] == open(os.path.join(GOLDEN, case["ref_result"]), "rb").read()
+
+
+def test_identities_side_file_matches_reference_verbatim_binary():
+    # tests/golden/dip_a-alignment_identities.txt was written by oracle/_ref/Ahsoka_ref (reference reader, verbatim)
+    case = next(c for c in CASES if c["name"] == "dip_a")
+    out = _both(open(os.path.join(GOLDEN, case["gfa"])).read(), open(os.path.join(GOLDEN, case["gaf"]), "rb").read())
+    assert out["reads-alignment_identities.txt"] == open(os.path.join(GOLDEN, "dip_a-alignment_identities.txt"), "rb").read()
+
+
+def _quirky_gaf(lines):
+    """Every tolerated irregularity of reference src/alignmentreader.cpp:78-183 in one file."""
+    out = []
+    n = len(lines)
+    for i, l in enumerate(lines):
+        f = l.split(b"\t")
+        if i % 11 == 0:
+            out.append(b"")                                             # blank line (:84)
+        if i % 7 == 1:
+            l = b" ".join(f)                                            # any whitespace separates fields
+        elif i % 7 == 2:
+            l = l + b"\textra:Z:field"                                  # tokens after the 16th are never read
+        elif i % 7 == 3:
+            f[15] = b"id:f:x:" + f[15].split(b":")[-1]                  # value = text after the LAST ':' (:120-134)
+            l = b"\t".join(f)
+        elif i % 7 == 4:
+            l = l + b"\r"                                               # CRLF: '\r' is whitespace to operator>>
+        elif i % 7 == 5:
+            f[5] = f[5].replace(b">", b">>", 1).replace(b"<", b"<<", 1)  # doubled direction characters (:143-149)
+            l = b"\t".join(f)
+        out.append(l)
+        if i % 13 == 0:
+            out.append(l)                                               # identical adjacent line
+        if i % 17 == 0:
+            out.append(lines[(i * 5 + 3) % n])                          # an earlier/later line repeated out of place
+        if i % 19 == 0:
+            g = list(f)
+            g[5] = g[5] + b">utg9999999l"                               # node that is not in the graph → chain 0 (:180)
+            out.append(b"\t".join(g))
+        if i % 23 == 0:
+            g = list(f)
+            g[5] = g[5].replace(b"utg00", b"u", 1)                      # other spelling, same raw id (:48-54)
+            out.append(b"\t".join(g))
+        if i % 29 == 0:
+            g = list(f)
+            g[15] = b"id:f:9.3e-1"
+            g[7] = b"+12junk"                                           # stoi stops at the first non-digit
+            out.append(b"\t".join(g))
+    body = b"\n".join(out) + b"\n"
+    return body + lines[0]                                              # unterminated last line is dropped (:82)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_native_reader_reproduces_reader_quirks(case):
+    gfa = open(os.path.join(GOLDEN, case["gfa"])).read()
+    lines = open(os.path.join(GOLDEN, case["gaf"]), "rb").read().split(b"\n")
+    lines = [l for l in lines if l]
+    _both(gfa, _quirky_gaf(lines))
+
+
+def test_unterminated_last_line_is_dropped():
+    case = CASES[0]
+    gfa = open(os.path.join(GOLDEN, case["gfa"])).read()
+    gaf = open(os.path.join(GOLDEN, case["gaf"]), "rb").read()
+    assert gaf.endswith(b"\n")
+    a = _both(gfa, gaf)
+    b = _both(gfa, gaf[:-1])
+    assert a["reads-alignment_identities.txt"].count(b"\n") == b["reads-alignment_identities.txt"].count(b"\n") + 1
+    with tempfile.TemporaryDirectory() as td:      # empty and missing-newline-only files: no alignments, header-only result
+        e = _run(td, "empty", gfa, b"", "native")
+        r = _run(td, "empty_ref", gfa, b"", "reference")
+    assert e == r
+
+
+MALFORMED = {
+    "short": lambda f: f[:15],
+    "no_id_tag": lambda f: f[:15] + [b"dv:f:0.1"],
+    "id_not_float": lambda f: f[:15] + [b"id:f:abc"],
+    "path_without_direction": lambda f: f[:5] + [f[5][1:]] + f[6:],
+    "node_without_digits": lambda f: f[:5] + [f[5] + b">utgl"] + f[6:],
+    "node_id_overflow": lambda f: f[:5] + [f[5] + b">utg99999999999l"] + f[6:],
+    "start_not_int": lambda f: f[:7] + [b"x"] + f[8:],
+}
+
+
+@pytest.mark.parametrize("kind", sorted(MALFORMED))
+def test_malformed_lines_fail_loudly_where_the_reference_dies(kind):
+    case = CASES[0]
+    gfa = open(os.path.join(GOLDEN, case["gfa"])).read()
+    lines = [l for l in open(os.path.join(GOLDEN, case["gaf"]), "rb").read().split(b"\n") if l]
+    lines[5] = b"\t".join(MALFORMED[kind](lines[5].split(b"\t")))
+    gaf = b"\n".join(lines) + b"\n"
+    with tempfile.TemporaryDirectory() as td:
+        nat = _run(td, "nat", gfa, gaf, "native", expect_ok=False)
+        ref = _run(td, "ref", gfa, gaf, "reference", expect_ok=False)
+    assert ref.returncode != 0, "the reference's reader accepted this line"
+    assert nat.returncode == 65
+    assert b"reads.gaf:6:" in nat.stderr
+
+
+def _synth_text(prm):
+    from ahsoka_b200 import synth
+    with tempfile.TemporaryDirectory() as td:
+        synth.generate(prm, os.path.join(td, "x"))
+        return open(os.path.join(td, "x.gfa")).read(), open(os.path.join(td, "x.gaf"), "rb").read()
+
+
+def test_allele_paths_of_multi_allele_bubbles():
+    # bubbles with 3 inner nodes take findPathsComplex (chainstoreadset.cpp:84-116): paths start at the SINK
+    from ahsoka_b200 import synth
+    gfa, gaf = _synth_text(synth.params(3, 5, 1, 10, depth=12.0, seed=311))
+    _both(gfa, gaf, ploidy=3)
+
+
+def test_allele_paths_of_nested_bubbles():
+    # put a node in series behind one inner node of some bubbles: the bubble then has three inner nodes and one
+    # allele path of four nodes (depth-first enumeration, addSequence chainstoreadset.cpp:44-82)
+    from ahsoka_b200 import synth
+    gfa, gaf = _synth_text(synth.params(2, 4, 1, 8, depth=10.0, seed=312))
+    L = [l.split("\t") for l in gfa.split("\n") if l.startswith("L")]
+    S = [l for l in gfa.split("\n") if l.startswith("S")]
+    nxt = len(S) + 1
+    # plus-strand links in file order: flank→a0, then per allele (anchor→inner, inner→next anchor)
+    plus = [l for l in L if l[2] == "+"]
+    outdeg = {}
+    for l in plus:
+        outdeg[l[1]] = outdeg.get(l[1], 0) + 1
+    inner_out = [l for l in plus if outdeg.get(l[1], 0) == 1 and sum(1 for m in plus if m[3] == l[1]) == 1 and
+                 outdeg.get(next(m[1] for m in plus if m[3] == l[1]), 0) == 2]
+    assert len(inner_out) > 8
+    edited = 0
+    new_L = list(L)
+    for l in inner_out[1::5]:
+        name = "utg%07dl" % nxt
+        nxt += 1
+        S.append("S\t%s\tA" % name)
+        inner, anchor = l[1], l[3]
+        new_L = [m for m in new_L if not (m[1] == inner and m[2] == "+" and m[3] == anchor) and not (m[1] == anchor and m[2] == "-" and m[3] == inner)]
+        for a, b in ((inner, name), (name, anchor)):
+            new_L.append(["L", a, "+", b, "+", "0M"])
+            new_L.append(["L", b, "-", a, "-", "0M"])
+        edited += 1
+    assert edited >= 2
+    gfa2 = "\n".join(S + ["\t".join(m) for m in new_L]) + "\n"
+    out = _both(gfa2, gaf)
+    assert out["out-bubbleinfo.txt"].count(b"bubble id") > 0

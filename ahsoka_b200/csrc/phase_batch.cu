@@ -620,6 +620,7 @@ struct HostTrace {       // AHS_TRACE=1: wall-clock of the host-side steps of on
         char buf[96]; snprintf(buf, sizeof buf, " %s=%.2fms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         line += buf; t0 = t1;
     }
+    void note(const char* what, double v) { if (on) { char buf[96]; snprintf(buf, sizeof buf, " %s=%.1f", what, v); line += buf; } }
     ~HostTrace() { if (on) fprintf(stderr, "[ahs trace]%s\n", line.c_str()); }
 };
 
@@ -651,6 +652,7 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     tr.mark("validate");
     Ctx* cx = get_ctx(device);
     std::lock_guard<std::mutex> g(cx->mu);
+    tr.mark("context");
     CK(cudaSetDevice(device));
     if (cx->out_busy) throw ArgFail{"previous ahs_batch_out of this device was not released with ahs_free_out"};
     CK(cudaDeviceSynchronize());                          // nothing of a failed earlier call is in flight
@@ -742,6 +744,12 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     tr.mark("copies_enqueue");
     for (int k = 0; k < n_chunks; k++) { CK(cudaStreamSynchronize(cx->lanes[k].stream2)); CK(cudaStreamSynchronize(cx->lanes[k].stream)); }
     tr.mark("run_sync");
+    {
+        auto mb = [](const Pool& p, bool used) { double t = 0; for (auto& c : p.chunks) t += (double)(used ? c.used : c.cap); return t / 1048576.0; };
+        tr.note("dev_used_mb", mb(cx->dev, true)); tr.note("dev_cap_mb", mb(cx->dev, false));
+        tr.note("pin_used_mb", mb(cx->pin, true)); tr.note("out_used_mb", mb(cx->outp, true));
+        tr.note("in_enode_mb", (double)sz.NEN * 4 / 1048576.0);
+    }
     CK(cudaEventRecord(e1, cx->lanes[0].stream)); CK(cudaEventSynchronize(e1));
     float d2h = 0; CK(cudaEventElapsedTime(&d2h, d0, e1));
     if (out->cell_off[NFt] != tot_cells) throw std::runtime_error("cell count mismatch");
@@ -838,6 +846,22 @@ int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int device) {
 
 int ahs_phase_batch_resident(const ahs_batch_in* in, ahs_batch_out* out, int device, int warmup, int iters) {
     return guarded("ahs_phase_batch_resident", [&]() { phase_on_device(in, out, device, warmup < 0 ? 0 : warmup, iters < 1 ? 1 : iters); });
+}
+
+int ahs_warmup(int device, uint64_t device_bytes, uint64_t pinned_bytes) {
+    return guarded("ahs_warmup", [&]() {
+        Ctx* cx = get_ctx(device);
+        std::lock_guard<std::mutex> g(cx->mu);
+        CK(cudaSetDevice(device));
+        if (cx->out_busy) return;                          // a result is outstanding: its pools must not move
+        auto reserve = [](Pool& p, uint64_t bytes) {
+            size_t have = 0; for (auto& c : p.chunks) have = std::max(have, c.cap);
+            if (bytes > have) { p.alloc((size_t)bytes); p.reset(); }
+        };
+        reserve(cx->dev, device_bytes);
+        reserve(cx->outp, pinned_bytes);                   // results (zero-copy output arrays)
+        reserve(cx->pin, pinned_bytes ? (size_t)64 << 20 : 0);   // staging of the per-chain offset arrays
+    });
 }
 
 int ahs_pin_host(const void* ptr, uint64_t bytes) {

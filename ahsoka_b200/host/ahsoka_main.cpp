@@ -26,6 +26,9 @@
 #include "argumentparser.hpp"
 #include "graph.hpp"
 #include "gaf_reader.hpp"
+#include "ahsoka_b200.h"
+
+#include <sys/stat.h>
 
 using std::cerr; using std::cout; using std::endl; using std::string;
 typedef std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>> ChainAlleles;
@@ -78,6 +81,17 @@ int main(int argc, char* argv[]) {
     const int threads = std::stoi(argparser.get_arg_parameter('t'));
     const char* host_env = getenv("AHSOKA_HOST");
     const bool ref_host = host_env && !strcmp(host_env, "reference");
+    // the device context and the staging memory are set up on a second thread while the graph and the alignments are parsed
+    std::thread warm;
+    if (cmd == "phase") {
+        struct stat sb;
+        const uint64_t gaf_bytes = stat(alignmentfile.c_str(), &sb) == 0 ? (uint64_t)sb.st_size : 0;
+        const char* dv = getenv("AHSOKA_DEVICE");
+        const int device = dv ? atoi(dv) : 0;
+        // a GAF node costs ~12 text bytes and 4 batch bytes; a pass keeps ~5.5x the node array on the device and returns ~0.6x
+        warm = std::thread([=] { StageTimer t("warmup (second thread)"); ahs_warmup(device, gaf_bytes / 3 * 6, gaf_bytes / 3); });
+    }
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
     Graph graph;
     { StageTimer t("read_graph"); graph = Graph::ReadGraph(gfafile); }
     cout << "number of threads used: " << threads << endl;

@@ -14,6 +14,7 @@
 // Not reproduced: ./logfile.log and the -readset*.txt debugging dumps (third-party
 // ReadSet::toString() text), see INTEGRATION.md.
 #include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,7 @@
 #include <set>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "alignmentreader.hpp"   // reference header, found through -I<reference>/src
@@ -152,17 +154,29 @@ void flatten_store(const GafStore& st, ChainAlleles& pathToAlleles,
     finish_view(fb, ploidy);
 }
 
-// Emission, semantics of reference src/alignmentstoreadset.cpp:70-83 and :411-486.
+// Emission, semantics of reference src/alignmentstoreadset.cpp:70-83 and :411-486: the same bytes in the same files;
+// a haplotype line is formatted once into a buffer and written to both files (the reference streams every node twice
+// and flushes with endl after every line).
+static inline void put_int(std::string& s, long v) {
+    char buf[24];
+    auto r = std::to_chars(buf, buf + sizeof buf, v);
+    s.append(buf, (size_t)(r.ptr - buf));
+}
+
 void emit(const ahs_batch_out& out, Graph& graph,
           std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
           std::vector<std::pair<int, int>>& size_sorting, const std::string& prefix) {
     std::ofstream full_output(prefix + "-result.txt", std::ios_base::app);        // append, :72
     const int ploidy = out.ploidy;
+    std::string full, line, haps;
+    std::unordered_set<int> usednodes;
     for (size_t c = 0; c < size_sorting.size(); c++) {
         const int chainid = size_sorting[c].second;
-        full_output << "chain id: " << chainid << std::endl;
-        full_output << "size of chain: " << pathToAlleles[chainid].size() << std::endl;
+        full.clear();
+        full += "chain id: "; put_int(full, chainid); full += '\n';
+        full += "size of chain: "; put_int(full, (long)pathToAlleles[chainid].size()); full += '\n';
         if (out.status[c] != AHS_CHAIN_OK) {
+            full_output.write(full.data(), (std::streamsize)full.size());
             if (out.status[c] >= AHS_CHAIN_TOO_LARGE)
                 std::cerr << "ahsoka_b200: chain " << chainid << " not phased (status " << out.status[c] << ")" << std::endl;
             continue;
@@ -171,8 +185,9 @@ void emit(const ahs_batch_out& out, Graph& graph,
         const int64_t p0 = out.pos_off[c], n_pos = out.pos_off[c + 1] - p0;
         auto& alleles_of = pathToAlleles[chainid];
         for (int i = 0; i < ploidy; i++) {
-            std::set<int> usednodes;
-            full_output << "haplotype " << i << ":" << std::endl;
+            usednodes.clear();
+            full += "haplotype "; put_int(full, i); full += ":\n";
+            line.clear();
             for (int64_t j = 0; j < n_pos; j++) {
                 const uint32_t cons = out.hap_allele[(p0 + j) * ploidy + i];
                 const std::vector<int>& ap = alleles_of[out.pos[p0 + j]].at(cons);
@@ -189,22 +204,28 @@ void emit(const ahs_batch_out& out, Graph& graph,
                         for (auto& to : eit->second) if (to.id == next) { hit = true; break; }
                         if (hit) { end = val; break; }
                     }
-                    const char dir = end ? '+' : '-';
-                    resfile << single << '(' << dir << ')' << ",";
-                    full_output << single << '(' << dir << ')' << ",";
+                    put_int(line, single);
+                    line += end ? "(+)," : "(-),";
                     usednodes.insert(single);
                 }
             }
-            resfile << std::endl;
-            full_output << std::endl;
+            line += '\n';
+            resfile.write(line.data(), (std::streamsize)line.size());
+            full += line;
         }
         resfile.close();
+        full_output.write(full.data(), (std::streamsize)full.size());
+        haps.clear();
         for (int i = 0; i < ploidy; i++) {                                           // :479-486
-            std::cout << "hap: " << std::endl;
-            for (int64_t j = 0; j < n_pos; j++) std::cout << (uint32_t)out.hap_allele[(p0 + j) * ploidy + i] << "(" << out.pos[p0 + j] << ")" << ",";
-            std::cout << std::endl;
+            haps += "hap: \n";
+            for (int64_t j = 0; j < n_pos; j++) {
+                put_int(haps, (long)out.hap_allele[(p0 + j) * ploidy + i]); haps += '('; put_int(haps, out.pos[p0 + j]); haps += "),";
+            }
+            haps += '\n';
         }
+        std::cout.write(haps.data(), (std::streamsize)haps.size());
     }
+    std::cout.flush();
     full_output.close();
 }
 

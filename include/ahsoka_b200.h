@@ -157,6 +157,16 @@ int  ahs_phase_batch_resident(const ahs_batch_in *in, ahs_batch_out *out, int de
 
 void ahs_free_out(ahs_batch_out *out);
 
+/*
+ * Optional: create the device context (CUDA context, streams, kernel attributes, tables) and reserve
+ * `device_bytes` of device memory (a pass uses ~5.5x the bytes of enode[]) and `pinned_bytes` of
+ * page-locked result memory (~0.6x enode[]) ahead of the first
+ * ahs_phase_batch on `device`, e.g. from a second host thread while the caller still parses its
+ * input (the reference has no counterpart: it is what a one-shot CLI process pays once, ~0.3-3 s).
+ * Thread-safe against ahs_phase_batch; zero sizes reserve nothing.
+ */
+int  ahs_warmup(int device, uint64_t device_bytes, uint64_t pinned_bytes);
+
 /* Page-lock / unlock a caller buffer so that the H2D copies inside ahs_phase_batch run at full
  * PCIe speed (optional; plain cudaHostRegister / cudaHostUnregister). */
 int  ahs_pin_host(const void *ptr, uint64_t bytes);

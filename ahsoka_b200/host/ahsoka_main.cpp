@@ -1,12 +1,13 @@
 // ahsoka_main.cpp — `Ahsoka phase` / `Ahsoka only-bubbles` with the phasing step behind the
 // C ABI.  Same options, same files, same stdout banners as reference src/polyassembly.cpp:22-176;
 // the reference's own translation units (graph.cpp, alignmentreader.cpp, argumentparser.cpp,
-// chainstoreadset.cpp) are linked unchanged for GFA parsing and bubble/chain detection, exactly as
-// BASELINE.json's north_star prescribes.  The two stages either side of the phasing call that cannot
-// ingest a BASELINE-sized input (the GAF reader, O(L²) strings per line, and the
-// O(B²) allele-path enumeration) run through this repo's result-identical replacements
-// (gaf_reader.cpp, chain_alleles.cpp); AHSOKA_HOST=reference selects the reference's own functions
-// instead, which is how tests/test_host_parity.py compares the two.  `-t N` with N > 1 runs the
+// chainstoreadset.cpp) are linked unchanged, as BASELINE.json's north_star prescribes, and
+// AHSOKA_HOST=reference runs every host stage through them.  By default the stages either side of the
+// phasing call that cannot ingest a BASELINE-sized input (GFA parsing and bubble
+// detection copying node sequences at every step, the GAF reader's O(L²) strings per line, the O(B²)
+// allele-path enumeration) run through this repo's result-identical replacements (graph_native.cpp,
+// gaf_reader.cpp, chain_alleles.cpp), which fill the reference's own Graph object;
+// tests/test_host_parity.py compares the two byte for byte.  `-t N` with N > 1 runs the
 // same single batch call (the reference's two-thread experiment, polyassembly.cpp:190-222,
 // only ever processed the ten largest chains and is not a parity target).
 #include <algorithm>
@@ -36,7 +37,11 @@ typedef std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<
 ChainAlleles ChainsToReadsetDetailed(Graph graph);     // reference src/chainstoreadset.cpp:161
 void alignmentsToReadset(AlignmentReader&, Graph&, ChainAlleles&, string, bool, std::vector<std::pair<int, int>>&, std::mutex&);
 void alignmentsToReadset(const ahs_host::GafStore&, Graph&, ChainAlleles&, string, bool, std::vector<std::pair<int, int>>&, std::mutex&);
-namespace ahs_host { ChainAlleles chain_alleles(const Graph& graph); }
+namespace ahs_host {
+ChainAlleles chain_alleles(const Graph& graph);
+int read_gfa(const std::string& filename, Graph& graph, std::string& err);
+int find_bubbles(Graph& graph, std::string& err);
+}
 
 namespace {
 struct StageTimer {     // AHSOKA_TIMING=1: "timing: <stage> <ms>" on stderr
@@ -93,11 +98,25 @@ int main(int argc, char* argv[]) {
     }
     struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
     Graph graph;
-    { StageTimer t("read_graph"); graph = Graph::ReadGraph(gfafile); }
+    {
+        StageTimer t("read_graph");
+        if (ref_host) graph = Graph::ReadGraph(gfafile);
+        else {
+            string err;
+            if (int rc = ahs_host::read_gfa(gfafile, graph, err)) { cerr << "ahsoka_b200: " << err << endl; return rc; }   // the reference aborts on the same line
+        }
+    }
     cout << "number of threads used: " << threads << endl;
     cout << "threads available: " << std::thread::hardware_concurrency() << endl;
     cout << "Step 1: Graph with " << graph.nodes.size() << " nodes read" << endl;
-    { StageTimer t("find_bubbles"); graph.findBubbles(); }
+    {
+        StageTimer t("find_bubbles");
+        if (ref_host) graph.findBubbles();
+        else {
+            string err;
+            if (int rc = ahs_host::find_bubbles(graph, err)) { cerr << "ahsoka_b200: " << err << " (AHSOKA_HOST=reference runs the reference's own detection)" << endl; return rc; }
+        }
+    }
     cout << "Step 2: Bubbles read" << endl;
     cout << "Number of bubble chains: " << graph.chains.size() << endl;
     {

@@ -207,3 +207,125 @@ def test_allele_paths_of_nested_bubbles():
     gfa2 = "\n".join(S + ["\t".join(m) for m in new_L]) + "\n"
     out = _both(gfa2, gaf)
     assert out["out-bubbleinfo.txt"].count(b"bubble id") > 0
+
+
+def _messy_gfa(seed):
+    """Random small graphs: bubble chains with tips, loops, cross links, one-sided links, repeated S lines, other
+    record types — every branch of Graph::findBubble (graph.cpp:381-500) gets exercised."""
+    import random
+    rng = random.Random(seed)
+    lines = ["H\tVN:Z:1.0"]
+    n = rng.randint(6, 40)
+    ids = list(range(1, n + 1))
+    rng.shuffle(ids)
+    for i in ids:
+        lines.append("S\tutg%06dl\t%s" % (i, "ACGT"[: rng.randint(1, 4)]))
+    links = set()
+
+    def link(a, sa, b, sb, both=True):
+        links.add((a, sa, b, sb))
+        if both:
+            links.add((b, "-" if sb == "+" else "+", a, "-" if sa == "+" else "+"))
+
+    # a backbone of bubbles / linear stretches
+    cur = 1
+    nxt = 2
+    while nxt + 3 <= n:
+        kind = rng.random()
+        if kind < 0.55:                      # simple bubble cur -> {a, b} -> c
+            a, b, c = nxt, nxt + 1, nxt + 2
+            for x in (a, b):
+                link(cur, "+", x, "+"); link(x, "+", c, "+")
+            cur, nxt = c, nxt + 3
+        elif kind < 0.7:                     # three-allele bubble
+            if nxt + 4 > n:
+                break
+            a, b, c, e = nxt, nxt + 1, nxt + 2, nxt + 3
+            for x in (a, b, c):
+                link(cur, "+", x, "+"); link(x, "+", e, "+")
+            cur, nxt = e, nxt + 4
+        elif kind < 0.85:                    # linear step
+            link(cur, "+", nxt, "+")
+            cur, nxt = nxt, nxt + 1
+        else:                                # nested: cur -> a -> b -> c, cur -> d -> c
+            if nxt + 4 > n:
+                break
+            a, b, d, c = nxt, nxt + 1, nxt + 2, nxt + 3
+            link(cur, "+", a, "+"); link(a, "+", b, "+"); link(b, "+", c, "+"); link(cur, "+", d, "+"); link(d, "+", c, "+")
+            cur, nxt = c, nxt + 4
+    for _ in range(rng.randint(0, 4)):      # noise: tips, cross links, loops, one-sided links, inversions
+        a, b = rng.randint(1, n), rng.randint(1, n)
+        link(a, rng.choice("+-"), b, rng.choice("+-"), both=rng.random() < 0.7)
+    out = list(links)
+    rng.shuffle(out)
+    for a, sa, b, sb in out:
+        lines.append("L\tutg%06dl\t%s\tutg%06dl\t%s\t%dM" % (a, sa, b, sb, rng.choice([0, 0, 17])))
+    if rng.random() < 0.3:
+        lines.insert(rng.randint(1, n), "")           # blank line
+    if rng.random() < 0.3:
+        lines.append("P\tpath1\tutg000001l+\t*")      # other record types are skipped (:194)
+    text = "\n".join(lines) + "\n"
+    if rng.random() < 0.2:
+        text += "S\tutg999999l\tA"                    # unterminated last line is dropped (:192)
+    return text
+
+
+def _only_bubbles(td, tag, gfa_text, host):
+    d = os.path.join(td, tag)
+    os.makedirs(d)
+    open(os.path.join(d, "g.gfa"), "w").write(gfa_text)
+    env = dict(os.environ)
+    env.pop("AHSOKA_HOST", None)
+    if host == "reference":
+        env["AHSOKA_HOST"] = "reference"
+    try:
+        r = subprocess.run([EXE, "only-bubbles", "-g", "g.gfa", "-o", "out"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=20, env=env)
+    except subprocess.TimeoutExpired:
+        return None
+    if r.returncode != 0:
+        return None
+    return r.stdout, open(os.path.join(d, "out-bubbleinfo.txt"), "rb").read()
+
+
+def test_bubble_detection_on_messy_graphs():
+    ok = 0
+    with_bubbles = 0
+    with tempfile.TemporaryDirectory() as td:
+        for seed in range(150):
+            gfa = _messy_gfa(seed)
+            ref = _only_bubbles(td, "r%d" % seed, gfa, "reference")
+            if ref is None:
+                continue        # the reference itself crashes or does not terminate on this graph
+            nat = _only_bubbles(td, "n%d" % seed, gfa, "native")
+            assert nat is not None, "native detection failed where the reference ran (seed %d)" % seed
+            assert nat == ref, "bubble chains differ from the reference's (seed %d)" % seed
+            ok += 1
+            with_bubbles += b"bubble id" in ref[1]
+            # and the stages behind it (reader's chain lookup, allele paths, flattening) on the same graph
+            try:
+                r2 = _run(td, "pr%d" % seed, gfa, b"", "reference")
+            except (AssertionError, subprocess.TimeoutExpired):
+                continue        # the reference's allele-path enumeration dies on this bubble
+            n2 = _run(td, "pn%d" % seed, gfa, b"", "native")
+            assert r2 == n2, "seed %d" % seed
+    assert ok >= 100 and with_bubbles >= 80, (ok, with_bubbles)
+
+
+MALFORMED_GFA = {
+    "s_without_sequence": "S\tutg000001l\n",
+    "s_without_digits": "S\tutgl\tA\n",
+    "l_bad_orientation": "S\tu1\tA\nS\tu2\tA\nL\tu1\t*\tu2\t+\t0M\n",
+    "l_star_overlap": "S\tu1\tA\nS\tu2\tA\nL\tu1\t+\tu2\t+\t*\n",
+    "l_negative_overlap": "S\tu1\tA\nS\tu2\tA\nL\tu1\t+\tu2\t+\t-3M\n",
+}
+
+
+@pytest.mark.parametrize("kind", sorted(MALFORMED_GFA))
+def test_malformed_gfa_fails_loudly_where_the_reference_dies(kind):
+    with tempfile.TemporaryDirectory() as td:
+        assert _only_bubbles(td, "ref", MALFORMED_GFA[kind], "reference") is None
+        d = os.path.join(td, "nat")
+        os.makedirs(d)
+        open(os.path.join(d, "g.gfa"), "w").write(MALFORMED_GFA[kind])
+        r = subprocess.run([EXE, "only-bubbles", "-g", "g.gfa", "-o", "out"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=20)
+    assert r.returncode == 66 and b"g.gfa:" in r.stderr

@@ -125,7 +125,9 @@ int main(int argc, char* argv[]) {
             bubblefile << "chain id: " << chain.id << "size: " << chain.bubbles.size() << endl;
             for (auto& bubble : chain.bubbles) {
                 bubblefile << "bubble id: " << bubble.id << endl << "node id: ";
-                for (auto& node : bubble.getNodes()) bubblefile << node.node_id << ",";
+                bubblefile << bubble.source.node_id << ",";          // Bubble::getNodes() order (graph.cpp:96-104) without copying the nodes
+                for (auto& node : bubble.innerNodes) bubblefile << node.node_id << ",";
+                bubblefile << bubble.sink.node_id << ",";
                 bubblefile << endl;
             }
         }

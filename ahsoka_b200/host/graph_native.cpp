@@ -190,10 +190,12 @@ void find_bubble(Graph& g, Ref node, Chain* bchain) {
                 if (inside.size() == 2) break;
                 for (size_t i = 0; i < inside.size(); i++) if (inside[i].id == node.id) { inside.erase(inside.begin() + i); break; }
                 for (size_t i = 0; i < inside.size(); i++) if (inside[i].id == t.id) { inside.erase(inside.begin() + i); break; }
-                std::vector<Node> inner;
-                inner.reserve(inside.size());
-                for (auto& r : inside) inner.push_back(snapshot(g, r));
-                bchain->bubbles.emplace_back(snapshot(g, node), snapshot(g, t), std::move(inner));   // Bubble(...), id 0; addBubble
+                bchain->bubbles.emplace_back();                                                  // Bubble(node, t.first, nodesInside), id 0; addBubble —
+                Bubble& bubble = bchain->bubbles.back();                                         // one copy per node instead of three
+                bubble.source = snapshot(g, node);
+                bubble.sink = snapshot(g, t);
+                bubble.innerNodes.reserve(inside.size());
+                for (auto& r : inside) bubble.innerNodes.push_back(snapshot(g, r));
                 chained = true;
                 break;                                                                          // findBubble(t.first, t.second, bchain), then S is empty
             }

@@ -14,6 +14,7 @@
 // Not reproduced: ./logfile.log and the -readset*.txt debugging dumps (third-party
 // ReadSet::toString() text), see INTEGRATION.md.
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <chrono>
 #include <cstdio>
@@ -23,6 +24,7 @@
 #include <mutex>
 #include <set>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -62,17 +64,18 @@ static bool same_entry(AlignmentPath& a, AlignmentPath& b) {
 // Alleles of one chain (reference src/polyassembly.cpp:126-140 containers), appended CSR; returns the
 // number of bubbles B the phasing sees (0 for chains of ≤1 bubble, alignmentstoreadset.cpp:86).
 static int flatten_chain_alleles(ChainAlleles& pathToAlleles, int chainid, FlatBatch& fb) {
-    // same copy the reference takes (alignmentstoreadset.cpp:76): its iteration order is stage A's
-    auto chainmap = std::make_pair(chainid, pathToAlleles[chainid]);
+    // the reference iterates a COPY of this map (alignmentstoreadset.cpp:76, :90) and that order is stage A's; a libstdc++
+    // unordered_map copy keeps the element order of its source (_M_assign walks the source list), so the source is read in place
+    const auto& bubbles = pathToAlleles[chainid];
     fb.chain_id.push_back(chainid);
     int B = 0;
-    if (chainmap.second.size() > 1) for (auto& kv : chainmap.second) B = std::max(B, kv.first + 1);
+    if (bubbles.size() > 1) for (auto& kv : bubbles) B = std::max(B, kv.first + 1);
     std::vector<char> seen(B, 0);
-    for (auto& kv : chainmap.second) if (kv.first >= 0 && kv.first < B) { fb.stage_a_order.push_back(kv.first); seen[kv.first] = 1; }
+    for (auto& kv : bubbles) if (kv.first >= 0 && kv.first < B) { fb.stage_a_order.push_back(kv.first); seen[kv.first] = 1; }
     for (int b = 0; b < B; b++) if (!seen[b]) fb.stage_a_order.push_back(b);
     for (int b = 0; b < B; b++) {
-        auto it = chainmap.second.find(b);
-        if (it != chainmap.second.end()) for (auto& path : it->second) {
+        auto it = bubbles.find(b);
+        if (it != bubbles.end()) for (auto& path : it->second) {
             fb.anode.insert(fb.anode.end(), path.begin(), path.end());
             fb.anode_off.push_back((int64_t)fb.anode.size());
         }
@@ -128,6 +131,16 @@ void flatten(AlignmentReader& reader, ChainAlleles& pathToAlleles,
 void flatten_store(const GafStore& st, ChainAlleles& pathToAlleles,
                    std::vector<std::pair<int, int>>& size_sorting, int ploidy, FlatBatch& fb) {
     std::vector<int32_t> stamp(st.names.size(), -1), local(st.names.size(), 0);
+    {
+        size_t n_entries = 0, n_nodes = 0;
+        for (auto& size : size_sorting) {
+            auto it = st.by_chain.find(size.second);
+            if (it == st.by_chain.end()) continue;
+            n_entries += it->second.size();
+            for (int32_t line : it->second) n_nodes += (size_t)(st.node_off[line + 1] - st.node_off[line]);
+        }
+        fb.enode.reserve(n_nodes); fb.enode_off.reserve(n_entries + 1); fb.entry_read.reserve(n_entries); fb.entry_identity.reserve(n_entries);
+    }
     int32_t c = 0;
     for (auto& size : size_sorting) {
         const int chainid = size.second;
@@ -166,64 +179,84 @@ static inline void put_int(std::string& s, long v) {
 void emit(const ahs_batch_out& out, Graph& graph,
           std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
           std::vector<std::pair<int, int>>& size_sorting, const std::string& prefix) {
-    std::ofstream full_output(prefix + "-result.txt", std::ios_base::app);        // append, :72
     const int ploidy = out.ploidy;
-    std::string full, line, haps;
-    std::unordered_set<int> usednodes;
-    for (size_t c = 0; c < size_sorting.size(); c++) {
-        const int chainid = size_sorting[c].second;
-        full.clear();
-        full += "chain id: "; put_int(full, chainid); full += '\n';
-        full += "size of chain: "; put_int(full, (long)pathToAlleles[chainid].size()); full += '\n';
-        if (out.status[c] != AHS_CHAIN_OK) {
-            full_output.write(full.data(), (std::streamsize)full.size());
-            if (out.status[c] >= AHS_CHAIN_TOO_LARGE)
-                std::cerr << "ahsoka_b200: chain " << chainid << " not phased (status " << out.status[c] << ")" << std::endl;
-            continue;
-        }
-        std::ofstream resfile(prefix + "-chain" + std::to_string(chainid) + "-result.txt");
-        const int64_t p0 = out.pos_off[c], n_pos = out.pos_off[c + 1] - p0;
-        auto& alleles_of = pathToAlleles[chainid];
-        for (int i = 0; i < ploidy; i++) {
-            usednodes.clear();
-            full += "haplotype "; put_int(full, i); full += ":\n";
-            line.clear();
-            for (int64_t j = 0; j < n_pos; j++) {
-                const uint32_t cons = out.hap_allele[(p0 + j) * ploidy + i];
-                const std::vector<int>& ap = alleles_of[out.pos[p0 + j]].at(cons);
-                for (size_t ind = 0; ind + 1 < ap.size(); ind++) {
-                    const int single = ap[ind], next = ap[ind + 1];
-                    if (usednodes.count(single)) continue;
-                    // Graph::getNode + Graph::getEdge (graph.cpp:502-512, 251-261) without the scan over all
-                    // nodes and without copying node sequences (f2): first of (single,+), (single,-) with an edge to next
-                    bool end = false;
-                    for (bool val : {true, false}) {
-                        auto eit = graph.edges.find(DirectedNode(single, val));
-                        if (eit == graph.edges.end()) continue;
-                        bool hit = false;
-                        for (auto& to : eit->second) if (to.id == next) { hit = true; break; }
-                        if (hit) { end = val; break; }
+    const size_t C = size_sorting.size();
+    // chains are independent: worker threads format a chain's text and write its <prefix>-chain<id>-result.txt; the
+    // shared -result.txt and the stdout lines are then written in size_sorting order by this thread
+    std::vector<std::string> full_of(C), haps_of(C);
+    for (size_t c = 0; c < C; c++) pathToAlleles[size_sorting[c].second];      // the reference's operator[] (:76), before the threads start
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        std::string line;
+        std::unordered_set<int> usednodes;
+        for (;;) {
+            const size_t c0 = next.fetch_add(64);
+            if (c0 >= C) break;
+            for (size_t c = c0; c < std::min(C, c0 + 64); c++) {
+                const int chainid = size_sorting[c].second;
+                const auto& alleles_of = pathToAlleles.find(chainid)->second;
+                std::string& full = full_of[c];
+                full += "chain id: "; put_int(full, chainid); full += '\n';
+                full += "size of chain: "; put_int(full, (long)alleles_of.size()); full += '\n';
+                if (out.status[c] != AHS_CHAIN_OK) continue;
+                std::ofstream resfile(prefix + "-chain" + std::to_string(chainid) + "-result.txt");
+                const int64_t p0 = out.pos_off[c], n_pos = out.pos_off[c + 1] - p0;
+                for (int i = 0; i < ploidy; i++) {
+                    usednodes.clear();
+                    full += "haplotype "; put_int(full, i); full += ":\n";
+                    line.clear();
+                    for (int64_t j = 0; j < n_pos; j++) {
+                        const uint32_t cons = out.hap_allele[(p0 + j) * ploidy + i];
+                        const std::vector<int>& ap = alleles_of.at(out.pos[p0 + j]).at(cons);
+                        for (size_t ind = 0; ind + 1 < ap.size(); ind++) {
+                            const int single = ap[ind], nxt = ap[ind + 1];
+                            if (usednodes.count(single)) continue;
+                            // Graph::getNode + Graph::getEdge (graph.cpp:502-512, 251-261) without the scan over all
+                            // nodes and without copying node sequences (f2): first of (single,+), (single,-) with an edge to nxt
+                            bool end = false;
+                            for (bool val : {true, false}) {
+                                auto eit = graph.edges.find(DirectedNode(single, val));
+                                if (eit == graph.edges.end()) continue;
+                                bool hit = false;
+                                for (auto& to : eit->second) if (to.id == nxt) { hit = true; break; }
+                                if (hit) { end = val; break; }
+                            }
+                            put_int(line, single);
+                            line += end ? "(+)," : "(-),";
+                            usednodes.insert(single);
+                        }
                     }
-                    put_int(line, single);
-                    line += end ? "(+)," : "(-),";
-                    usednodes.insert(single);
+                    line += '\n';
+                    resfile.write(line.data(), (std::streamsize)line.size());
+                    full += line;
+                }
+                resfile.close();
+                std::string& haps = haps_of[c];
+                for (int i = 0; i < ploidy; i++) {                                           // :479-486
+                    haps += "hap: \n";
+                    for (int64_t j = 0; j < n_pos; j++) {
+                        put_int(haps, (long)out.hap_allele[(p0 + j) * ploidy + i]); haps += '('; put_int(haps, out.pos[p0 + j]); haps += "),";
+                    }
+                    haps += '\n';
                 }
             }
-            line += '\n';
-            resfile.write(line.data(), (std::streamsize)line.size());
-            full += line;
         }
-        resfile.close();
-        full_output.write(full.data(), (std::streamsize)full.size());
-        haps.clear();
-        for (int i = 0; i < ploidy; i++) {                                           // :479-486
-            haps += "hap: \n";
-            for (int64_t j = 0; j < n_pos; j++) {
-                put_int(haps, (long)out.hap_allele[(p0 + j) * ploidy + i]); haps += '('; put_int(haps, out.pos[p0 + j]); haps += "),";
-            }
-            haps += '\n';
-        }
-        std::cout.write(haps.data(), (std::streamsize)haps.size());
+    };
+    {
+        unsigned T = std::thread::hardware_concurrency();
+        if (T < 1) T = 1;
+        if (C < 256) T = 1;
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < T; t++) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+    }
+    std::ofstream full_output(prefix + "-result.txt", std::ios_base::app);        // append, :72
+    for (size_t c = 0; c < C; c++) {
+        full_output.write(full_of[c].data(), (std::streamsize)full_of[c].size());
+        if (out.status[c] >= AHS_CHAIN_TOO_LARGE)
+            std::cerr << "ahsoka_b200: chain " << size_sorting[c].second << " not phased (status " << out.status[c] << ")" << std::endl;
+        std::cout.write(haps_of[c].data(), (std::streamsize)haps_of[c].size());
     }
     std::cout.flush();
     full_output.close();
@@ -261,10 +294,20 @@ static void phase_and_emit(FlatBatch& fb, int ploidy, Graph& graph, ChainAlleles
     ahs_batch_out out;
     const char* dv = getenv("AHSOKA_DEVICE");
     int rc;
+    // page-lock the large arrays of the batch: the uploads inside the call then run asynchronously at full PCIe speed
+    // instead of through the driver's staging buffer
+    const void* big[4] = {fb.enode.data(), fb.enode_off.data(), fb.entry_read.data(), fb.entry_identity.data()};
+    const uint64_t big_bytes[4] = {fb.enode.size() * 4, fb.enode_off.size() * 8, fb.entry_read.size() * 4, fb.entry_identity.size() * 4};
+    bool pinned[4] = {false, false, false, false};
+    if (fb.enode.size() >= ((size_t)1 << 22) && !getenv("AHSOKA_NO_PIN")) {
+        StageTimer t("pin_batch");
+        for (int i = 0; i < 4; i++) pinned[i] = ahs_pin_host(big[i], big_bytes[i]) == AHS_OK;
+    }
     {
         StageTimer t("phase_batch");
         rc = ahs_phase_batch(&fb.view, &out, dv ? atoi(dv) : 0);
     }
+    for (int i = 0; i < 4; i++) if (pinned[i]) ahs_unpin_host(big[i]);
     if (rc != AHS_OK) {
         std::cerr << "ahsoka_b200: phasing failed (" << rc << "): " << ahs_last_error() << std::endl;
         exit(70);                                             // fail loudly: no CPU path behind the ABI

@@ -75,7 +75,9 @@ ChainAlleles chain_alleles(const Graph& graph) {
                 add_sequence(bubble.sink, right_within ? 0 : 1, bv, seq, alleles, 0);
             }
         }
-        if (!chain.bubbles.empty()) out[chain.id] = per_bubble;    // the last of the reference's per-bubble assignments
+        // the last of the reference's per-bubble copy assignments; a copy-assigned libstdc++ unordered_map takes the bucket
+        // count and the element order of its source, which is exactly what moving the source hands over
+        if (!chain.bubbles.empty()) out[chain.id] = std::move(per_bubble);
     }
     return out;
 }

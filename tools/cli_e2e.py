@@ -30,9 +30,13 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         b = synth.generate(synth.config(a.workload, a.scale), os.path.join(td, "s"))
         env = dict(os.environ, AHSOKA_TIMING="1", AHSOKA_PLOIDY=str(int(b.ploidy)))
+        if os.environ.get("CLI_E2E_VERBOSE"):
+            print("affinity", len(os.sched_getaffinity(0)), file=sys.stderr)
         if a.host == "reference":
             env["AHSOKA_HOST"] = "reference"
         out = None
+        counts = {"chains": int(b.n_chains)}
+        del b                                   # the generator's copy of the batch is not needed while the CLI runs
         for _ in range(a.repeat):
             t0 = time.time()
             r = subprocess.run([a.exe, "phase", "-g", "s.gfa", "-a", "s.gaf", "-o", "out", "-t", str(a.threads)], cwd=td, env=env,
@@ -45,9 +49,14 @@ def main():
                 if l.startswith("timing:"):
                     f = l.split()
                     stages[" ".join(f[1:-1])] = round(float(f[-1]), 1)
-            out = {"workload": a.workload, "scale": a.scale, "host": a.host, "chains": int(b.n_chains), "gaf_lines": sum(1 for _ in open(os.path.join(td, "s.gaf"))),
+            trace = [l for l in r.stderr.split("\n") if l.startswith("[ahs trace]")]
+            out = {"workload": a.workload, "scale": a.scale, "host": a.host, "chains": counts["chains"], "gaf_lines": sum(1 for _ in open(os.path.join(td, "s.gaf"))),
                    "gaf_mb": round(os.path.getsize(os.path.join(td, "s.gaf")) / 1e6, 1), "gfa_mb": round(os.path.getsize(os.path.join(td, "s.gfa")) / 1e6, 1),
                    "stages_ms": stages, "wall_s": round(wall, 2), "host_cores": os.cpu_count()}
+            if trace:
+                out["ahs_trace"] = trace[-1]
+            if os.environ.get("CLI_E2E_VERBOSE"):
+                print(json.dumps(out), file=sys.stderr)
         print(json.dumps(out))
 
 

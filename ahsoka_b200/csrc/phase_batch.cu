@@ -29,9 +29,6 @@ namespace ahs {
 constexpr int32_t AHS_OUT_MALLOCED = 0x4d414c43;
 static thread_local char g_err[512] = "";
 
-// All kernels of this library are loaded when the CUDA context is created (ahs_warmup, off the caller's critical path)
-// instead of one by one at their first launch inside the first ahs_phase_batch call.  A value set by the user wins.
-__attribute__((constructor)) static void ahs_eager_module_loading() { setenv("CUDA_MODULE_LOADING", "EAGER", 0); }
 static void set_err(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
 
 struct CudaFail { cudaError_t e; const char* what; int line; };

@@ -294,20 +294,10 @@ static void phase_and_emit(FlatBatch& fb, int ploidy, Graph& graph, ChainAlleles
     ahs_batch_out out;
     const char* dv = getenv("AHSOKA_DEVICE");
     int rc;
-    // page-lock the large arrays of the batch: the uploads inside the call then run asynchronously at full PCIe speed
-    // instead of through the driver's staging buffer
-    const void* big[4] = {fb.enode.data(), fb.enode_off.data(), fb.entry_read.data(), fb.entry_identity.data()};
-    const uint64_t big_bytes[4] = {fb.enode.size() * 4, fb.enode_off.size() * 8, fb.entry_read.size() * 4, fb.entry_identity.size() * 4};
-    bool pinned[4] = {false, false, false, false};
-    if (fb.enode.size() >= ((size_t)1 << 22) && !getenv("AHSOKA_NO_PIN")) {
-        StageTimer t("pin_batch");
-        for (int i = 0; i < 4; i++) pinned[i] = ahs_pin_host(big[i], big_bytes[i]) == AHS_OK;
-    }
     {
         StageTimer t("phase_batch");
         rc = ahs_phase_batch(&fb.view, &out, dv ? atoi(dv) : 0);
     }
-    for (int i = 0; i < 4; i++) if (pinned[i]) ahs_unpin_host(big[i]);
     if (rc != AHS_OK) {
         std::cerr << "ahsoka_b200: phasing failed (" << rc << "): " << ahs_last_error() << std::endl;
         exit(70);                                             // fail loudly: no CPU path behind the ABI

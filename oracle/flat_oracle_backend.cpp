@@ -9,6 +9,4 @@ extern "C" void ahs_oracle_free_out(ahs_batch_out*);
 extern "C" int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int) { return ahs_oracle_phase_batch(in, out, 1); }
 extern "C" void ahs_free_out(ahs_batch_out* o) { ahs_oracle_free_out(o); }
 extern "C" int ahs_warmup(int, uint64_t, uint64_t) { return 0; }
-extern "C" int ahs_pin_host(const void*, uint64_t) { return 1; }      // nothing to page-lock for a CPU checker
-extern "C" int ahs_unpin_host(const void*) { return 0; }
 extern "C" const char* ahs_last_error(void) { return "oracle backend"; }

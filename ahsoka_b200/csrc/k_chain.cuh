@@ -107,8 +107,9 @@ __device__ __forceinline__ int cc_min_key(int mine, int32_t* cell, int tid, int&
 }
 
 // shared-memory footprint of the scoring kernel
-__host__ __device__ inline size_t cs_smem_bytes(int nmax) {
-    return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15) & ~(size_t)15;
+constexpr int CS_WARP_KEYS = 128;          // per-warp scratch of the rate sort: the partners of one read, compacted (<= CC_MAXN - 1)
+__host__ __device__ inline size_t cs_smem_bytes(int nmax, int nt) {
+    return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15) + (size_t)(nt / 32) * CS_WARP_KEYS * 8;
 }
 
 // ascending bitonic sort of 32*KPL keys (uint32_t or uint64_t) held KPL per lane (element e = s*32 + lane)
@@ -141,6 +142,28 @@ __device__ __forceinline__ void warp_sort(T (&v)[KPL], int lane) {
     }
 }
 
+// Rule R1's pooling for one read: the m partner keys in ws[0..m) (any order) are sorted as 32*K2 >= m keys, the `cut`
+// lowest rates are pooled as same-haplotype pairs, the rest as different-haplotype pairs.  K_BITS / N_SHIFT / MASK give
+// the (k, n) fields of a key.
+template <int K2, class T, int N_SHIFT, int MASK>
+__device__ __forceinline__ void cs_pool(const T* __restrict__ ws, int m, int cut, int lane, int& Ks, int& Ns, int& Kd, int& Nd) {
+    T v[K2];
+#pragma unroll
+    for (int s = 0; s < K2; s++) v[s] = s * 32 + lane < m ? ws[s * 32 + lane] : (T)~(T)0;
+    warp_sort<K2>(v, lane);
+#pragma unroll
+    for (int s = 0; s < K2; s++) if (s * 32 + lane < m) {
+        const int kq = (int)(v[s] & (T)MASK), nq = (int)((v[s] >> N_SHIFT) & (T)MASK);
+        if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
+    }
+}
+template <int KPL, class T, int N_SHIFT, int MASK>
+__device__ __forceinline__ void cs_pool_any(const T* __restrict__ ws, int m, int cut, int lane, int& Ks, int& Ns, int& Kd, int& Nd) {
+    if (m <= 32) cs_pool<1, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+    else if (KPL >= 2 && m <= 64) cs_pool<(KPL >= 2 ? 2 : 1), T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+    else cs_pool<KPL, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: read-pair scoring of one chain per block (rule R1).  Wout[cw_off[c] + pair number] = Q10 weight,
 // pair number = position of (x,y), x < y, in the row-major upper triangle.
@@ -156,6 +179,7 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
     int32_t* first = W + (size_t)nmax * ns; int32_t* last = first + nmax;
     int32_t* scal = last + nmax;
     uint16_t* es = (uint16_t*)(scal + 16); uint16_t* ed = es + nmax;
+    uint64_t* wkeys = (uint64_t*)(cc_sm + (((size_t)nmax * ns * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15)) + (size_t)wid * CS_WARP_KEYS;
     int64_t pairs_total = 0;
     while (true) {
         __syncthreads();
@@ -206,49 +230,45 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
             const bool narrow = d.bubble_off[c + 1] - d.bubble_off[c] <= 255;
             for (int i = wid; i < n; i += NW) {
                 int m = 0, Ks = 0, Ns = 0, Kd = 0, Nd = 0;
+                // the partners' keys are compacted into the warp's scratch first: a read of a 75-read chain has ~35
+                // partners, so 32 or 64 keys are sorted instead of 32*KPL
                 if (narrow) {
-                    uint32_t kk[KPL];
+                    uint32_t* ws = (uint32_t*)wkeys;
 #pragma unroll
                     for (int s = 0; s < KPL; s++) {
                         const int j = s * 32 + lane;
                         const int nk = j < n ? W[i * ns + j] : 0;
                         const uint32_t nq = (uint32_t)nk >> 16, kq = (uint32_t)nk & 0xffffu;
-                        kk[s] = nk ? (((kq * 65535u) / nq) << 16) | (nq << 8) | kq : 0xffffffffu;
-                        m += __popc(__ballot_sync(0xffffffffu, nk != 0));
+                        const uint32_t bal = __ballot_sync(0xffffffffu, nk != 0);
+                        if (nk) ws[m + __popc(bal & ((1u << lane) - 1u))] = (((kq * 65535u) / nq) << 16) | (nq << 8) | kq;
+                        m += __popc(bal);
                     }
-                    if (m > 0) {
-                        warp_sort<KPL>(kk, lane);
-                        const int cut = max(1, m / d.ploidy);
-#pragma unroll
-                        for (int s = 0; s < KPL; s++) if (kk[s] != 0xffffffffu) {
-                            const int kq = (int)(kk[s] & 0xffu), nq = (int)((kk[s] >> 8) & 0xffu);
-                            if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
-                        }
-                    }
+                    __syncwarp();
+                    if (m > 0) cs_pool_any<KPL, uint32_t, 8, 0xff>(ws, m, max(1, m / d.ploidy), lane, Ks, Ns, Kd, Nd);
                 } else {
-                    uint64_t kk[KPL];
+                    uint64_t* ws = wkeys;
 #pragma unroll
                     for (int s = 0; s < KPL; s++) {
                         const int j = s * 32 + lane;
                         const int nk = j < n ? W[i * ns + j] : 0;
-                        kk[s] = nk ? rate_key(nk >> 16, nk & 0xffff) : ~0ull;
-                        m += __popc(__ballot_sync(0xffffffffu, nk != 0));
+                        const uint32_t bal = __ballot_sync(0xffffffffu, nk != 0);
+                        if (nk) ws[m + __popc(bal & ((1u << lane) - 1u))] = rate_key(nk >> 16, nk & 0xffff);
+                        m += __popc(bal);
                     }
-                    if (m > 0) {
-                        warp_sort<KPL>(kk, lane);
-                        const int cut = max(1, m / d.ploidy);
-#pragma unroll
-                        for (int s = 0; s < KPL; s++) if (kk[s] != ~0ull) {
-                            const int kq = (int)(kk[s] & 0x7fff), nq = (int)((kk[s] >> 15) & 0x7fff);
-                            if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
-                        }
-                    }
+                    __syncwarp();
+                    if (m > 0) cs_pool_any<KPL, uint64_t, 15, 0x7fff>(ws, m, max(1, m / d.ploidy), lane, Ks, Ns, Kd, Nd);
                 }
+                __syncwarp();                                   // the scratch is rewritten for the warp's next read
                 uint32_t es_i = 0, ed_i = 0;
                 if (m > 0) {
                     Ks = warp_sum_i32(Ks); Ns = warp_sum_i32(Ns); Kd = warp_sum_i32(Kd); Nd = warp_sum_i32(Nd);
-                    es_i = (uint32_t)(((int64_t)Ks * 1024 + Ns / 2) / Ns);
-                    ed_i = Nd > 0 ? (uint32_t)(((int64_t)Kd * 1024 + Nd / 2) / Nd) : es_i;
+                    if (narrow) {                               // sums of <= 127 values <= 255: the numerators fit 32 bits
+                        es_i = ((uint32_t)Ks * 1024u + (uint32_t)Ns / 2u) / (uint32_t)Ns;
+                        ed_i = Nd > 0 ? ((uint32_t)Kd * 1024u + (uint32_t)Nd / 2u) / (uint32_t)Nd : es_i;
+                    } else {
+                        es_i = (uint32_t)(((int64_t)Ks * 1024 + Ns / 2) / Ns);
+                        ed_i = Nd > 0 ? (uint32_t)(((int64_t)Kd * 1024 + Nd / 2) / Nd) : es_i;
+                    }
                 }
                 if (lane == 0) { es[i] = (uint16_t)es_i; ed[i] = (uint16_t)ed_i; }
                 pl += m;

@@ -123,7 +123,7 @@ static void check_classes(size_t smem_optin) {
         if (kCluster[k].nmax * cc_fresh_g(kCluster[k].nt, kCluster[k].per) > kCluster[k].nt) throw std::logic_error("cluster class table: fresh-cost lanes");
     }
     if (kCluster[N_CLUSTER - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
-    for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax) > smem_optin) throw std::logic_error("score class table");
+    for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax, kScore[k].nt) > smem_optin) throw std::logic_error("score class table");
 }
 
 static Ctx* get_ctx(int device) {
@@ -510,7 +510,7 @@ struct Pipeline {
             int first, len; range_of(k ? kScore[k - 1].nmax + 1 : 1, kScore[k].nmax, first, len);
             if (!len) continue;
             const int nt = kScore[k].nt;
-            const size_t smem = cs_smem_bytes(kScore[k].nmax);
+            const size_t smem = cs_smem_bytes(kScore[k].nmax, kScore[k].nt);
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, 2048 / nt), (228 * 1024) / (smem + 1024)));
             const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
             score_launch<BITS>(nt, kScore[k].kpl, grid, smem, st, d, dv_order + first, len, kScore[k].nmax, counters + 8 + k); n_launches += 1;

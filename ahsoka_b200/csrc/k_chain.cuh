@@ -37,7 +37,7 @@
 
 namespace ahs {
 
-constexpr int CC_MAXN = 128;
+constexpr int CC_MAXN = 160;
 constexpr int32_t CC_FORB = -0x7fffffff;          // forbidden edge inside this kernel (-CC_FORB is representable)
 constexpr uint32_t CC_POS = 1u << 31;             // slot flag: weight > 0 (sign bit: see CCBest::consider)
 constexpr uint32_t CC_FLAG = 1u << 17;            // slot flag: edge was forbidden in a round (tentatively, then for good)
@@ -107,7 +107,7 @@ __device__ __forceinline__ int cc_min_key(int mine, int32_t* cell, int tid, int&
 }
 
 // shared-memory footprint of the scoring kernel
-constexpr int CS_WARP_KEYS = 128;          // per-warp scratch of the rate sort: the partners of one read, compacted (<= CC_MAXN - 1)
+constexpr int CS_WARP_KEYS = 160;          // per-warp scratch of the rate sort: the partners of one read, compacted (<= CC_MAXN - 1)
 __host__ __device__ inline size_t cs_smem_bytes(int nmax, int nt) {
     return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15) + (size_t)(nt / 32) * CS_WARP_KEYS * 8;
 }
@@ -161,6 +161,7 @@ template <int KPL, class T, int N_SHIFT, int MASK>
 __device__ __forceinline__ void cs_pool_any(const T* __restrict__ ws, int m, int cut, int lane, int& Ks, int& Ns, int& Kd, int& Nd) {
     if (m <= 32) cs_pool<1, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
     else if (KPL >= 2 && m <= 64) cs_pool<(KPL >= 2 ? 2 : 1), T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+    else if (KPL >= 8 && m <= 128) cs_pool<(KPL >= 8 ? 4 : 1), T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
     else cs_pool<KPL, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
 }
 
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
                 uint32_t es_i = 0, ed_i = 0;
                 if (m > 0) {
                     Ks = warp_sum_i32(Ks); Ns = warp_sum_i32(Ns); Kd = warp_sum_i32(Kd); Nd = warp_sum_i32(Nd);
-                    if (narrow) {                               // sums of <= 127 values <= 255: the numerators fit 32 bits
+                    if (narrow) {                               // sums of < CC_MAXN values <= 255: the numerators fit 32 bits
                         es_i = ((uint32_t)Ks * 1024u + (uint32_t)Ns / 2u) / (uint32_t)Ns;
                         ed_i = Nd > 0 ? ((uint32_t)Kd * 1024u + (uint32_t)Nd / 2u) / (uint32_t)Nd : es_i;
                     } else {
@@ -299,7 +300,7 @@ __host__ __device__ constexpr int cc_min_blocks(int nt, int per) {
 
 // lanes that share one node x in the fresh-cost pass of a merge (threads / G >= largest n of the block size's classes)
 __host__ __device__ constexpr int cc_fresh_g(int nt, int per = 8) { return per > 8 ? (nt <= 64 ? 1 : nt < 512 ? 2 : 4) : nt <= 32 ? 1 : nt <= 192 ? 2 : nt <= 768 ? 4 : 8; }
-static_assert(CC_MAXN <= 128, "k_cluster_chain walks rows in four 32-lane strides");
+static_assert(CC_MAXN <= 160, "k_cluster_chain walks rows in five 32-lane strides");
 
 // ------------------------------------------------------------------------------------------------
 // cluster editing of one chain per block (rule R2)
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
         scal = (int32_t*)p; p += 64;                  // [0] active nodes, [1] edges flagged in the round, [3] work item
         alist = p; p += nmax; apos = p; p += nmax; label = p; p += nmax; active = p; p += nmax; nodefl = p; p += nmax;
     }
+    constexpr bool WIDE5 = NT == 1024 && PER > 8;      // the classes above 128 reads: rows are walked in five 32-lane strides
     int phase = 0, kphase = 0;
     uint32_t key[PER]; int F[PER], P[PER];
     int32_t* scr = scratch + ((size_t)blockIdx.x * NW + wid) * (32 * PER * 3);       // this warp's packing area (global, L2)
@@ -550,7 +552,7 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                 for (int x = wid; x < n; x += NW) {
                     if (!nodefl[x]) continue;
                     const int32_t* rx = W + x * ns;
-                    int g0 = 0, g1 = 0, g2 = 0, g3 = 0;            // t = lane, lane + 32, lane + 64, lane + 96  (n <= 128)
+                    int g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0;    // t = lane, lane + 32, ..., lane + 128  (n <= 160)
                     for (int m = 0; m < mw; m++)
                         for (uint32_t bits = fmask[x * mw + m]; bits; bits &= bits - 1) {      // warp-uniform
                             const int bb = m * 32 + __ffs(bits) - 1;
@@ -560,12 +562,14 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                             if (lane + 32 < n) g1 += max(max(rb[lane + 32], 0) + old, 0);
                             if (lane + 64 < n) g2 += max(max(rb[lane + 64], 0) + old, 0);
                             if (lane + 96 < n) g3 += max(max(rb[lane + 96], 0) + old, 0);
+                            if (WIDE5 && lane + 128 < n) g4 += max(max(rb[lane + 128], 0) + old, 0);
                         }
                     int32_t* dx = D + x * ns;
                     if (lane < n) dx[lane] = g0;
                     if (lane + 32 < n) dx[lane + 32] = g1;
                     if (lane + 64 < n) dx[lane + 64] = g2;
                     if (lane + 96 < n) dx[lane + 96] = g3;
+                    if (WIDE5 && lane + 128 < n) dx[lane + 128] = g4;
                 }
                 __syncthreads();
                 // the forbidden edges leave (their old weight is parked in D[x][y], which nobody else reads), the icp of

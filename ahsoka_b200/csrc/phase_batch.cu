@@ -83,15 +83,16 @@ static Ctx* g_ctx[64] = {nullptr};
 struct ClusterClass { int nmax, nt, per; };
 static const ClusterClass kCluster[] = {{16, 32, 8}, {23, 32, 8}, {28, 64, 8}, {32, 64, 8}, {36, 96, 8}, {39, 96, 8}, {42, 128, 8}, {45, 128, 8},
                                     {50, 192, 8}, {55, 192, 8}, {60, 256, 8}, {64, 256, 8}, {71, 256, 12}, {78, 256, 12}, {85, 512, 8}, {91, 512, 8},
-                                    {101, 768, 8}, {111, 768, 8}, {120, 1024, 8}, {128, 1024, 8}};
+                                    {101, 768, 8}, {111, 768, 8}, {120, 1024, 8}, {128, 1024, 8},
+                                    {136, 1024, 9}, {148, 1024, 11}, {160, 1024, 13}};
 constexpr int N_CLUSTER = (int)(sizeof(kCluster) / sizeof(kCluster[0]));
 // Scoring: (largest n, threads per block, sort keys per lane)
 struct ScoreClass { int nmax, nt, kpl; };
-static const ScoreClass kScore[] = {{32, 64, 1}, {48, 128, 2}, {64, 128, 2}, {96, 256, 4}, {128, 256, 4}};
+static const ScoreClass kScore[] = {{32, 64, 1}, {48, 128, 2}, {64, 128, 2}, {96, 256, 4}, {128, 256, 4}, {160, 256, 8}};
 constexpr int N_SCORE = (int)(sizeof(kScore) / sizeof(kScore[0]));
 
-#define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8) X(256, 12)
-#define AHS_FOR_EACH_SC(X) X(64, 1) X(128, 2) X(256, 4)
+#define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8) X(256, 12) X(1024, 9) X(1024, 11) X(1024, 13)
+#define AHS_FOR_EACH_SC(X) X(64, 1) X(128, 2) X(256, 4) X(256, 8)
 static void chain_kernel_attributes(size_t optin) {
 #define X(NT, PER) CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
                    CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -121,6 +122,7 @@ static void check_classes(size_t smem_optin) {
         if (cc_smem_bytes(kCluster[k].nmax, kCluster[k].nt) > smem_optin) throw LimitFail{"device shared memory too small for the cluster-editing classes"};
         if ((int64_t)kCluster[k].nmax * (kCluster[k].nmax - 1) / 2 > (int64_t)kCluster[k].per * kCluster[k].nt) throw std::logic_error("cluster class table: slots");
         if (kCluster[k].nmax * cc_fresh_g(kCluster[k].nt, kCluster[k].per) > kCluster[k].nt) throw std::logic_error("cluster class table: fresh-cost lanes");
+        if (kCluster[k].nmax > 128 && !(kCluster[k].nt == 1024 && kCluster[k].per > 8)) throw std::logic_error("cluster class table: classes above 128 reads need the five-stride kernels");
     }
     if (kCluster[N_CLUSTER - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
     for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax, kScore[k].nt) > smem_optin) throw std::logic_error("score class table");

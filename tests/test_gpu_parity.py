@@ -25,10 +25,10 @@ def test_diploid_small_chains(seed):
     assert got.n_chains_ok > 30
 
 
-@pytest.mark.parametrize("mean_len,n_chains,seed", [(80, 30, 71), (140, 12, 72)])
+@pytest.mark.parametrize("mean_len,n_chains,seed", [(80, 30, 71), (110, 40, 74), (140, 12, 72)])
 def test_diploid_mid_and_big_chains(mean_len, n_chains, seed):
-    # ~100 and ~180 final reads per chain: the large shared-memory classes of the fused kernel and,
-    # above 166 reads, the HBM-resident scoring / cluster-editing path
+    # ~100, ~145 and ~180 final reads per chain: the large shared-memory classes (up to 160 reads, 1024 threads with
+    # 9-13 pair slots each) and, above, the HBM-resident scoring / cluster-editing path
     got = _check(synth.generate(synth.params(2, n_chains, 1, mean_len, depth=30.0, seed=seed)))
     assert got.n_chains_ok == n_chains
 
@@ -37,6 +37,12 @@ def test_long_chains_low_depth_wide_rate_keys():
     # ~400 bubbles, ~70 final reads per chain: shared-memory scoring with the 62-bit rate keys (overlaps may exceed 255)
     got = _check(synth.generate(synth.params(2, 8, 1, 400, depth=4.0, seed=73)))
     assert got.n_chains_ok == 8
+
+
+def test_cfg3_sample_triploid_chains_up_to_150_reads():
+    got = _check(synth.generate(synth.config("cfg3", 0.01)))
+    assert got.n_chains_ok > 150
+    assert int(np.diff(got.read_off).max()) > 128
 
 
 def test_cfg2_sample():

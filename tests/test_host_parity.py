@@ -329,3 +329,28 @@ def test_malformed_gfa_fails_loudly_where_the_reference_dies(kind):
         open(os.path.join(d, "g.gfa"), "w").write(MALFORMED_GFA[kind])
         r = subprocess.run([EXE, "only-bubbles", "-g", "g.gfa", "-o", "out"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=20)
     assert r.returncode == 66 and b"g.gfa:" in r.stderr
+
+
+def _cli_files(exe, td, tag, gfa_text, gaf_bytes, ploidy):
+    d = os.path.join(td, tag)
+    os.makedirs(d)
+    open(os.path.join(d, "g.gfa"), "w").write(gfa_text)
+    open(os.path.join(d, "reads.gaf"), "wb").write(gaf_bytes)
+    env = dict(os.environ, AHSOKA_PLOIDY=str(ploidy))
+    env.pop("AHSOKA_HOST", None)
+    r = subprocess.run([exe, "phase", "-g", "g.gfa", "-a", "reads.gaf", "-o", "out", "-t", "1"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout, open(os.path.join(d, "out-result.txt"), "rb").read(), open(os.path.join(d, "out-bubbleinfo.txt"), "rb").read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ploidy,seed", [(2, 411), (3, 412), (4, 413)])
+def test_b200_cli_equals_oracle_cli_on_polyploid_graphs(ploidy, seed):
+    # the whole drop-in (native host stages + CUDA library) against the same host with the CPU oracle behind the C ABI
+    from ahsoka_b200 import synth
+    cuda_exe = os.path.join(ROOT, "oracle", "_ref", "Ahsoka_b200")
+    if not os.path.exists(cuda_exe):
+        pytest.skip("oracle/_ref/Ahsoka_b200 not built")
+    gfa, gaf = _synth_text(synth.params(ploidy, 12, 1, 14, depth=12.0 * ploidy, seed=seed))
+    with tempfile.TemporaryDirectory() as td:
+        assert _cli_files(cuda_exe, td, "cuda", gfa, gaf, ploidy) == _cli_files(EXE, td, "cpu", gfa, gaf, ploidy)

@@ -100,7 +100,8 @@ def simulate(n, pi, pj, pw):
 
 def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.001
-    b = synth.generate(synth.config("cfg2", scale))
+    workload = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+    b = synth.generate(synth.config(workload, scale))
     r = oracle_phase(b)
     tot = []
     for c in range(b.n_chains):
@@ -112,7 +113,7 @@ def main():
         for f in range(f0, f1):
             lo, hi = int(r.cell_off[f]), int(r.cell_off[f + 1])
             rows.append((r.cell_pos[lo:hi], r.cell_allele[lo:hi].astype(np.int32)))
-        sc = oracle_score(rows, 2)
+        sc = oracle_score(rows, int(b.ploidy))
         st, W, active = simulate(n, sc["i"], sc["j"], sc["w"].astype(np.int64))
         k, label = oracle_cluster(n, sc["i"], sc["j"], sc["w"])
         st["nclusters"] = int(active.sum()); st["oracle_k"] = k

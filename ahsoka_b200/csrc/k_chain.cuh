@@ -107,9 +107,9 @@ __device__ __forceinline__ int cc_min_key(int mine, int32_t* cell, int tid, int&
 }
 
 // shared-memory footprint of the scoring kernel
-constexpr int CS_WARP_KEYS = 160;          // per-warp scratch of the rate sort: the partners of one read, compacted (<= CC_MAXN - 1)
+// the last term is the per-warp scratch of the rate sort: the partners of one read, compacted (< nmax keys of 8 bytes)
 __host__ __device__ inline size_t cs_smem_bytes(int nmax, int nt) {
-    return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15) + (size_t)(nt / 32) * CS_WARP_KEYS * 8;
+    return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15) + (size_t)(nt / 32) * nmax * 8;
 }
 
 // ascending bitonic sort of 32*KPL keys (uint32_t or uint64_t) held KPL per lane (element e = s*32 + lane)
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
     int32_t* first = W + (size_t)nmax * ns; int32_t* last = first + nmax;
     int32_t* scal = last + nmax;
     uint16_t* es = (uint16_t*)(scal + 16); uint16_t* ed = es + nmax;
-    uint64_t* wkeys = (uint64_t*)(cc_sm + (((size_t)nmax * ns * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15)) + (size_t)wid * CS_WARP_KEYS;
+    uint64_t* wkeys = (uint64_t*)(cc_sm + (((size_t)nmax * ns * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15)) + (size_t)wid * nmax;
     int64_t pairs_total = 0;
     while (true) {
         __syncthreads();

@@ -354,3 +354,26 @@ def test_b200_cli_equals_oracle_cli_on_polyploid_graphs(ploidy, seed):
     gfa, gaf = _synth_text(synth.params(ploidy, 12, 1, 14, depth=12.0 * ploidy, seed=seed))
     with tempfile.TemporaryDirectory() as td:
         assert _cli_files(cuda_exe, td, "cuda", gfa, gaf, ploidy) == _cli_files(EXE, td, "cpu", gfa, gaf, ploidy)
+
+
+def test_reader_thread_count_does_not_change_the_batch():
+    # a GAF above 1 MB is parsed in line-aligned slabs on several threads and merged in file order: same batch, same side file
+    from ahsoka_b200 import synth
+    gfa, gaf = _synth_text(synth.params(2, 60, 1, 30, depth=25.0, dup_lines=200, seed=515))
+    assert len(gaf) > (1 << 20)
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for t in (2, 3, 7):
+            d = os.path.join(td, "t%d" % t)
+            os.makedirs(d)
+            open(os.path.join(d, "g.gfa"), "w").write(gfa)
+            open(os.path.join(d, "reads.gaf"), "wb").write(gaf)
+            env = dict(os.environ, AHSOKA_DUMP_BATCH=os.path.join(d, "batch.bin"))
+            env.pop("AHSOKA_HOST", None)
+            r = subprocess.run([EXE, "phase", "-g", "g.gfa", "-a", "reads.gaf", "-o", "out", "-t", str(t)], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, env=env)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append((open(os.path.join(d, "batch.bin"), "rb").read(), open(os.path.join(d, "reads-alignment_identities.txt"), "rb").read(),
+                         open(os.path.join(d, "out-result.txt"), "rb").read()))
+        ref = _run(td, "ref", gfa, gaf, "reference")
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == (ref["batch.bin"], ref["reads-alignment_identities.txt"], ref["out-result.txt"])

@@ -669,8 +669,16 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
         if (const char* e = getenv("AHS_CHUNKS")) n_chunks = std::max(1, std::min(N_LANES, atoi(e)));       // tuning / debugging
     }
     std::vector<int64_t> cut(n_chunks + 1, 0); cut[n_chunks] = C;
+    // the first chunk is the smallest: nothing runs under its upload, and it only has to cover the next chunk's
+    std::vector<double> frac(n_chunks + 1, 1.0);
+    for (int k = 0; k <= n_chunks; k++) frac[k] = (double)k / n_chunks;
+    if (n_chunks == 3) { frac[1] = 0.12; frac[2] = 0.53; }
+    if (const char* e = getenv("AHS_CUTS")) {                // tuning / debugging: "0.2,0.6"
+        const char* p = e;
+        for (int k = 1; k < n_chunks && *p; k++) { frac[k] = std::min(1.0, std::max(frac[k - 1], atof(p))); while (*p && *p != ',') p++; if (*p == ',') p++; }
+    }
     for (int k = 1; k < n_chunks; k++) {
-        const int64_t target = sz.NEN / n_chunks * k;
+        const int64_t target = (int64_t)((double)sz.NEN * frac[k]);
         int64_t lo = cut[k - 1], hi = C;                  // first chain whose entries start at or after the target
         while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (in->enode_off[in->entry_off[mid]] >= target) hi = mid; else lo = mid + 1; }
         cut[k] = lo;

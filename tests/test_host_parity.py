@@ -104,6 +104,10 @@ def _quirky_gaf(lines):
             g = list(f)
             g[5] = g[5].replace(b"utg00", b"u", 1)                      # other spelling, same raw id (:48-54)
             out.append(b"\t".join(g))
+        if i % 31 == 0:
+            g = list(f)
+            g[5] = g[5] + lines[(i * 7 + 11) % n].split(b"\t")[5] + g[5]    # one line through several chains, one of them twice
+            out.append(b"\t".join(g))
         if i % 29 == 0:
             g = list(f)
             g[15] = b"id:f:9.3e-1"

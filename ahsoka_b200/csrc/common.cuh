@@ -26,6 +26,9 @@ __device__ __forceinline__ uint32_t hash64(uint64_t k) {
     return (uint32_t)k;
 }
 
+// slot of a node id in an open-addressing table of mask + 1 = 2^k >= 4 slots: Fibonacci hashing (the top k bits of x * 2^32/phi);
+// consecutive ids — the usual numbering of a chain's nodes — land far apart
+__device__ __forceinline__ uint32_t hash_slot(uint32_t x, uint32_t mask) { return (x * 0x9E3779B1u) >> __clz(mask); }
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {      // murmur3 finaliser
     x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
     return x;

@@ -109,7 +109,7 @@ __global__ void k_build_triggers(DB d) {
         const uint32_t trig = (uint32_t)(len >= 3 ? d.anode[o + 1] : d.anode[o]);
         unsigned long long* tab = d.hslots + d.hoff[c];
         const uint32_t mask = d.hmaskc[c];
-        uint32_t slot = hash32(trig) & mask;
+        uint32_t slot = hash_slot(trig, mask);
         while (true) {
             const unsigned long long claimed = (0xfffffffeull << 32) | trig;          // head = -2: no allele linked yet
             const unsigned long long prev = atomicCAS(&tab[slot], SLOT_EMPTY, claimed);
@@ -146,7 +146,7 @@ __device__ __forceinline__ bool grp_entry_has(const int32_t* __restrict__ nodes,
 // nodes, :495-548).  Common case, decided by the lane alone: a 3-node path whose end nodes are the neighbours of
 // the trigger in the alignment.  Everything else is decided by the whole group scanning the entry.
 template <int G>
-__global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t e_end) {
+__global__ void __launch_bounds__(256, 6) k_project(DB d, int64_t e_begin, int64_t e_end) {
     AHS_BAIL_ON_ERR(d);
     const unsigned gm = grp_mask<G>();
     const int lane = lane_id(), gl = lane % G;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) k_project(DB d, int64_t e_begin, int64_t 
                 has_prev = x > 0; has_next = x + 1 < L;
                 if (has_prev) prev = __ldg(nodes + x - 1);
                 if (has_next) next = __ldg(nodes + x + 1);
-                uint32_t slot = hash32((uint32_t)v) & mask;
+                uint32_t slot = hash_slot((uint32_t)v, mask);
                 while (true) {
                     const unsigned long long sl = tab[slot];
                     if (sl == SLOT_EMPTY) break;

@@ -283,13 +283,13 @@ struct Pipeline {
         }
         sz.M = acc;
         d.mrow_off = (int64_t*)up_pinned(h_mrow_off.data(), C);
-        // per-chain trigger tables: power of two >= 2 x alleles of the chain
+        // per-chain trigger tables: power of two >= 4 x alleles of the chain (most probes are misses: they end at the first empty slot)
         std::vector<int64_t> hoff(C); std::vector<uint32_t> hmaskc(C);
         h_slots = 0;
         for (int64_t c = 0; c < C; c++) {
             const int64_t nal = in->allele_off[in->bubble_off[c + 1]] - in->allele_off[in->bubble_off[c]];
             if (nal < 0 || nal > sz.NA) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
-            int64_t cap = 4; while (cap < 2 * nal) cap <<= 1;
+            int64_t cap = 4; while (cap < 4 * nal) cap <<= 1;
             hoff[c] = h_slots; hmaskc[c] = (uint32_t)(cap - 1); h_slots += cap;
         }
         d.hoff = up_pinned(hoff.data(), C); d.hmaskc = up_pinned(hmaskc.data(), C);

@@ -26,6 +26,7 @@ __device__ __forceinline__ uint32_t hash64(uint64_t k) {
     return (uint32_t)k;
 }
 
+constexpr int CH_HAS_UNIV = 1 << 16;       // ch_flags bit: some bubble of the chain has an allele path of <= 2 nodes (SURVEY A#9)
 // slot of a node id in an open-addressing table of mask + 1 = 2^k >= 4 slots: Fibonacci hashing (the top k bits of x * 2^32/phi);
 // consecutive ids — the usual numbering of a chain's nodes — land far apart
 __device__ __forceinline__ uint32_t hash_slot(uint32_t x, uint32_t mask) { return (x * 0x9E3779B1u) >> __clz(mask); }

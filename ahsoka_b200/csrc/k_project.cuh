@@ -105,7 +105,7 @@ __global__ void k_build_triggers(DB d) {
         // simple-path flag << 31, end nodes, stage-A rank
         d.arec[ga] = make_int4((int)((uint32_t)(gb - d.bubble_off[c]) | ((uint32_t)a << 20) | (len == 3 ? 0x80000000u : 0u)),
                                len == 3 ? d.anode[o] : 0, len == 3 ? d.anode[o + 2] : 0, d.rankA[gb]);
-        if (len <= 2) atomicMin(&d.bubble_univ[gb], (uint32_t)a);          // no inner node: matches every entry (A#9)
+        if (len <= 2) { atomicMin(&d.bubble_univ[gb], (uint32_t)a); atomicOr(&d.ch_flags[c], CH_HAS_UNIV); }   // no inner node: matches every entry (A#9)
         const uint32_t trig = (uint32_t)(len >= 3 ? d.anode[o + 1] : d.anode[o]);
         unsigned long long* tab = d.hslots + d.hoff[c];
         const uint32_t mask = d.hmaskc[c];
@@ -310,28 +310,30 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
         const uint32_t fe = d.first_entry[r];
         const bool has_entry = fe != 0xffffffffu;
         const bool hg = d.has_good[r] != 0;
+        const bool univ = (d.ch_flags[c] & CH_HAS_UNIV) != 0;              // rare: a bubble with an allele path of <= 2 nodes
         // creation triple: minimum (position, allele, entry) over all matches, universal alleles included
         uint64_t ck = d.create_key[r];
-        if (has_entry) for (int b = gl; b < T; b += G) {
+        if (has_entry && univ) for (int b = gl; b < T; b += G) {
             const uint32_t u = d.bubble_univ[b0g + b];
             if (u != 0xffffffffu) { uint64_t k = make_key((uint32_t)b, u, fe); ck = k < ck ? k : ck; }
         }
         ck = grp_min_u64<G>(ck, gm);
         const int bc = (ck == KEY_NONE) ? INT32_MAX : (int)(ck >> 40);
         int nv = 0, last = -1;
+        uint32_t cov = 0;                                                   // this lane's covered positions b = gl + G j, j < 32
         if (bc < T) {
             const int ac = (int)((ck >> 32) & 0xff);
             for (int b = gl; b < B; b += G) {
                 uint32_t code = 0;
                 if (b < T) {
                     uint32_t m = mrow[b] & 0x7fffu;
-                    const uint32_t u = d.bubble_univ[b0g + b];
+                    const uint32_t u = univ ? d.bubble_univ[b0g + b] : 0xffffffffu;
                     if (u != 0xffffffffu && hg) m |= 1u << u;
                     if (b == bc) code = (uint32_t)ac + 1u;
                     else if (m) code = (uint32_t)__ffs((int)m);             // lowest set bit = first matching allele
                 }
                 mrow[b] = (uint16_t)code;
-                if (code) { nv++; last = max(last, b); }
+                if (code) { nv++; last = max(last, b); if (b < 32 * G) cov |= 1u << (b / G); }
             }
             nv = __reduce_add_sync(gm, nv); last = __reduce_max_sync(gm, last);
         }
@@ -341,7 +343,10 @@ __global__ void __launch_bounds__(256) k_read_rows(DB d) {
             pass = nv > 1 && mapq >= 93;                                    // :270
         }
         __syncwarp(gm);                                                     // the group's codes are written
-        if (pass) for (int b = gl; b < T; b += G) if (mrow[b]) d.poscov[b0g + b] = 1;
+        if (pass) {
+            for (uint32_t m = cov; m; m &= m - 1) d.poscov[b0g + gl + G * (__ffs((int)m) - 1)] = 1;   // codes are only set below T
+            for (int b = gl + 32 * G; b < T; b += G) if (mrow[b]) d.poscov[b0g + b] = 1;
+        }
         if (gl == 0) {
             d.rd_nv[r] = nv; d.rd_first[r] = bc; d.rd_last[r] = last; d.rd_mapq[r] = mapq; d.rd_pass[r] = pass ? 1 : 0;
             d.create_key[r] = ck;

@@ -225,3 +225,38 @@ def test_chunked_call_is_result_identical(chunks, monkeypatch):
     want = oracle_phase(b, os.cpu_count() or 1)
     monkeypatch.setenv("AHS_CHUNKS", chunks)
     assert not api.phase_batch(b).diff(want)
+
+
+def test_deletion_allele_matches_every_entry():
+    # allele path of two nodes (no inner node): stage B matches it for every entry of the chain (SURVEY A#9); same hand-made
+    # chain as tests/test_oracle_cpu.py, alone and next to ordinary chains (the per-chain "has universal allele" flag)
+    from ahsoka_b200.api import Batch
+    anode = [1, 2, 4, 1, 3, 4,   4, 5, 7, 7, 4,   7, 8, 10, 7, 9, 10]
+    anode_off = [0, 3, 6, 9, 11, 14, 17]
+    allele_off = [0, 2, 4, 6]
+    reads = [[1, 2, 4, 5, 7, 8, 10], [1, 3, 4, 7, 9, 10], [1, 2, 4], [7, 8, 10, 4, 5], [1, 3, 4, 5, 7, 9, 10]]
+    enode = sum(reads, [])
+    enode_off = np.cumsum([0] + [len(x) for x in reads])
+    b = Batch(2, [0], [0, 3], allele_off, anode_off, anode, [2, 1, 0], [0, len(reads)], [0, len(reads)], enode_off, enode,
+              list(range(len(reads))), [0.99] * len(reads))
+    got = _check(b)
+    assert got.status[0] == 0
+    # the same chain between two synthetic ones
+    s = synth.generate(synth.params(2, 2, 1, 12, depth=20.0, seed=333))
+    nb, na, nan_, nr, ne, nen = (int(s.bubble_off[1]), int(s.allele_off[s.bubble_off[1]]), int(s.anode_off[s.allele_off[s.bubble_off[1]]]),
+                                 int(s.read_off[1]), int(s.entry_off[1]), int(s.enode_off[s.entry_off[1]]))
+    cat = np.concatenate
+    mixed = Batch(2, [int(s.chain_id[0]), 777, int(s.chain_id[1])],
+                  cat([s.bubble_off[:2], [nb + 3], s.bubble_off[2:] + 3]),
+                  cat([s.allele_off[:nb + 1], na + np.array(allele_off[1:]), s.allele_off[nb + 1:] + 6]),
+                  cat([s.anode_off[:na + 1], nan_ + np.array(anode_off[1:]), s.anode_off[na + 1:] + len(anode)]),
+                  cat([s.anode[:nan_], np.array(anode) + 10 ** 6, s.anode[nan_:]]),
+                  cat([s.stage_a_order[:nb], [2, 1, 0], s.stage_a_order[nb:]]),
+                  cat([s.read_off[:2], [nr + len(reads)], s.read_off[2:] + len(reads)]),
+                  cat([s.entry_off[:2], [ne + len(reads)], s.entry_off[2:] + len(reads)]),
+                  cat([s.enode_off[:ne + 1], nen + enode_off[1:], s.enode_off[ne + 1:] + len(enode)]),
+                  cat([s.enode[:nen], np.array(enode) + 10 ** 6, s.enode[nen:]]),
+                  cat([s.entry_read[:ne], np.arange(len(reads)), s.entry_read[ne:]]),
+                  cat([s.entry_identity[:ne], np.full(len(reads), 0.99, dtype=np.float32), s.entry_identity[ne:]]))
+    got = _check(mixed)
+    assert list(got.status) == [0, 0, 0]

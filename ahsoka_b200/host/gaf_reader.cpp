@@ -251,39 +251,78 @@ int read_gaf(const std::string& filename, const Graph& graph, GafStore& st, std:
     lap("identities_file", t0);
     if (rc) return rc;
 
-    // merge in file order: intern names, concatenate, list each line once per chain it touches
-    size_t n_lines = 0, n_nodes = 0;
-    for (auto& s : slab) { n_lines += s.name.size(); n_nodes += s.node_raw.size(); }
-    st.name_id.reserve(n_lines); st.identity.reserve(n_lines); st.startpos.reserve(n_lines); st.endpos.reserve(n_lines);
-    st.node_off.reserve(n_lines + 1); st.node_raw.reserve(n_nodes);
-    std::unordered_map<std::string_view, int32_t> intern;
-    intern.reserve(n_lines);
-    std::vector<Tok> path;
-    path.reserve(n_lines);
-    for (auto& s : slab) {
-        const int64_t base = (int64_t)st.node_raw.size();
-        st.node_raw.insert(st.node_raw.end(), s.node_raw.begin(), s.node_raw.end());
-        for (size_t i = 0; i < s.name.size(); i++) {
-            const int32_t line = (int32_t)st.name_id.size();
-            auto ins = intern.emplace(std::string_view(s.name[i].p, s.name[i].n), (int32_t)st.names.size());
-            if (ins.second) st.names.emplace_back(s.name[i].p, s.name[i].n);
-            st.name_id.push_back(ins.first->second);
-            st.identity.push_back(s.identity[i]); st.startpos.push_back(s.start[i]); st.endpos.push_back(s.end[i]);
-            st.node_off.push_back(base + s.node_off[i + 1]);
-            path.push_back(s.path[i]);
-            for (int64_t k = s.chain_off[i]; k < s.chain_off[i + 1]; k++) {
-                std::vector<int32_t>& v = st.by_chain[s.chains[k]];
-                if (!v.empty()) {
-                    const int32_t prev = v.back();
-                    if (st.name_id[prev] == st.name_id[line] && st.identity[prev] == st.identity[line] &&
-                        st.startpos[prev] == st.startpos[line] && st.endpos[prev] == st.endpos[line] &&
-                        same_node_names(path[prev], path[line])) continue;
+    // merge in file order: concatenate, intern names, list each line once per chain it touches.  Every phase runs on
+    // the T threads again: the slabs are copied in place; names are interned by the thread that owns their hash class
+    // (ids are unique, first-appearance order WITHIN an owner, which is all the per-chain read numbering needs); chains are
+    // filled by the thread that owns the chain id, each walking the lines in file order.
+    std::vector<size_t> line_base(T + 1, 0), node_base(T + 1, 0);
+    for (int t = 0; t < T; t++) { line_base[t + 1] = line_base[t] + slab[t].name.size(); node_base[t + 1] = node_base[t] + slab[t].node_raw.size(); }
+    const size_t n_lines = line_base[T], n_nodes = node_base[T];
+    if (n_lines > (size_t)INT32_MAX) { err = filename + ": more than 2^31 alignment lines"; return 65; }
+    st.name_id.resize(n_lines); st.identity.resize(n_lines); st.startpos.resize(n_lines); st.endpos.resize(n_lines);
+    st.node_off.resize(n_lines + 1); st.node_raw.resize(n_nodes);
+    st.node_off[0] = 0;
+    std::vector<Tok> path(n_lines), name_tok(n_lines);
+    std::vector<size_t> name_hash(n_lines);
+    std::vector<int32_t> local_id(n_lines);
+    auto run = [&](auto&& fn) {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; t++) pool.emplace_back([&, t] { fn(t); });
+        fn(0);
+        for (auto& th : pool) th.join();
+    };
+    run([&](int t) {                                          // slab t -> its place in the store
+        Slab& sl = slab[t];
+        const size_t lb = line_base[t], nb = node_base[t];
+        if (!sl.node_raw.empty()) memcpy(&st.node_raw[nb], sl.node_raw.data(), sl.node_raw.size() * sizeof(int32_t));
+        for (size_t i = 0; i < sl.name.size(); i++) {
+            st.identity[lb + i] = sl.identity[i]; st.startpos[lb + i] = sl.start[i]; st.endpos[lb + i] = sl.end[i];
+            st.node_off[lb + i + 1] = (int64_t)nb + sl.node_off[i + 1];
+            path[lb + i] = sl.path[i]; name_tok[lb + i] = sl.name[i];
+            name_hash[lb + i] = std::hash<std::string_view>()(std::string_view(sl.name[i].p, sl.name[i].n));
+        }
+        std::vector<int32_t>().swap(sl.node_raw);
+    });
+    std::vector<std::vector<Tok>> own_names(T);
+    run([&](int t) {                                          // names whose hash class is t
+        std::unordered_map<std::string_view, int32_t> intern;
+        intern.reserve(n_lines / T + 16);
+        for (size_t line = 0; line < n_lines; line++) {
+            if ((int)(name_hash[line] % (size_t)T) != t) continue;
+            auto ins = intern.emplace(std::string_view(name_tok[line].p, name_tok[line].n), (int32_t)own_names[t].size());
+            if (ins.second) own_names[t].push_back(name_tok[line]);
+            local_id[line] = ins.first->second;
+        }
+    });
+    std::vector<size_t> gbase(T + 1, 0);
+    for (int t = 0; t < T; t++) gbase[t + 1] = gbase[t] + own_names[t].size();
+    st.names.resize(gbase[T]);
+    run([&](int t) {
+        for (size_t i = 0; i < own_names[t].size(); i++) st.names[gbase[t] + i].assign(own_names[t][i].p, own_names[t][i].n);
+        for (size_t line = line_base[t]; line < line_base[t + 1]; line++)
+            st.name_id[line] = (int32_t)(gbase[name_hash[line] % (size_t)T] + (size_t)local_id[line]);
+    });
+    for (auto& sl : slab) for (int32_t ch : sl.chains) st.by_chain[ch];       // create the lists; the threads below only look them up
+    run([&](int t) {                                          // chains whose id class is t
+        for (int u = 0; u < T; u++) {
+            const Slab& sl = slab[u];
+            for (size_t i = 0; i + 1 < sl.chain_off.size(); i++) {
+                const int32_t line = (int32_t)(line_base[u] + i);
+                for (int64_t k = sl.chain_off[i]; k < sl.chain_off[i + 1]; k++) {
+                    const int32_t ch = sl.chains[k];
+                    if ((int)((uint32_t)ch % (uint32_t)T) != t) continue;
+                    std::vector<int32_t>& v = st.by_chain.find(ch)->second;
+                    if (!v.empty()) {
+                        const int32_t prev = v.back();
+                        if (st.name_id[prev] == st.name_id[line] && st.identity[prev] == st.identity[line] &&
+                            st.startpos[prev] == st.startpos[line] && st.endpos[prev] == st.endpos[line] &&
+                            same_node_names(path[prev], path[line])) continue;
+                    }
+                    v.push_back(line);
                 }
-                v.push_back(line);
             }
         }
-        Slab().node_raw.swap(s.node_raw);
-    }
+    });
     lap("merge", t0);
     return 0;
 }

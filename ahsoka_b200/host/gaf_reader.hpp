@@ -23,7 +23,7 @@ namespace ahs_host {
 
 struct GafStore {
     // one record per GAF line the reference's reader would have accepted, in file order
-    std::vector<int32_t> name_id;         // interned read name, ids in first-appearance order over the file
+    std::vector<int32_t> name_id;         // interned read name (one id per distinct name; no particular order)
     std::vector<float> identity;          // stof() of the text after the last ':' of token 16
     std::vector<int32_t> startpos, endpos;
     std::vector<int64_t> node_off{0};     // CSR into node_raw

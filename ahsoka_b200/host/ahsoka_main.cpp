@@ -30,6 +30,7 @@
 #include "ahsoka_b200.h"
 
 #include <sys/stat.h>
+#include <unistd.h>
 
 using std::cerr; using std::cout; using std::endl; using std::string;
 typedef std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>> ChainAlleles;
@@ -120,19 +121,29 @@ int main(int argc, char* argv[]) {
     cout << "Step 2: Bubbles read" << endl;
     cout << "Number of bubble chains: " << graph.chains.size() << endl;
     {
+        StageTimer t("bubbleinfo");
         std::ofstream bubblefile(prefix + "-bubbleinfo.txt");
+        // same bytes as polyassembly.cpp:100-110; '\n' instead of endl (one write per buffer instead of one per line)
         for (auto& chain : graph.chains) {     // graph.chains[i].id == i (graph.cpp:351-365): no getChain() scan needed
-            bubblefile << "chain id: " << chain.id << "size: " << chain.bubbles.size() << endl;
+            bubblefile << "chain id: " << chain.id << "size: " << chain.bubbles.size() << '\n';
             for (auto& bubble : chain.bubbles) {
-                bubblefile << "bubble id: " << bubble.id << endl << "node id: ";
+                bubblefile << "bubble id: " << bubble.id << '\n' << "node id: ";
                 bubblefile << bubble.source.node_id << ",";          // Bubble::getNodes() order (graph.cpp:96-104) without copying the nodes
                 for (auto& node : bubble.innerNodes) bubblefile << node.node_id << ",";
                 bubblefile << bubble.sink.node_id << ",";
-                bubblefile << endl;
+                bubblefile << '\n';
             }
         }
     }
-    if (cmd == "only-bubbles") return 0;
+    // every output file is closed by now: leave without running the destructors of the graph (tens of millions of small
+    // allocations, seconds at BASELINE scale); nothing observable depends on them
+    auto leave = [&]() -> int {
+        if (warm.joinable()) warm.join();
+        cout.flush(); cerr.flush(); fflush(nullptr);
+        _exit(0);
+        return 0;
+    };
+    if (cmd == "only-bubbles") return leave();
 
     AlignmentReader alignmentreader;
     ahs_host::GafStore store;
@@ -166,5 +177,5 @@ int main(int argc, char* argv[]) {
     std::mutex g_display_mutex;
     if (ref_host) alignmentsToReadset(alignmentreader, graph, chainpathToAlleles, prefix, false, size_sorting, g_display_mutex);
     else alignmentsToReadset(store, graph, chainpathToAlleles, prefix, false, size_sorting, g_display_mutex);
-    return 0;
+    return leave();
 }

@@ -40,7 +40,7 @@ class BatchOut(C.Structure):
 
 class Limits(C.Structure):
     _fields_ = [("max_ploidy", C.c_int32), ("max_alleles", C.c_int32), ("max_reads_cluster", C.c_int32),
-                ("max_positions", C.c_int32)]
+                ("max_positions", C.c_int32), ("max_clusters_position", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 _I32 = ("chain_id", "anode", "stage_a_order", "enode", "entry_read")
@@ -260,6 +260,8 @@ def load_library(path: str = LIB_PATH):
     lib.ahs_pin_host.restype = C.c_int
     lib.ahs_unpin_host.argtypes = [C.c_void_p]
     lib.ahs_unpin_host.restype = C.c_int
+    lib.ahs_debug_std_sort.argtypes = [i32p, i32p, C.c_int32, C.c_int, C.c_int]
+    lib.ahs_debug_std_sort.restype = C.c_int
     _lib = lib
     return lib
 
@@ -281,6 +283,16 @@ def unpin_batch(batch: Batch) -> None:
         a = getattr(batch, k)
         if a.nbytes:
             lib.ahs_unpin_host(a.ctypes.data)
+
+
+def debug_std_sort(keys, values, descending=False, device=0):
+    """Device replay of libstdc++'s std::sort (comparator on the key only); returns sorted copies."""
+    lib = load_library()
+    k = np.ascontiguousarray(keys, dtype=np.int32).copy(); v = np.ascontiguousarray(values, dtype=np.int32).copy()
+    rc = lib.ahs_debug_std_sort(k.ctypes.data_as(i32p), v.ctypes.data_as(i32p), len(k), int(descending), device)
+    if rc != 0:
+        raise RuntimeError(f"ahs_debug_std_sort failed ({rc}): {lib.ahs_last_error().decode()}")
+    return k, v
 
 
 def limits() -> Limits:

@@ -402,10 +402,51 @@ __device__ void kv_insertion_sort(KV a, int first, int last) {
         } else kv_unguarded_linear_insert<DESC>(a, i);
     }
 }
-// returns false if the depth limit was reached (libstdc++ switches to heapsort: not replayed)
+// std::__adjust_heap + std::__push_heap (bits/stl_heap.h) on the sub-array starting at `first`
 template <bool DESC>
-__device__ bool kv_std_sort(KV a, int n) {
-    if (n <= 1) return true;
+__device__ void kv_adjust_heap(KV a, int first, int hole, int len, int32_t vk, int32_t vv) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (kv_less<DESC>(a.k[first + child], a.k[first + child - 1])) child--;
+        a.k[first + hole] = a.k[first + child]; a.v[first + hole] = a.v[first + child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        a.k[first + hole] = a.k[first + child - 1]; a.v[first + hole] = a.v[first + child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;
+    while (hole > top && kv_less<DESC>(a.k[first + parent], vk)) {
+        a.k[first + hole] = a.k[first + parent]; a.v[first + hole] = a.v[first + parent];
+        hole = parent; parent = (hole - 1) / 2;
+    }
+    a.k[first + hole] = vk; a.v[first + hole] = vv;
+}
+// std::__partial_sort(first, last, last): __heap_select (= __make_heap, the selection loop is empty) + __sort_heap —
+// what __introsort_loop falls back to when its depth limit is used up
+template <bool DESC>
+__device__ void kv_heap_sort(KV a, int first, int last) {
+    const int len = last - first;
+    if (len < 2) return;
+    for (int parent = (len - 2) / 2; ; parent--) {
+        kv_adjust_heap<DESC>(a, first, parent, len, a.k[first + parent], a.v[first + parent]);
+        if (parent == 0) break;
+    }
+    for (int end = last; end - first > 1; ) {
+        --end;
+        const int32_t vk = a.k[end], vv = a.v[end];
+        a.k[end] = a.k[first]; a.v[end] = a.v[first];
+        kv_adjust_heap<DESC>(a, first, 0, end - first, vk, vv);
+    }
+}
+// std::sort(first, last, comp) of libstdc++ (bits/stl_algo.h: __introsort_loop with depth limit 2 lg n, then
+// __final_insertion_sort), heap-sort fall-back included
+template <bool DESC>
+__device__ void kv_std_sort(KV a, int n) {
+    if (n <= 1) return;
     int depth0 = 0; for (int m = n; m > 1; m >>= 1) depth0++;
     depth0 *= 2;
     int stk_first[64], stk_last[64], stk_depth[64]; int sp = 0;
@@ -414,7 +455,7 @@ __device__ bool kv_std_sort(KV a, int n) {
         --sp;
         int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
         while (last - first > 16) {
-            if (depth == 0) return false;
+            if (depth == 0) { kv_heap_sort<DESC>(a, first, last); break; }
             --depth;
             // __move_median_to_first(first, first+1, mid, last-1)
             int mid = first + (last - first) / 2, A = first + 1, Bm = mid, Cc = last - 1;
@@ -437,8 +478,9 @@ __device__ bool kv_std_sort(KV a, int n) {
                 ++lo;
             }
             // recurse on [cut,last), loop on [first,cut): the right part is sorted first, but the
-            // parts are disjoint, so the order of processing does not change the result
-            if (sp < 64) { stk_first[sp] = lo; stk_last[sp] = last; stk_depth[sp] = depth; ++sp; }
+            // parts are disjoint, so the order of processing does not change the result.  The stack
+            // cannot overflow: every push lowers `depth`, so at most depth0 <= 2 * 31 ranges are pending.
+            stk_first[sp] = lo; stk_last[sp] = last; stk_depth[sp] = depth; ++sp;
             last = lo;
         }
     }
@@ -447,7 +489,12 @@ __device__ bool kv_std_sort(KV a, int n) {
         kv_insertion_sort<DESC>(a, 0, 16);
         for (int i = 16; i < n; ++i) kv_unguarded_linear_insert<DESC>(a, i);
     } else kv_insertion_sort<DESC>(a, 0, n);
-    return true;
+}
+
+// diagnostic kernel behind ahs_debug_std_sort: one thread replays std::sort on (key, value) pairs
+__global__ void k_debug_std_sort(int32_t* k, int32_t* v, int n, int desc) {
+    KV a; a.k = k; a.v = v;
+    if (desc) kv_std_sort<true>(a, n); else kv_std_sort<false>(a, n);
 }
 
 __global__ void k_chain_sort(DB d) {
@@ -457,7 +504,7 @@ __global__ void k_chain_sort(DB d) {
         const int n = d.ch_nfinal[c];
         if (n == 0) { d.ch_status[c] = AHS_CHAIN_EMPTY; continue; }            // :279-282
         KV a; a.k = d.okey + d.read_off[c]; a.v = d.ord + d.read_off[c];
-        if (!kv_std_sort<false>(a, n)) d.ch_status[c] = AHS_CHAIN_SORT_FALLBACK;
+        kv_std_sort<false>(a, n);
         // covered positions (ReadSet::get_positions, :317)
     }
 }

@@ -3,6 +3,7 @@
 // result.  No torch, no CPU fallback: without a usable CUDA device every entry point fails.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -26,7 +27,6 @@
 
 namespace ahs {
 
-constexpr int32_t AHS_OUT_MALLOCED = 0x4d414c43;
 static thread_local char g_err[512] = "";
 
 static void set_err(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
@@ -35,6 +35,7 @@ struct CudaFail { cudaError_t e; const char* what; int line; };
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) throw CudaFail{_e, #call, __LINE__}; } while (0)
 struct LimitFail { std::string msg; };
 struct ArgFail { std::string msg; };
+struct PassThrough { int rc; std::string msg; };      // failure of one device thread of a multi-device call, re-raised by the caller
 
 constexpr int MAX_READS_CLUSTER = 8191;        // 13-bit node ids in the slot keys of k_cluster_big
 constexpr int MAX_POSITIONS = 32767;
@@ -51,7 +52,7 @@ struct Pool {
         for (auto& c : chunks) if (c.cap - c.used >= bytes) { void* r = c.p + c.used; c.used += bytes; return r; }
         size_t cap = std::max(bytes, (size_t)(host ? 64 : 256) << 20);
         Chunk c; c.cap = cap; c.used = bytes;
-        if (host) CK(cudaHostAlloc((void**)&c.p, cap, cudaHostAllocDefault)); else CK(cudaMalloc((void**)&c.p, cap));
+        if (host) CK(cudaHostAlloc((void**)&c.p, cap, cudaHostAllocPortable)); else CK(cudaMalloc((void**)&c.p, cap));
         chunks.push_back(c);
         return c.p;
     }
@@ -603,6 +604,7 @@ static int guarded(const char* what, const std::function<void()>& fn) {
     catch (const CudaFail& f) { set_err("%s: CUDA error %d (%s) at %s, line %d", what, (int)f.e, cudaGetErrorString(f.e), f.what, f.line); cudaGetLastError(); return AHS_ERR_CUDA; }
     catch (const LimitFail& f) { set_err("%s: limit exceeded: %s", what, f.msg.c_str()); return AHS_ERR_LIMIT; }
     catch (const ArgFail& f) { set_err("%s: bad argument: %s", what, f.msg.c_str()); return AHS_ERR_ARG; }
+    catch (const PassThrough& f) { set_err("%s: %s", what, f.msg.c_str()); return f.rc; }
     catch (const std::exception& e) { set_err("%s: %s", what, e.what()); return AHS_ERR_INTERNAL; }
 }
 
@@ -627,42 +629,164 @@ struct HostTrace {       // AHS_TRACE=1: wall-clock of the host-side steps of on
     ~HostTrace() { if (on) fprintf(stderr, "[ahs trace]%s\n", line.c_str()); }
 };
 
-// a chunk of consecutive chains as a batch of its own: the big arrays are slices of the caller's (their offsets are
+// a range of consecutive chains as a batch of its own: the big arrays are slices of the caller's (their offsets are
 // rebased on the device after the upload), the three per-chain offset arrays are rebased here
+struct Range { int64_t c0, c1; };
+
 struct ChainView {
     ahs_batch_in v; std::vector<int64_t> bubble_off, read_off, entry_off;
     void make(const ahs_batch_in* in, int64_t c0, int64_t c1) {
-        const int64_t n = c1 - c0, b0 = in->bubble_off[c0], e0 = in->entry_off[c0], a0 = in->allele_off[b0];
+        const int64_t C = in->n_chains, NB = in->bubble_off[C], NE = in->entry_off[C];
+        const int64_t n = c1 - c0, b0 = in->bubble_off[c0], e0 = in->entry_off[c0];
+        // the interior offsets dereferenced below are checked here; everything else is validated on the device
+        const int64_t NA = in->allele_off[NB] , a0 = in->allele_off[b0], a1 = in->allele_off[in->bubble_off[c1]];
+        if (a0 < 0 || a1 < a0 || a1 > NA) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
+        const int64_t NAN_ = in->anode_off[NA], an0 = in->anode_off[a0], an1 = in->anode_off[a1];
+        const int64_t NEN = in->enode_off[NE], en0 = in->enode_off[e0], en1 = in->enode_off[in->entry_off[c1]];
+        if (an0 < 0 || an1 < an0 || an1 > NAN_ || en0 < 0 || en1 < en0 || en1 > NEN) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
         bubble_off.resize(n + 1); read_off.resize(n + 1); entry_off.resize(n + 1);
         for (int64_t c = 0; c <= n; c++) { bubble_off[c] = in->bubble_off[c0 + c] - b0; read_off[c] = in->read_off[c0 + c] - in->read_off[c0]; entry_off[c] = in->entry_off[c0 + c] - e0; }
         v = *in;
         v.n_chains = (int32_t)n; v.chain_id = in->chain_id ? in->chain_id + c0 : nullptr;
         v.bubble_off = bubble_off.data(); v.read_off = read_off.data(); v.entry_off = entry_off.data();
-        v.allele_off = in->allele_off + b0; v.anode_off = in->anode_off + a0; v.anode = in->anode + in->anode_off[a0];
+        v.allele_off = in->allele_off + b0; v.anode_off = in->anode_off + a0; v.anode = in->anode + an0;
         v.stage_a_order = in->stage_a_order ? in->stage_a_order + b0 : nullptr;
-        v.enode_off = in->enode_off + e0; v.enode = in->enode + in->enode_off[e0];
+        v.enode_off = in->enode_off + e0; v.enode = in->enode + en0;
         v.entry_read = in->entry_read + e0; v.entry_identity = in->entry_identity + e0;
     }
 };
 
-// one batch on one device; iters > 0 = resident timing mode.  A call with host output (iters == 0) and a large batch runs
-// as N_LANES chunks of chains, each a pipeline on its own streams: chunk k+1 uploads and projects under the clustering
-// of chunk k, so that most of the H2D time is hidden.
-static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int device, int warmup, int iters) {
-    if (!out) throw ArgFail{"null output"};
+// the output arrays of a call: allocated once the sizes of every range are known, from the page-locked result pool of
+// the call's first device (portable: every device of the call copies its ranges straight into them)
+static void alloc_out(ahs_batch_out* out, Ctx* cx, int64_t C, int p, int64_t NFt, int64_t NPt, int64_t cells) {
+    memset(out, 0, sizeof(*out));
+    out->n_chains = (int32_t)C; out->ploidy = p;
+    out->status = cx->outp.get<int32_t>(C); out->n_clusters = cx->outp.get<int32_t>(C); out->dp_cost = cx->outp.get<double>(C); out->maxpos = cx->outp.get<int32_t>(C);
+    out->read_off = cx->outp.get<int64_t>(C + 1); out->pos_off = cx->outp.get<int64_t>(C + 1);
+    out->read_id = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1)); out->read_mapq = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1));
+    out->read_cluster = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1)); out->cell_off = cx->outp.get<int64_t>(NFt + 1);
+    out->cell_pos = cx->outp.get<int32_t>(std::max<int64_t>(cells, 1)); out->cell_allele = cx->outp.get<uint8_t>(std::max<int64_t>(cells, 1));
+    out->pos = cx->outp.get<int32_t>(std::max<int64_t>(NPt, 1)); out->path = cx->outp.get<int32_t>(std::max<int64_t>(NPt * p, 1));
+    out->hap_allele = cx->outp.get<uint8_t>(std::max<int64_t>(NPt * p, 1));
+    out->read_off[0] = 0; out->pos_off[0] = 0; out->cell_off[0] = 0;
+}
+
+// Everything one device does for one call: its ranges of chains run as pipelines on the context's lanes (range k+1
+// uploads and projects under the clustering of range k, so that most of the H2D time is hidden), then — once the
+// caller has placed every range in the output arrays — the results are copied straight into their slices.
+struct DeviceJob {
+    Ctx* cx = nullptr; int device = -1; const ahs_batch_in* in = nullptr;
+    std::vector<Range> ranges;
+    std::vector<ChainView> views; std::vector<Pipeline> pls; std::vector<Sizes> szs;
+    std::unique_lock<std::mutex> lock;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float acc[8] = {0}, h2d = 0, d2h = 0;
+    int iters = 0; int64_t* h_pairs = nullptr;
     HostTrace tr;
-    Sizes sz = validate(in);
-    tr.mark("validate");
-    Ctx* cx = get_ctx(device);
-    std::lock_guard<std::mutex> g(cx->mu);
-    tr.mark("context");
-    CK(cudaSetDevice(device));
-    if (cx->out_busy) throw ArgFail{"previous ahs_batch_out of this device was not released with ahs_free_out"};
-    CK(cudaDeviceSynchronize());                          // nothing of a failed earlier call is in flight
-    cx->dev.reset(); cx->outp.reset(); cx->pin.reset();
-    if (sz.C == 0) { fill_empty_out(out, cx, in->ploidy); cx->out_busy = true; return; }
-    const int64_t C = sz.C; const int p = in->ploidy;
-    // ---- chunks: equal shares of the alignment nodes (the bulk of the upload)
+
+    void begin(int dev, const ahs_batch_in* in_) {
+        device = dev; in = in_;
+        cx = get_ctx(device);
+        lock = std::unique_lock<std::mutex>(cx->mu);
+        tr.mark("context");
+        CK(cudaSetDevice(device));
+        if (cx->out_busy) throw ArgFail{"previous ahs_batch_out of this device was not released with ahs_free_out"};
+        CK(cudaDeviceSynchronize());                          // nothing of a failed earlier call is in flight
+        cx->dev.reset(); cx->outp.reset(); cx->pin.reset();
+    }
+
+    // phase 1 (ends with sync #1 per range) and phase 2 of every range, enqueued
+    void enqueue(int warmup, int iters_) {
+        iters = iters_;
+        const int n = (int)ranges.size();
+        views.resize(n); pls.resize(n); szs.resize(n);
+        e0 = cx->lanes[0].ev[8]; e1 = cx->lanes[0].ev[9];
+        CK(cudaSetDevice(device));
+        CK(cudaEventRecord(e0, cx->lanes[0].stream));
+        bool first = true;
+        for (int k = 0; k < n; k++) {
+            Pipeline& pl = pls[k];
+            pl.cx = cx; pl.ln = &cx->lanes[k % N_LANES]; pl.early_out = iters == 0;
+            if (n == 1 && ranges[0].c0 == 0 && ranges[0].c1 == in->n_chains) { pl.in = in; pl.sz = validate(in); }
+            else { views[k].make(in, ranges[k].c0, ranges[k].c1); pl.in = &views[k].v; pl.sz = validate(pl.in, true); }
+            szs[k] = pl.sz;
+            if (pl.sz.C == 0) continue;
+            pl.upload();
+            if (first) { CK(cudaEventRecord(e1, pl.ln->stream)); tr.mark("upload_enqueue"); first = false; }
+            pl.alloc_phase1();
+            // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
+            std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
+            const int total = iters > 0 ? warmup + iters : 1;
+            for (int it = 0; it < total; it++) {
+                if (iters > 0) for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
+                pl.run();                                     // ends with phase 2 enqueued; sync #1 inside waited for this range's upload only
+                tr.mark("run_enqueue");
+                if (iters > 0) {
+                    CK(cudaStreamSynchronize(pl.ln->stream));
+                    pl.collect_times();
+                    if (it >= warmup) for (int i = 0; i < 8; i++) acc[i] += pl.ms[i];
+                }
+            }
+        }
+        if (first) CK(cudaEventRecord(e1, cx->lanes[0].stream));
+    }
+
+    // copies of every range into its slices of `out`; f_base / q_base / cell_base: final reads, positions and cells of
+    // the ranges that precede range k in chain order (over all devices of the call)
+    void copy_out(ahs_batch_out* out, const int64_t* f_base, const int64_t* q_base, const int64_t* cell_base) {
+        const int n = (int)ranges.size(); const int p = in->ploidy;
+        CK(cudaSetDevice(device));
+        h_pairs = cx->pin.get<int64_t>(std::max(n, 1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&h2d, e0, e1));
+        cudaEvent_t d0 = cx->lanes[0].ev[8];
+        CK(cudaEventRecord(d0, cx->lanes[0].stream2));
+        for (int k = 0; k < n; k++) {
+            h_pairs[k] = 0;
+            if (szs[k].C == 0) continue;
+            Pipeline& pl = pls[k];
+            const int64_t c0 = ranges[k].c0, f = f_base[k], q = q_base[k], cells = cell_base[k];
+            Pipeline::Slices sl{out->status + c0, out->read_id + f, out->read_mapq + f, out->read_cluster + f, out->cell_pos + cells, out->n_clusters + c0,
+                                out->pos + q, out->path + q * p, out->maxpos + c0, out->cell_off + f, out->cell_allele + cells, out->hap_allele + q * p,
+                                out->dp_cost + c0, false};
+            for (int64_t c = 0; c < szs[k].C; c++) { out->read_off[c0 + c + 1] = f + pl.h_frow_off[c + 1]; out->pos_off[c0 + c + 1] = q + pl.h_pos_off[c + 1]; }
+            cudaStream_t ms = pl.early_out ? pl.ln->stream2 : pl.ln->stream;
+            if (pl.early_out) CK(cudaStreamWaitEvent(ms, pl.ln->ev_cells, 0));
+            if (cells && pl.d.NF) { k_rebase<<<grid_for(pl.d.NF + 1, 256, cx->sms), 256, 0, ms>>>(pl.d.cell_off, pl.d.NF + 1, -cells); CK(cudaGetLastError()); }
+            pl.copy_matrix(sl, ms);
+            pl.copy_rest(sl, h_pairs + k);
+        }
+        tr.mark("copies_enqueue");
+        for (int k = 0; k < std::min(n, N_LANES); k++) { CK(cudaStreamSynchronize(cx->lanes[k].stream2)); CK(cudaStreamSynchronize(cx->lanes[k].stream)); }
+        tr.mark("run_sync");
+        {
+            auto mb = [](const Pool& p, bool used) { double t = 0; for (auto& c : p.chunks) t += (double)(used ? c.used : c.cap); return t / 1048576.0; };
+            tr.note("dev_used_mb", mb(cx->dev, true)); tr.note("dev_cap_mb", mb(cx->dev, false));
+            tr.note("pin_used_mb", mb(cx->pin, true)); tr.note("out_used_mb", mb(cx->outp, true));
+        }
+        CK(cudaEventRecord(e1, cx->lanes[0].stream)); CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&d2h, d0, e1));
+    }
+
+    // stage times of this device: summed over its ranges (resident mode: averaged over the timed iterations)
+    void times(float* ms8, int& launches) {
+        const int n = (int)ranges.size();
+        for (int i = 0; i < 8; i++) ms8[i] = 0;
+        launches = 0;
+        if (iters > 0) { for (int i = 0; i < 8; i++) ms8[i] = acc[i] / iters; for (auto& pl : pls) launches += pl.n_launches; return; }
+        int firstk = -1, last = -1;
+        for (int k = 0; k < n; k++) if (szs[k].C) {
+            if (n <= N_LANES) { pls[k].collect_times(); for (int i = 0; i < 6; i++) ms8[i] += pls[k].ms[i]; }      // a lane's events are re-recorded by a later range
+            launches += pls[k].n_launches;
+            if (firstk < 0) firstk = k; last = k;
+        }
+        if (firstk >= 0 && n <= N_LANES) { float t = 0; CK(cudaEventElapsedTime(&t, pls[firstk].ln->ev[0], pls[last].ln->ev[7])); ms8[6] = t; }      // first kernel -> last kernel
+    }
+};
+
+// chains of one call on one device; iters > 0 = resident timing mode.  A call with host output (iters == 0) and a large
+// batch runs as three ranges of chains (equal shares of the alignment nodes, the bulk of the upload).
+static std::vector<Range> ranges_single(const ahs_batch_in* in, const Sizes& sz, int iters) {
+    const int64_t C = sz.C;
     int n_chunks = 1;
     if (iters == 0 && C >= 4096 && sz.NEN >= (int64_t)16 << 20) {
         n_chunks = 3;
@@ -674,156 +798,157 @@ static void phase_on_device(const ahs_batch_in* in, ahs_batch_out* out, int devi
     for (int k = 0; k <= n_chunks; k++) frac[k] = (double)k / n_chunks;
     if (n_chunks == 3) { frac[1] = 0.12; frac[2] = 0.53; }
     if (const char* e = getenv("AHS_CUTS")) {                // tuning / debugging: "0.2,0.6"
-        const char* p = e;
-        for (int k = 1; k < n_chunks && *p; k++) { frac[k] = std::min(1.0, std::max(frac[k - 1], atof(p))); while (*p && *p != ',') p++; if (*p == ',') p++; }
+        const char* q = e;
+        for (int k = 1; k < n_chunks && *q; k++) { frac[k] = std::min(1.0, std::max(frac[k - 1], atof(q))); while (*q && *q != ',') q++; if (*q == ',') q++; }
     }
     for (int k = 1; k < n_chunks; k++) {
         const int64_t target = (int64_t)((double)sz.NEN * frac[k]);
         int64_t lo = cut[k - 1], hi = C;                  // first chain whose entries start at or after the target
-        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (in->enode_off[in->entry_off[mid]] >= target) hi = mid; else lo = mid + 1; }
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2, e = in->entry_off[mid];
+            if (e < 0 || e > sz.NE) throw ArgFail{"entry_off out of range"};
+            if (in->enode_off[e] >= target) hi = mid; else lo = mid + 1;
+        }
         cut[k] = lo;
     }
-    std::vector<ChainView> views(n_chunks); std::vector<Pipeline> pls(n_chunks);
-    std::vector<Sizes> szs(n_chunks);
-    cudaEvent_t e0 = cx->lanes[0].ev[8], e1 = cx->lanes[0].ev[9];
-    CK(cudaEventRecord(e0, cx->lanes[0].stream));
-    float acc[8] = {0};
-    int64_t tot_cells = 0, NFt = 0, NPt = 0;
-    for (int k = 0; k < n_chunks; k++) {
-        Pipeline& pl = pls[k];
-        pl.cx = cx; pl.ln = &cx->lanes[k]; pl.early_out = iters == 0;
-        if (n_chunks == 1) { pl.in = in; pl.sz = sz; }
-        else { views[k].make(in, cut[k], cut[k + 1]); pl.in = &views[k].v; pl.sz = validate(pl.in, true); }
-        szs[k] = pl.sz;
-        if (pl.sz.C == 0) continue;
-        pl.cell_base = tot_cells;
-        pl.upload();
-        if (k == 0) { CK(cudaEventRecord(e1, pl.ln->stream)); tr.mark("upload_enqueue"); }
-        pl.alloc_phase1();
-        // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
-        std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
-        const int total = iters > 0 ? warmup + iters : 1;
-        for (int it = 0; it < total; it++) {
-            if (iters > 0) for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
-            pl.run();                                     // ends with phase 2 enqueued; sync #1 inside waited for this chunk's upload only
-            tr.mark("run_enqueue");
-            if (iters > 0) {
-                CK(cudaStreamSynchronize(pl.ln->stream));
-                pl.collect_times();
-                if (it >= warmup) for (int i = 0; i < 8; i++) acc[i] += pl.ms[i];
-            }
+    std::vector<Range> r;
+    for (int k = 0; k < n_chunks; k++) r.push_back(Range{cut[k], cut[k + 1]});
+    return r;
+}
+
+// Multi-device plan: the chains arrive largest first (size_sorting, polyassembly.cpp:135-140).  Heavy
+// chains are dealt one by one, the tail of light chains in blocks of consecutive chains, largest cost first onto the
+// least loaded device (LPT).  A device's share is therefore a handful of RANGES of the caller's arrays: they are
+// uploaded and downloaded in place, nothing is re-packed on the host.
+static std::vector<std::vector<Range>> plan_devices(const ahs_batch_in* in, const Sizes& sz, int G, std::vector<double>* load_out) {
+    const int64_t C = sz.C; const int p = in->ploidy;
+    std::vector<double> cost(C); double T = 0;
+    for (int64_t c = 0; c < C; c++) {
+        const int64_t e0 = in->entry_off[c], e1 = in->entry_off[c + 1];
+        if (e0 < 0 || e1 > sz.NE) throw ArgFail{"entry_off out of range"};
+        cost[c] = ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], e1 - e0, in->enode_off[e1] - in->enode_off[e0], p);
+        T += cost[c];
+    }
+    const double grain = T / (4.0 * G);                        // ~4 ranges per device: one per pipeline lane
+    struct Item { int64_t c0, c1; double cost; };
+    std::vector<Item> items;
+    for (int64_t c = 0; c < C;) {
+        if (cost[c] >= grain) { items.push_back(Item{c, c + 1, cost[c]}); c++; continue; }
+        Item it{c, c, 0.0};
+        while (c < C && cost[c] < grain && it.cost + cost[c] <= grain) { it.cost += cost[c]; c++; }
+        if (it.c1 == it.c0 && c < C) { it.cost = cost[c]; c++; }
+        it.c1 = c;
+        items.push_back(it);
+    }
+    std::vector<int> order(items.size()); std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].cost > items[b].cost; });
+    std::vector<double> load(G, 0.0); std::vector<std::vector<Range>> plan(G);
+    for (int i : order) { const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); load[g] += items[i].cost; plan[g].push_back(Range{items[i].c0, items[i].c1}); }
+    for (auto& r : plan) {
+        std::sort(r.begin(), r.end(), [](const Range& a, const Range& b) { return a.c0 < b.c0; });
+        std::vector<Range> m;
+        for (auto& x : r) { if (!m.empty() && m.back().c1 == x.c0) m.back().c1 = x.c1; else m.push_back(x); }
+        r = m;
+    }
+    if (load_out) *load_out = load;
+    return plan;
+}
+
+// small reusable barrier for the device threads of one call
+struct ThreadBarrier {
+    std::mutex m; std::condition_variable cv; int n, waiting = 0, gen = 0;
+    explicit ThreadBarrier(int n_) : n(n_) {}
+    void arrive() { std::unique_lock<std::mutex> l(m); const int g = gen; if (++waiting == n) { waiting = 0; gen++; cv.notify_all(); } else cv.wait(l, [&] { return gen != g; }); }
+};
+
+// one batch on the given devices.  G == 1: the whole batch on that device.  G > 1: plan_devices(); one host thread per
+// device; no inter-GPU traffic; every device writes its ranges straight into the (portable, page-locked) output arrays.
+static void phase_on_devices(const ahs_batch_in* in, ahs_batch_out* out, const int* devs, int G, int warmup, int iters) {
+    if (!out) throw ArgFail{"null output"};
+    if (!devs || G < 1) throw ArgFail{"no devices"};
+    for (int g = 0; g < G; g++) for (int h = 0; h < g; h++) if (devs[g] == devs[h]) throw ArgFail{"ahs_phase_batch_multi: a device id is listed twice"};
+    Sizes sz = validate(in);
+    const int64_t C = sz.C; const int p = in->ploidy;
+    std::vector<DeviceJob> jobs(G);
+    if (C == 0) {
+        jobs[0].begin(devs[0], in);
+        fill_empty_out(out, jobs[0].cx, p); jobs[0].cx->out_busy = true;
+        jobs[0].lock.unlock();
+        return;
+    }
+    std::vector<std::vector<Range>> plan;
+    std::vector<double> load;
+    if (G == 1) plan.push_back(ranges_single(in, sz, iters)); else plan = plan_devices(in, sz, G, &load);
+    // every range of the call, in chain order: (device, index within the device)
+    struct Place { int64_t c0; int g, k; };
+    std::vector<Place> places;
+    for (int g = 0; g < G; g++) for (int k = 0; k < (int)plan[g].size(); k++) places.push_back(Place{plan[g][k].c0, g, k});
+    std::sort(places.begin(), places.end(), [](const Place& a, const Place& b) { return a.c0 < b.c0; });
+    std::vector<std::vector<int64_t>> f_base(G), q_base(G), cell_base(G);
+    for (int g = 0; g < G; g++) { f_base[g].assign(plan[g].size(), 0); q_base[g] = f_base[g]; cell_base[g] = f_base[g]; }
+    std::vector<std::string> errs(G); std::vector<int> rcs(G, AHS_OK);
+    ThreadBarrier bar(G);
+    int64_t NFt = 0, NPt = 0, tot_cells = 0;
+    auto any_failed = [&]() { for (int g = 0; g < G; g++) if (rcs[g] != AHS_OK) return true; return false; };
+    auto body = [&](int g) {
+        DeviceJob& job = jobs[g];
+        rcs[g] = guarded("device", [&]() { job.begin(devs[g], in); job.ranges = plan[g]; job.enqueue(warmup, iters); });
+        if (rcs[g] != AHS_OK) errs[g] = g_err;
+        bar.arrive();
+        if (g == 0 && !any_failed()) {
+            rcs[0] = guarded("output", [&]() {
+                for (auto& pc : places) {
+                    Pipeline& pl = jobs[pc.g].pls[pc.k];
+                    f_base[pc.g][pc.k] = NFt; q_base[pc.g][pc.k] = NPt; cell_base[pc.g][pc.k] = tot_cells;
+                    if (jobs[pc.g].szs[pc.k].C == 0) continue;
+                    NFt += pl.d.NF; NPt += pl.d.NP; tot_cells += pl.h_tot_cells;
+                }
+                alloc_out(out, jobs[0].cx, C, p, NFt, NPt, tot_cells);
+                jobs[0].cx->out_busy = true;                       // under the context's lock; taken back below if the call fails
+            });
+            if (rcs[0] != AHS_OK) errs[0] = g_err;
         }
-        tot_cells += pl.h_tot_cells; NFt += pl.d.NF; NPt += pl.d.NP;
+        bar.arrive();
+        if (!any_failed()) {
+            rcs[g] = guarded("device", [&]() { job.copy_out(out, f_base[g].data(), q_base[g].data(), cell_base[g].data()); });
+            if (rcs[g] != AHS_OK) errs[g] = g_err;
+        } else if (job.cx) { cudaSetDevice(devs[g]); cudaDeviceSynchronize(); cudaGetLastError(); }
+        if (job.lock.owns_lock()) job.lock.unlock();            // by the thread that took it
+    };
+    if (G == 1) body(0);
+    else { std::vector<std::thread> th; for (int g = 0; g < G; g++) th.emplace_back(body, g); for (auto& t : th) t.join(); }
+    for (int g = 0; g < G; g++) if (rcs[g] != AHS_OK) {
+        if (jobs[0].cx) { std::lock_guard<std::mutex> l(jobs[0].cx->mu); jobs[0].cx->out_busy = false; jobs[0].cx->outp.reset(); }
+        const std::string msg = G > 1 ? "device " + std::to_string(devs[g]) + ": " + errs[g] : errs[g];
+        if (rcs[g] == AHS_ERR_ARG) throw ArgFail{msg};
+        if (rcs[g] == AHS_ERR_LIMIT) throw LimitFail{msg};
+        if (rcs[g] == AHS_ERR_CUDA) throw PassThrough{AHS_ERR_CUDA, msg};
+        throw std::runtime_error(msg);
     }
-    // ---- output arrays (sizes are known now), then the copies
-    memset(out, 0, sizeof(*out));
-    out->n_chains = (int32_t)C; out->ploidy = p;
-    out->status = cx->outp.get<int32_t>(C); out->n_clusters = cx->outp.get<int32_t>(C); out->dp_cost = cx->outp.get<double>(C); out->maxpos = cx->outp.get<int32_t>(C);
-    out->read_off = cx->outp.get<int64_t>(C + 1); out->pos_off = cx->outp.get<int64_t>(C + 1);
-    out->read_id = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1)); out->read_mapq = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1));
-    out->read_cluster = cx->outp.get<int32_t>(std::max<int64_t>(NFt, 1)); out->cell_off = cx->outp.get<int64_t>(NFt + 1);
-    out->cell_pos = cx->outp.get<int32_t>(std::max<int64_t>(tot_cells, 1)); out->cell_allele = cx->outp.get<uint8_t>(std::max<int64_t>(tot_cells, 1));
-    out->pos = cx->outp.get<int32_t>(std::max<int64_t>(NPt, 1)); out->path = cx->outp.get<int32_t>(std::max<int64_t>(NPt * p, 1));
-    out->hap_allele = cx->outp.get<uint8_t>(std::max<int64_t>(NPt * p, 1));
-    out->cell_off[0] = 0;
-    int64_t* h_pairs = cx->outp.get<int64_t>(n_chunks);
-    std::vector<Pipeline::Slices> sl(n_chunks);
-    {
-        int64_t f = 0, q = 0, cells = 0;
-        out->read_off[0] = 0; out->pos_off[0] = 0;
-        for (int k = 0; k < n_chunks; k++) {
-            Pipeline& pl = pls[k];
-            const int64_t c0 = cut[k];
-            sl[k] = Pipeline::Slices{out->status + c0, out->read_id + f, out->read_mapq + f, out->read_cluster + f, out->cell_pos + cells, out->n_clusters + c0,
-                                     out->pos + q, out->path + q * p, out->maxpos + c0, out->cell_off + f, out->cell_allele + cells, out->hap_allele + q * p,
-                                     out->dp_cost + c0, k == 0};
-            h_pairs[k] = 0;
-            if (szs[k].C == 0) continue;
-            for (int64_t c = 0; c < szs[k].C; c++) { out->read_off[c0 + c + 1] = f + pl.h_frow_off[c + 1]; out->pos_off[c0 + c + 1] = q + pl.h_pos_off[c + 1]; }
-            f += pl.d.NF; q += pl.d.NP; cells += pl.h_tot_cells;
-        }
-    }
-    cudaEvent_t d0 = cx->lanes[0].ev[8];
-    float h2d = 0; CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&h2d, e0, e1));
-    CK(cudaEventRecord(d0, cx->lanes[0].stream2));
-    for (int k = 0; k < n_chunks; k++) if (szs[k].C) {
-        Pipeline& pl = pls[k];
-        if (pl.early_out) { CK(cudaStreamWaitEvent(pl.ln->stream2, pl.ln->ev_cells, 0)); pl.copy_matrix(sl[k], pl.ln->stream2); }
-        else pl.copy_matrix(sl[k], pl.ln->stream);
-        pl.copy_rest(sl[k], h_pairs + k);
-    }
-    tr.mark("copies_enqueue");
-    for (int k = 0; k < n_chunks; k++) { CK(cudaStreamSynchronize(cx->lanes[k].stream2)); CK(cudaStreamSynchronize(cx->lanes[k].stream)); }
-    tr.mark("run_sync");
-    {
-        auto mb = [](const Pool& p, bool used) { double t = 0; for (auto& c : p.chunks) t += (double)(used ? c.used : c.cap); return t / 1048576.0; };
-        tr.note("dev_used_mb", mb(cx->dev, true)); tr.note("dev_cap_mb", mb(cx->dev, false));
-        tr.note("pin_used_mb", mb(cx->pin, true)); tr.note("out_used_mb", mb(cx->outp, true));
-        tr.note("in_enode_mb", (double)sz.NEN * 4 / 1048576.0);
-    }
-    CK(cudaEventRecord(e1, cx->lanes[0].stream)); CK(cudaEventSynchronize(e1));
-    float d2h = 0; CK(cudaEventElapsedTime(&d2h, d0, e1));
     if (out->cell_off[NFt] != tot_cells) throw std::runtime_error("cell count mismatch");
     out->n_cells = tot_cells;
-    for (int k = 0; k < n_chunks; k++) out->n_pairs += h_pairs[k] / 2;
+    for (int g = 0; g < G; g++) for (size_t k = 0; k < plan[g].size(); k++) out->n_pairs += jobs[g].h_pairs[k] / 2;
     for (int64_t c = 0; c < C; c++) out->n_chains_ok += out->status[c] == AHS_CHAIN_OK;
-    // ---- timings and byte counts
-    if (iters > 0) for (int i = 0; i < 8; i++) pls[0].ms[i] = acc[i] / iters;
-    else {
-        for (int k = 0; k < n_chunks; k++) if (szs[k].C) { pls[k].collect_times(); if (k) for (int i = 0; i < 6; i++) pls[0].ms[i] += pls[k].ms[i]; }
-        int last = 0; for (int k = 0; k < n_chunks; k++) if (szs[k].C) last = k;
-        float t = 0; CK(cudaEventElapsedTime(&t, cx->lanes[0].ev[0], cx->lanes[last].ev[7])); pls[0].ms[6] = t;      // first kernel -> last kernel
+    // ---- timings (max over devices) and byte counts
+    int bits = 2;
+    for (int g = 0; g < G; g++) {
+        float ms8[8]; int launches = 0;
+        CK(cudaSetDevice(devs[g]));
+        jobs[g].times(ms8, launches);
+        out->ms_h2d = std::max(out->ms_h2d, jobs[g].h2d); out->ms_d2h = std::max(out->ms_d2h, jobs[g].d2h);
+        out->ms_project = std::max(out->ms_project, ms8[0]); out->ms_rows = std::max(out->ms_rows, ms8[1]); out->ms_score = std::max(out->ms_score, ms8[2]);
+        out->ms_cluster = std::max(out->ms_cluster, ms8[3]); out->ms_consensus = std::max(out->ms_consensus, ms8[4]); out->ms_thread = std::max(out->ms_thread, ms8[5]);
+        out->ms_total_device = std::max(out->ms_total_device, ms8[6]);
+        out->n_launches += launches;
+        for (auto& pl : jobs[g].pls) if (pl.sz.C) bits = std::max(bits, (int)pl.d.bits);
     }
-    Pipeline& p0 = pls[0];
-    out->ms_h2d = h2d; out->ms_project = p0.ms[0]; out->ms_rows = p0.ms[1]; out->ms_score = p0.ms[2]; out->ms_cluster = p0.ms[3];
-    out->ms_consensus = p0.ms[4]; out->ms_thread = p0.ms[5]; out->ms_total_device = p0.ms[6]; out->ms_d2h = d2h;
-    for (int k = 0; k < n_chunks; k++) out->n_launches += pls[k].n_launches;
     {   // algorithmic bytes, SURVEY.md §8d: each datum crosses HBM once
-        const double code_bytes = p0.d.bits / 8.0;
+        const double code_bytes = bits / 8.0;
         const int64_t cells = out->n_cells;
         out->bytes_project = 4 * sz.NEN + 4 * sz.NAN_ + 8 * sz.NE + (int64_t)(code_bytes * cells) + 12 * NFt;
         out->bytes_score = (int64_t)(code_bytes * cells) + 12 * NFt + 4 * out->n_pairs;
         out->bytes_consensus = (int64_t)(code_bytes * cells) + 16 * NFt + 5 * NPt * p;   // k_pos ~ ploidy retained clusters
     }
-    cx->out_busy = true;
-}
-
-// ------------------------------------------------------------------ multi-device: LPT over chains, host gather
-struct SubBatch {
-    std::vector<int32_t> chain_id, anode, stage_a_order, enode, entry_read, src_chain;
-    std::vector<int64_t> bubble_off{0}, allele_off{0}, anode_off{0}, read_off{0}, entry_off{0}, enode_off{0};
-    std::vector<float> ident; ahs_batch_in view;
-    void add_chain(const ahs_batch_in* in, int c) {
-        src_chain.push_back(c); chain_id.push_back(in->chain_id ? in->chain_id[c] : c);
-        for (int64_t b = in->bubble_off[c]; b < in->bubble_off[c + 1]; b++) {
-            for (int64_t a = in->allele_off[b]; a < in->allele_off[b + 1]; a++) {
-                anode.insert(anode.end(), in->anode + in->anode_off[a], in->anode + in->anode_off[a + 1]);
-                anode_off.push_back((int64_t)anode.size());
-            }
-            allele_off.push_back((int64_t)anode_off.size() - 1);
-            stage_a_order.push_back(in->stage_a_order ? in->stage_a_order[b] : (int32_t)(in->bubble_off[c + 1] - 1 - b));
-        }
-        bubble_off.push_back((int64_t)allele_off.size() - 1);
-        for (int64_t e = in->entry_off[c]; e < in->entry_off[c + 1]; e++) {
-            enode.insert(enode.end(), in->enode + in->enode_off[e], in->enode + in->enode_off[e + 1]);
-            enode_off.push_back((int64_t)enode.size());
-            entry_read.push_back(in->entry_read[e]); ident.push_back(in->entry_identity[e]);
-        }
-        entry_off.push_back((int64_t)entry_read.size());
-        read_off.push_back(read_off.back() + in->read_off[c + 1] - in->read_off[c]);
-    }
-    void finish(int ploidy) {
-        view.n_chains = (int32_t)chain_id.size(); view.ploidy = ploidy; view.chain_id = chain_id.data();
-        view.bubble_off = bubble_off.data(); view.allele_off = allele_off.data(); view.anode_off = anode_off.data(); view.anode = anode.data();
-        view.stage_a_order = stage_a_order.data(); view.read_off = read_off.data(); view.entry_off = entry_off.data();
-        view.enode_off = enode_off.data(); view.enode = enode.data(); view.entry_read = entry_read.data(); view.entry_identity = ident.data();
-    }
-};
-
-template <class T> static T* mdup(const std::vector<T>& v) {
-    T* p = (T*)malloc(sizeof(T) * std::max<size_t>(v.size(), 1));
-    if (!v.empty()) memcpy(p, v.data(), sizeof(T) * v.size());
-    return p;
 }
 
 }  // namespace ahs
@@ -836,7 +961,9 @@ int ahs_abi_version(void) { return AHS_ABI_VERSION; }
 
 void ahs_get_limits(ahs_limits* out) {
     if (!out) return;
+    memset(out, 0, sizeof(*out));
     out->max_ploidy = MAX_PLOIDY; out->max_alleles = MAX_ALLELES; out->max_reads_cluster = MAX_READS_CLUSTER; out->max_positions = MAX_POSITIONS;
+    out->max_clusters_position = K3_CAP;
 }
 
 int ahs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
@@ -852,11 +979,33 @@ double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_node
 }
 
 int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int device) {
-    return guarded("ahs_phase_batch", [&]() { phase_on_device(in, out, device, 0, 0); });
+    return guarded("ahs_phase_batch", [&]() { phase_on_devices(in, out, &device, 1, 0, 0); });
 }
 
 int ahs_phase_batch_resident(const ahs_batch_in* in, ahs_batch_out* out, int device, int warmup, int iters) {
-    return guarded("ahs_phase_batch_resident", [&]() { phase_on_device(in, out, device, warmup < 0 ? 0 : warmup, iters < 1 ? 1 : iters); });
+    return guarded("ahs_phase_batch_resident", [&]() { phase_on_devices(in, out, &device, 1, warmup < 0 ? 0 : warmup, iters < 1 ? 1 : iters); });
+}
+
+int ahs_phase_batch_multi(const ahs_batch_in* in, ahs_batch_out* out, const int* device_ids, int n_devices) {
+    return guarded("ahs_phase_batch_multi", [&]() { phase_on_devices(in, out, device_ids, n_devices, 0, 0); });
+}
+
+int ahs_debug_std_sort(int32_t* keys, int32_t* values, int32_t n, int descending, int device) {
+    return guarded("ahs_debug_std_sort", [&]() {
+        if (n < 0 || (n > 0 && (!keys || !values))) throw ArgFail{"null array"};
+        Ctx* cx = get_ctx(device);
+        std::lock_guard<std::mutex> g(cx->mu);
+        CK(cudaSetDevice(device));
+        if (n == 0) return;
+        int32_t *dk = nullptr, *dv = nullptr;
+        CK(cudaMalloc(&dk, (size_t)n * 4)); CK(cudaMalloc(&dv, (size_t)n * 4));
+        CK(cudaMemcpy(dk, keys, (size_t)n * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dv, values, (size_t)n * 4, cudaMemcpyHostToDevice));
+        k_debug_std_sort<<<1, 1>>>(dk, dv, n, descending);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) { CK(cudaMemcpy(keys, dk, (size_t)n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(values, dv, (size_t)n * 4, cudaMemcpyDeviceToHost)); }
+        cudaFree(dk); cudaFree(dv);
+        CK(e);
+    });
 }
 
 int ahs_warmup(int device, uint64_t device_bytes, uint64_t pinned_bytes) {
@@ -891,81 +1040,17 @@ int ahs_unpin_host(const void* ptr) {
 
 void ahs_free_out(ahs_batch_out* out) {
     if (!out) return;
-    if (out->reserved == AHS_OUT_MALLOCED) {      // gathered multi-device result: malloc'ed
-        free(out->status); free(out->read_off); free(out->read_id); free(out->read_mapq); free(out->read_cluster); free(out->cell_off);
-        free(out->cell_pos); free(out->cell_allele); free(out->n_clusters); free(out->pos_off); free(out->pos); free(out->path);
-        free(out->hap_allele); free(out->dp_cost); free(out->maxpos);
-    } else {
-        std::lock_guard<std::mutex> g(g_ctx_mu);
-        for (auto* c : g_ctx) if (c && c->out_busy) {
-            for (auto& ch : c->outp.chunks) if ((char*)out->read_off >= ch.p && (char*)out->read_off < ch.p + ch.cap) c->out_busy = false;
+    if (out->read_off) {
+        // the arrays live in the page-locked result pool of one device context: find it by address
+        Ctx* owner = nullptr;
+        {
+            std::lock_guard<std::mutex> g(g_ctx_mu);
+            for (auto* c : g_ctx) if (c && !owner)
+                for (auto& ch : c->outp.chunks) if ((char*)out->read_off >= ch.p && (char*)out->read_off < ch.p + ch.cap) owner = c;
         }
+        if (owner) { std::lock_guard<std::mutex> g(owner->mu); owner->out_busy = false; }
     }
     memset(out, 0, sizeof(*out));
-}
-
-int ahs_phase_batch_multi(const ahs_batch_in* in, ahs_batch_out* out, const int* device_ids, int n_devices) {
-    if (n_devices == 1 && device_ids) return ahs_phase_batch(in, out, device_ids[0]);
-    std::vector<std::string> errs(n_devices > 0 ? n_devices : 0);
-    int rc_all = guarded("ahs_phase_batch_multi", [&]() {
-        if (!device_ids || n_devices < 1) throw ArgFail{"no devices"};
-        if (!out) throw ArgFail{"null output"};
-        validate(in);
-        const int C = in->n_chains, G = n_devices, p = in->ploidy;
-        // LPT: chains by decreasing cost onto the least loaded device
-        std::vector<int> order(C); std::iota(order.begin(), order.end(), 0);
-        std::vector<double> cost(C);
-        for (int c = 0; c < C; c++) cost[c] = ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], in->entry_off[c + 1] - in->entry_off[c],
-                                                              in->enode_off[in->entry_off[c + 1]] - in->enode_off[in->entry_off[c]], p);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-        std::vector<SubBatch> sub(G); std::vector<double> load(G, 0.0); std::vector<std::vector<int>> assign(G);
-        for (int c : order) { int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); load[g] += cost[c]; assign[g].push_back(c); }
-        for (int g = 0; g < G; g++) { std::sort(assign[g].begin(), assign[g].end()); for (int c : assign[g]) sub[g].add_chain(in, c); sub[g].finish(p); }
-        std::vector<ahs_batch_out> outs(G); std::vector<int> rcs(G, 0);
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; g++) th.emplace_back([&, g]() { rcs[g] = ahs_phase_batch(&sub[g].view, &outs[g], device_ids[g]); if (rcs[g]) errs[g] = ahs_last_error(); });
-        for (auto& t : th) t.join();
-        for (int g = 0; g < G; g++) if (rcs[g]) { for (int h = 0; h < G; h++) if (!rcs[h]) ahs_free_out(&outs[h]); throw std::runtime_error("device " + std::to_string(device_ids[g]) + ": " + errs[g]); }
-        // gather in input order
-        std::vector<int> where_g(C), where_i(C);
-        for (int g = 0; g < G; g++) for (size_t i = 0; i < assign[g].size(); i++) { where_g[assign[g][i]] = g; where_i[assign[g][i]] = (int)i; }
-        std::vector<int32_t> status, read_id, read_mapq, read_cluster, cell_pos, n_clusters, pos, path, maxpos;
-        std::vector<int64_t> read_off{0}, cell_off{0}, pos_off{0}; std::vector<uint8_t> cell_allele, hap_allele; std::vector<double> dp_cost;
-        memset(out, 0, sizeof(*out));
-        for (int c = 0; c < C; c++) {
-            const ahs_batch_out& o = outs[where_g[c]]; const int i = where_i[c];
-            status.push_back(o.status[i]); n_clusters.push_back(o.n_clusters[i]); dp_cost.push_back(o.dp_cost[i]); maxpos.push_back(o.maxpos[i]);
-            for (int64_t r = o.read_off[i]; r < o.read_off[i + 1]; r++) {
-                read_id.push_back(o.read_id[r]); read_mapq.push_back(o.read_mapq[r]); read_cluster.push_back(o.read_cluster[r]);
-                for (int64_t x = o.cell_off[r]; x < o.cell_off[r + 1]; x++) { cell_pos.push_back(o.cell_pos[x]); cell_allele.push_back(o.cell_allele[x]); }
-                cell_off.push_back((int64_t)cell_pos.size());
-            }
-            read_off.push_back((int64_t)read_id.size());
-            for (int64_t q = o.pos_off[i]; q < o.pos_off[i + 1]; q++) {
-                pos.push_back(o.pos[q]);
-                for (int h = 0; h < p; h++) { path.push_back(o.path[q * p + h]); hap_allele.push_back(o.hap_allele[q * p + h]); }
-            }
-            pos_off.push_back((int64_t)pos.size());
-        }
-        for (int g = 0; g < G; g++) {
-            out->n_cells += outs[g].n_cells; out->n_pairs += outs[g].n_pairs; out->n_chains_ok += outs[g].n_chains_ok;
-            out->ms_h2d = std::max(out->ms_h2d, outs[g].ms_h2d); out->ms_project = std::max(out->ms_project, outs[g].ms_project);
-            out->ms_rows = std::max(out->ms_rows, outs[g].ms_rows); out->ms_score = std::max(out->ms_score, outs[g].ms_score);
-            out->ms_cluster = std::max(out->ms_cluster, outs[g].ms_cluster); out->ms_consensus = std::max(out->ms_consensus, outs[g].ms_consensus);
-            out->ms_thread = std::max(out->ms_thread, outs[g].ms_thread); out->ms_d2h = std::max(out->ms_d2h, outs[g].ms_d2h);
-            out->ms_total_device = std::max(out->ms_total_device, outs[g].ms_total_device);
-            out->n_launches += outs[g].n_launches; out->bytes_project += outs[g].bytes_project; out->bytes_score += outs[g].bytes_score;
-            out->bytes_consensus += outs[g].bytes_consensus;
-            ahs_free_out(&outs[g]);
-        }
-        out->n_chains = C; out->reserved = AHS_OUT_MALLOCED;       // tells ahs_free_out that the arrays are malloc'ed
-        out->ploidy = p;
-        out->status = mdup(status); out->read_off = mdup(read_off); out->read_id = mdup(read_id); out->read_mapq = mdup(read_mapq);
-        out->read_cluster = mdup(read_cluster); out->cell_off = mdup(cell_off); out->cell_pos = mdup(cell_pos); out->cell_allele = mdup(cell_allele);
-        out->n_clusters = mdup(n_clusters); out->pos_off = mdup(pos_off); out->pos = mdup(pos); out->path = mdup(path);
-        out->hap_allele = mdup(hap_allele); out->dp_cost = mdup(dp_cost); out->maxpos = mdup(maxpos);
-    });
-    return rc_all;
 }
 
 }  // extern "C"

@@ -93,7 +93,12 @@ def make_batch(workload, scale, rank):
     return synth.generate(prm)
 
 
-WORKLOAD_NAMES = {"cfg2": "cfg2: BASELINE.json configs[1] synthetic diploid human-scale graph"}
+WORKLOAD_NAMES = {"cfg1": "cfg1: BASELINE.json configs[0] one chain of 1k bubbles, 2k reads",
+                  "cfg2": "cfg2: BASELINE.json configs[1] synthetic diploid human-scale graph",
+                  "cfg3": "cfg3: BASELINE.json configs[2] synthetic triploid graph",
+                  "cfg4": "cfg4: BASELINE.json configs[3] synthetic tetraploid graph",
+                  "cfg5": "cfg5: BASELINE.json configs[4] synthetic hexaploid graph, Zipf-skewed chain sizes",
+                  "zipf2": "zipf2: diploid, Zipf-skewed chain sizes up to 10k bubbles (load-balancing stress)"}
 
 
 def workload_desc(workload, scale, batch):
@@ -124,49 +129,60 @@ def cpu_port_baseline(batch, seconds_target=15.0):
 
 
 def run_reference_arm(args):
-    """Reference sources verbatim (+ WhatsHap shim) as `Ahsoka phase -t 1` on a bounded sample."""
+    """Reference sources verbatim (+ WhatsHap shim) as `Ahsoka phase -t 1`, one process per host core, each on its own
+    bounded sample of the workload (the reference is single-threaded: -t > 1 is an unfinished experiment)."""
     from ahsoka_b200 import synth
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     exe = os.path.join(ROOT, "oracle", "_ref", "Ahsoka_ref")
+    cores = os.cpu_count() or 1
     # bounded sample: the reference-verbatim CLI costs ~2.6 s per cfg2 chain on one core (its projection is
-    # O(bubbles x alleles x entries), SURVEY §0.7); keep the whole K+W run near 2-3 minutes
+    # O(bubbles x alleles x entries), SURVEY 0.7); keep the whole K+W run near 2-3 minutes
     n_chains = args.ref_chains if args.ref_chains > 0 else int(max(2, min(12, 150.0 / (2.6 * (args.steps + args.warmup)))))
-    prm = synth.config(args.workload, 1.0)
-    prm.n_chains = n_chains
     times, cells, chains = [], 0, 0
-    kind, cores, sample = "reference", 1, ""
+    kind, sample = "reference", ""
     with tempfile.TemporaryDirectory() as td:
-        batch = synth.generate(prm, os.path.join(td, "s"))
         if os.path.exists(exe):
             from tests.oracle_binding import oracle_phase
-            want = oracle_phase(batch)           # only to count the cells the CLI run phases (not timed)
-            cells, chains = want.n_cells, want.n_chains_ok
+            n_proc = cores
+            for i in range(n_proc):
+                prm = synth.config(args.workload, 1.0)
+                prm.n_chains = n_chains; prm.seed = prm.seed + 7919 * i
+                batch = synth.generate(prm, os.path.join(td, f"s{i}"))
+                want = oracle_phase(batch)           # only to count the cells the CLI runs phase (not timed)
+                cells += want.n_cells; chains += want.n_chains_ok
             for it in range(args.warmup + args.steps):
-                out = os.path.join(td, f"o{it}")
                 t0 = time.perf_counter()
-                subprocess.run([exe, "phase", "-g", os.path.join(td, "s.gfa"), "-a", os.path.join(td, "s.gaf"), "-o", out, "-t", "1"],
-                               cwd=td, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+                procs = [subprocess.Popen([exe, "phase", "-g", os.path.join(td, f"s{i}.gfa"), "-a", os.path.join(td, f"s{i}.gaf"),
+                                           "-o", os.path.join(td, f"o{it}_{i}"), "-t", "1"], cwd=td, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                         for i in range(n_proc)]
+                rcs = [p.wait() for p in procs]
                 dt = time.perf_counter() - t0
+                if any(rcs):
+                    raise SystemExit("bench.py: the reference binary failed on the sample")
                 if it >= args.warmup:
                     times.append(dt)
-            sample = (f"{n_chains} chains of {args.workload} as GFA+GAF through `Ahsoka phase -t 1` "
-                      f"(reference src/*.cpp verbatim at -O2 + WhatsHap API shim), whole CLI run incl. parsing")
+            sample = (f"{n_proc} concurrent `Ahsoka phase -t 1` processes (one per host core), each on its own {n_chains}-chain GFA+GAF sample of "
+                      f"{args.workload} (reference src/*.cpp verbatim at -O2 + WhatsHap API shim), whole CLI runs incl. parsing")
         else:
             from tests.oracle_binding import oracle_phase
-            kind, cores = "port", os.cpu_count() or 1
+            kind = "port"
+            prm = synth.config(args.workload, 1.0)
+            prm.n_chains = n_chains * cores * 8
+            batch = synth.generate(prm)
             for it in range(args.warmup + args.steps):
                 t0 = time.perf_counter(); r = oracle_phase(batch, cores); dt = time.perf_counter() - t0
                 cells, chains = r.n_cells, r.n_chains_ok
                 if it >= args.warmup:
                     times.append(dt)
-            sample = f"{n_chains} chains of {args.workload}, CPU oracle port, {cores} threads (reference-verbatim binary not built)"
+            sample = f"{prm.n_chains} chains of {args.workload}, CPU oracle port, {cores} threads (reference-verbatim binary not built)"
     dt = sum(times) / len(times)
     val = cells / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64 fixed point",
-            "data": "synthetic", "config": {"workload": WORKLOAD_NAMES.get(args.workload, args.workload), "sample_chains": n_chains, "cells": cells, "ploidy": 2},
+            "data": "synthetic", "config": {"workload": WORKLOAD_NAMES.get(args.workload, args.workload), "sample_chains": n_chains * (cores if kind == "reference" else cores * 8),
+                                            "cells": cells, "ploidy": int(synth.config(args.workload, 1.0).ploidy)},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "chains_per_s": chains / dt},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     _emit(line)
@@ -215,6 +231,15 @@ def main():
     if lib.ahs_device_count() <= local:
         raise SystemExit("bench.py: no CUDA device for this rank; the phasing path has no CPU fallback")
 
+    # one rank = one GPU = one share of the host cores (the ranks of a box would otherwise all run on the same CPUs)
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cpus) >= world:
+            per = len(cpus) // world
+            os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+    except (AttributeError, OSError):
+        pass
+
     batch = make_batch(args.workload, args.scale, rank)
     api.pin_batch(batch)
 
@@ -246,8 +271,39 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
+    # ---- the same call with PAGEABLE input arrays, as a one-shot caller (the drop-in CLI) passes them
+    api.unpin_batch(batch)
+    api.phase_batch(batch, device=local, copy=False).release()
+    pg_times = []
+    for _ in range(max(2, min(args.steps, 5))):
+        t0 = time.perf_counter(); r2 = api.phase_batch(batch, device=local, copy=False); pg_times.append(time.perf_counter() - t0)
+        r2.release()
+    e2e_pageable_ms = 1e3 * sum(pg_times) / len(pg_times)
+    barrier()
+    # ---- N > 1: the north-star split, checked once outside the timed regions.  Rank 0 deals ITS batch over all N
+    # devices of the box inside one process (ahs_phase_batch_multi: heavy chains one by one, the tail in ranges of
+    # consecutive chains, LPT; no inter-GPU traffic; every device writes its ranges straight into the output arrays)
+    # and compares every output array with the single-device result; the other ranks idle at the barrier.
+    multi = None
+    if world > 1 and rank == 0 and lib.ahs_device_count() >= world:
+        devs = list(range(world))
+        single = api.phase_batch(batch, device=local)
+        api.phase_batch(batch, devices=devs, copy=False).release()          # contexts + pools of the other devices
+        mt = []
+        for _ in range(3):
+            t0 = time.perf_counter(); rm = api.phase_batch(batch, devices=devs, copy=False); mt.append(time.perf_counter() - t0)
+            bad = rm.diff(single)
+            ms_dev = rm.timings["ms_total_device"]
+            rm.release()
+            if bad:
+                raise SystemExit(f"bench.py: multi-device result differs from the single-device result in {bad}")
+        multi = {"devices": world, "equal_to_single_device": True, "ms_per_call_pageable_inputs": 1e3 * min(mt),
+                 "single_device_ms_same_inputs": e2e_pageable_ms, "speedup": e2e_pageable_ms / (1e3 * min(mt)),
+                 "slowest_device_kernel_ms": ms_dev, "what": "one batch dealt over all devices by ahs_phase_batch_multi inside rank 0 (strong scaling of one call)"}
+    barrier()
 
     cells, chains_ok = res.n_cells, res.n_chains_ok
+    cells_local = cells
     if dist is not None:
         import torch
         v = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
@@ -287,8 +343,12 @@ def main():
             "data": "synthetic", "config": dict(workload_desc(args.workload, args.scale, batch), parallelism=f"chains x{world} (no collective)"),
             "chains_per_s": chains_ok / (ms_step * 1e-3), "cells": cells, "pairs_per_gpu": res.n_pairs,
             "e2e": {"value": cells / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": batch.nbytes(), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms, "inputs": "page-locked host arrays (ahs_pin_host, outside the timed region)",
+                    "pageable_inputs": {"value": cells_local / (e2e_pageable_ms * 1e-3), "ms_per_step": e2e_pageable_ms, "n_gpus": 1,
+                                        "what": "rank 0's call with plain pageable numpy arrays, as a one-shot caller passes them"}},
             "gpu_launches": int(t["n_launches"]) * args.steps, "roofline": roofline, "clocks": clocks}
+    if multi is not None:
+        line["multi"] = multi
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_port_baseline(batch)
     _emit(line)

@@ -11,8 +11,14 @@
  * below, calls ahs_phase_batch(), and writes the result text exactly as
  * src/alignmentstoreadset.cpp:70-83 and :411-486 do.  See INTEGRATION.md.
  *
- * Plain C: pointers and sizes only, no exceptions cross the boundary, no global
- * state besides the CUDA context of the selected device.
+ * Plain C: pointers and sizes only, no exceptions cross the boundary.  State kept between
+ * calls, per device: the CUDA context, streams and memory pools (reused by the next call) and
+ * the result buffers of the LAST call, which the caller owns until ahs_free_out().
+ *
+ * One outstanding result per device: ahs_phase_batch() on a device whose previous
+ * ahs_batch_out has not been released returns AHS_ERR_ARG (the result arrays live in a
+ * per-device page-locked pool).  Calls on different devices may run concurrently from
+ * different host threads; calls on one device are serialised by the library.
  */
 #ifndef AHSOKA_B200_H
 #define AHSOKA_B200_H
@@ -23,7 +29,7 @@
 extern "C" {
 #endif
 
-#define AHS_ABI_VERSION 1
+#define AHS_ABI_VERSION 2
 
 /* Return codes of the entry points. */
 #define AHS_OK              0
@@ -37,7 +43,7 @@ extern "C" {
 #define AHS_CHAIN_TRIVIAL       1   /* <= 1 bubble: header only (alignmentstoreadset.cpp:86) */
 #define AHS_CHAIN_EMPTY         2   /* no read survives the filter (alignmentstoreadset.cpp:279-282) */
 #define AHS_CHAIN_TOO_LARGE     3   /* exceeds a build limit (cluster editing workspace, DP states) */
-#define AHS_CHAIN_SORT_FALLBACK 4   /* introsort depth limit reached: libstdc++ would heap-sort; not emulated */
+#define AHS_CHAIN_SORT_FALLBACK 4   /* ABI 1 only: never produced since ABI 2 (std::sort's heap-sort fall-back is replayed too) */
 
 /*
  * Input batch, caller-owned, read-only, host memory.  CSR by chain.
@@ -123,6 +129,9 @@ typedef struct ahs_limits {
     int32_t max_alleles;           /* alleles per bubble (4-bit codes: 15) */
     int32_t max_reads_cluster;     /* final reads per chain accepted by cluster editing */
     int32_t max_positions;         /* bubbles per chain */
+    int32_t max_clusters_position; /* clusters present at one position (coverage / consensus stage); more ->
+                                      AHS_CHAIN_TOO_LARGE for that chain */
+    int32_t reserved[3];
 } ahs_limits;
 
 int  ahs_abi_version(void);
@@ -173,6 +182,14 @@ int  ahs_pin_host(const void *ptr, uint64_t bytes);
 int  ahs_unpin_host(const void *ptr);
 
 const char *ahs_last_error(void);
+
+/*
+ * Diagnostic: sort n (key, value) pairs in place exactly as libstdc++'s std::sort does with a comparator that
+ * looks at the key only (ascending, or descending if `descending` != 0) — the device routine that replays
+ * ReadSet::sort() (alignmentstoreadset.cpp:297) and the cluster sort (:720), heap-sort fall-back included.
+ * Host arrays in, host arrays out; runs one device thread.  For the parity tests.
+ */
+int  ahs_debug_std_sort(int32_t *keys, int32_t *values, int32_t n, int descending, int device);
 
 /* Cost model used for LPT sharding (cells + pairs + DP work), exposed for the host tools. */
 double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_nodes, int ploidy);

@@ -309,6 +309,30 @@ int ahs_oracle_cluster(int n, int64_t n_pairs, const int32_t* pi, const int32_t*
     return (int)cl.size();
 }
 
+// libstdc++'s own std::sort on (key, value) pairs with a comparator that looks at the key only: the behaviour
+// ReadSet::sort() (reference src/alignmentstoreadset.cpp:297) and the cluster sort (:720) have in the reference binary.
+void ahs_oracle_std_sort(int32_t* keys, int32_t* values, int32_t n, int descending) {
+    std::vector<std::pair<int32_t, int32_t>> a(n);
+    for (int i = 0; i < n; i++) a[i] = {keys[i], values[i]};
+    if (descending) std::sort(a.begin(), a.end(), [](const std::pair<int32_t, int32_t>& x, const std::pair<int32_t, int32_t>& y) { return x.first > y.first; });
+    else std::sort(a.begin(), a.end(), [](const std::pair<int32_t, int32_t>& x, const std::pair<int32_t, int32_t>& y) { return x.first < y.first; });
+    for (int i = 0; i < n; i++) { keys[i] = a[i].first; values[i] = a[i].second; }
+}
+
+// McIlroy's adversary ("A killer adversary for quicksort", 1999) run against std::sort itself: returns keys that drive
+// libstdc++'s introsort to its depth limit, i.e. into the heap-sort fall-back.
+void ahs_oracle_antiqsort(int32_t n, int32_t* keys_out) {
+    std::vector<int32_t> val(n, n - 1), ptr(n);
+    const int32_t gas = n - 1; int32_t nsolid = 0, candidate = 0;
+    for (int i = 0; i < n; i++) ptr[i] = i;
+    std::sort(ptr.begin(), ptr.end(), [&](int32_t x, int32_t y) {
+        if (val[x] == gas && val[y] == gas) { if (x == candidate) val[x] = nsolid++; else val[y] = nsolid++; }
+        if (val[x] == gas) candidate = x; else if (val[y] == gas) candidate = y;
+        return val[x] < val[y];
+    });
+    for (int i = 0; i < n; i++) keys_out[i] = val[i];
+}
+
 int ahs_oracle_log_tables(int64_t* ln, int64_t* ln1) {
     const LogTables& T = log_tables();
     memcpy(ln, T.ln, sizeof(T.ln)); memcpy(ln1, T.ln1, sizeof(T.ln1));

@@ -24,6 +24,10 @@ def load():
         lib.ahs_oracle_cluster.argtypes = [C.c_int, C.c_int64, i32p, i32p, i32p, C.c_int, i32p]
         lib.ahs_oracle_cluster.restype = C.c_int
         lib.ahs_oracle_log_tables.argtypes = [i64p, i64p]
+        lib.ahs_oracle_std_sort.argtypes = [i32p, i32p, C.c_int32, C.c_int]
+        lib.ahs_oracle_std_sort.restype = None
+        lib.ahs_oracle_antiqsort.argtypes = [C.c_int32, i32p]
+        lib.ahs_oracle_antiqsort.restype = None
         _lib = lib
     return _lib
 
@@ -66,3 +70,20 @@ def oracle_cluster(n, pi, pj, pw, paranoid=False):
     k = lib.ahs_oracle_cluster(n, len(pi), pi.ctypes.data_as(i32p), pj.ctypes.data_as(i32p), pw.ctypes.data_as(i32p), int(paranoid),
                                label.ctypes.data_as(i32p))
     return k, label[:n]
+
+
+def oracle_std_sort(keys, values, descending=False):
+    """libstdc++ std::sort on (key, value) pairs, comparator on the key only.  Returns sorted copies."""
+    lib = load()
+    k = np.ascontiguousarray(keys, dtype=np.int32).copy(); v = np.ascontiguousarray(values, dtype=np.int32).copy()
+    i32p = C.POINTER(C.c_int32)
+    lib.ahs_oracle_std_sort(k.ctypes.data_as(i32p), v.ctypes.data_as(i32p), len(k), int(descending))
+    return k, v
+
+
+def oracle_antiqsort(n):
+    """Keys that drive libstdc++'s introsort into its heap-sort fall-back (McIlroy's adversary)."""
+    lib = load()
+    k = np.zeros(max(n, 1), dtype=np.int32)
+    lib.ahs_oracle_antiqsort(n, k.ctypes.data_as(C.POINTER(C.c_int32)))
+    return k[:n]

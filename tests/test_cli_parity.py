@@ -9,7 +9,7 @@ the text format of README.md:28-42) to the reference text itself.
 
   * not gpu: host drop-in (flatten + emission) with the CPU oracle behind the C ABI
              (oracle/_ref/Ahsoka_flat_oracle) must reproduce those files byte for byte;
-  * gpu:     the same drop-in with the CUDA library behind the C ABI (oracle/_ref/Ahsoka_b200).
+  * gpu:     the same drop-in with the CUDA library behind the C ABI (ahsoka_b200/bin/Ahsoka_b200).
 Neither test reads /root/reference at run time (the binaries are prebuilt and travel to the GPU box).
 """
 import json
@@ -22,6 +22,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+B200_CLI = os.path.join(ROOT, "ahsoka_b200", "bin", "Ahsoka_b200")
 
 CASES = [c for c in json.load(open(os.path.join(GOLDEN, "index.json")))["cases"] if "ref_result" in c]
 
@@ -75,9 +76,9 @@ def test_reference_verbatim_binary_still_reproduces_golden(case):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_b200_cli_matches_reference_verbatim(case):
-    exe = os.path.join(REF_DIR, "Ahsoka_b200")
+    exe = B200_CLI
     if not os.path.exists(exe):
-        pytest.skip("oracle/_ref/Ahsoka_b200 not built (needs /root/reference at build time)")
+        pytest.skip("ahsoka_b200/bin/Ahsoka_b200 not built (needs /root/reference at build time)")
     want = open(os.path.join(GOLDEN, case["ref_result"])).read()
     with tempfile.TemporaryDirectory() as td:
         _stage(case, td)
@@ -89,3 +90,41 @@ def test_b200_cli_matches_reference_verbatim(case):
                 _stage(case, td2)
                 _, out_cpu = _run_cli(ora, case, td2)
             assert _hap_lines(out_gpu) == _hap_lines(out_cpu)
+
+
+# ---- BASELINE.json configs[0] (cfg1: one chain of 1000 bubbles, 2k reads) through the CLI.  The GFA / GAF pair is
+# re-generated from the seed (14 MB of text is not committed); tests/golden/cfg1.inputs.md5 pins it to the files
+# tests/golden/cfg1.ref-result.txt was produced from by oracle/_ref/Ahsoka_ref (reference sources verbatim + shim).
+def _cfg1_inputs(td):
+    import hashlib
+    import sys
+    sys.path.insert(0, ROOT)
+    from ahsoka_b200 import synth
+    synth.generate(synth.config("cfg1"), os.path.join(td, "cfg1"))
+    md5 = [hashlib.md5(open(os.path.join(td, "cfg1" + ext), "rb").read()).hexdigest() for ext in (".gfa", ".gaf")]
+    assert md5 == open(os.path.join(GOLDEN, "cfg1.inputs.md5")).read().split(), "generator drifted: cfg1 inputs differ from the golden run's"
+
+
+def _cfg1_cli(exe):
+    want = open(os.path.join(GOLDEN, "cfg1.ref-result.txt")).read()
+    with tempfile.TemporaryDirectory() as td:
+        _cfg1_inputs(td)
+        out = os.path.join(td, "out")
+        r = subprocess.run([exe, "phase", "-g", os.path.join(td, "cfg1.gfa"), "-a", os.path.join(td, "cfg1.gaf"), "-o", out, "-t", "1"],
+                           cwd=td, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert open(out + "-result.txt").read() == want
+
+
+def test_cfg1_flat_oracle_cli_matches_reference_verbatim():
+    exe = os.path.join(REF_DIR, "Ahsoka_flat_oracle")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/Ahsoka_flat_oracle not built (needs /root/reference at build time)")
+    _cfg1_cli(exe)
+
+
+@pytest.mark.gpu
+def test_cfg1_b200_cli_matches_reference_verbatim():
+    if not os.path.exists(B200_CLI):
+        pytest.skip("ahsoka_b200/bin/Ahsoka_b200 not built (needs /root/reference at build time)")
+    _cfg1_cli(B200_CLI)

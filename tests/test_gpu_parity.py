@@ -174,11 +174,60 @@ def test_phasing_recovers_the_simulated_haplotypes():
 
 
 def test_multi_device_lpt_gather():
-    if api.load_library().ahs_device_count() < 2:
+    # one batch dealt over the devices of the box (heavy chains one by one, the tail in ranges of consecutive chains,
+    # LPT), every device writing its ranges straight into the output arrays.  Needs >= 2 GPUs: on a one-GPU box the
+    # same assertion runs inside `bench.py --gpus 2` (key "multi" of the JSON line).
+    n = api.load_library().ahs_device_count()
+    if n < 2:
         pytest.skip("needs two CUDA devices")
     b = synth.generate(synth.config("cfg2", 0.02))
-    got = api.phase_batch(b, devices=[0, 1])
-    assert not got.diff(oracle_phase(b))
+    want = oracle_phase(b)
+    for devs in ([0, 1], list(range(n))):
+        got = api.phase_batch(b, devices=devs)
+        assert not got.diff(want)
+    skew = synth.generate(synth.params(2, 300, 2, 40, 2, 400, 1.2, 3, depth=30.0, seed=77))       # Zipf-skewed chain sizes
+    assert not api.phase_batch(skew, devices=[0, 1]).diff(oracle_phase(skew))
+    with pytest.raises(RuntimeError, match="listed twice"):
+        api.phase_batch(b, devices=[0, 0])
+
+
+def test_multi_device_call_on_one_device_equals_single_call():
+    # the multi-device entry point with one device is the single-device path (runs on any box)
+    b = synth.generate(synth.config("cfg2", 0.01))
+    assert not api.phase_batch(b, devices=[0]).diff(oracle_phase(b))
+
+
+@pytest.mark.parametrize("desc", [False, True])
+def test_std_sort_replay_including_the_heap_sort_fallback(desc):
+    # ReadSet::sort() (alignmentstoreadset.cpp:297) and the cluster sort (:720) are libstdc++ std::sort calls with a
+    # comparator on the key only; the device replays them move for move.  Inputs: ties, already sorted keys (what
+    # ReadSet::sort sees), permutations, and McIlroy's adversary, which drives introsort into its heap-sort fall-back.
+    from tests.oracle_binding import oracle_antiqsort, oracle_std_sort
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 15, 16, 17, 33, 100, 128, 129, 1000, 8191, 20000):
+        cases = [rng.integers(0, 50, n), np.sort(rng.integers(0, max(2, n // 8), n)), rng.permutation(n)]
+        k = oracle_antiqsort(n)
+        cases.append(-k if desc else k)
+        for keys in cases:
+            vals = np.arange(n, dtype=np.int32)
+            gk, gv = api.debug_std_sort(keys, vals, desc)
+            wk, wv = oracle_std_sort(keys, vals, desc)
+            assert np.array_equal(gk, wk) and np.array_equal(gv, wv), (n, desc)
+
+
+def test_cfg4_shape_tetraploid_chains_of_200_to_330_reads():
+    # BASELINE configs[3] at its shape: ploidy 4, 60x -> 200-330 final reads per chain: HBM-resident scoring, the
+    # big-chain cluster editing and the 4096-state threading DP together
+    b = synth.generate(synth.config("cfg4", 0.005))
+    got = _check(b)
+    assert b.ploidy == 4 and got.n_chains_ok == b.n_chains
+    assert int(np.diff(got.read_off).max()) > 250
+
+
+def test_tetraploid_more_than_eight_alleles():
+    # ploidy 4 with up to 12 alleles per bubble: 4-bit codes and 8 clusters per DP column
+    got = _check(synth.generate(synth.params(4, 10, 1, 30, depth=60.0, max_alleles=12, seed=77)))
+    assert got.n_chains_ok == 10
 
 
 def test_randomised_shapes_twice_each():

@@ -352,9 +352,9 @@ def _cli_files(exe, td, tag, gfa_text, gaf_bytes, ploidy):
 def test_b200_cli_equals_oracle_cli_on_polyploid_graphs(ploidy, seed):
     # the whole drop-in (native host stages + CUDA library) against the same host with the CPU oracle behind the C ABI
     from ahsoka_b200 import synth
-    cuda_exe = os.path.join(ROOT, "oracle", "_ref", "Ahsoka_b200")
+    cuda_exe = os.path.join(ROOT, "ahsoka_b200", "bin", "Ahsoka_b200")
     if not os.path.exists(cuda_exe):
-        pytest.skip("oracle/_ref/Ahsoka_b200 not built")
+        pytest.skip("ahsoka_b200/bin/Ahsoka_b200 not built")
     gfa, gaf = _synth_text(synth.params(ploidy, 12, 1, 14, depth=12.0 * ploidy, seed=seed))
     with tempfile.TemporaryDirectory() as td:
         assert _cli_files(cuda_exe, td, "cuda", gfa, gaf, ploidy) == _cli_files(EXE, td, "cpu", gfa, gaf, ploidy)

@@ -1,7 +1,7 @@
-"""Stage times of the drop-in CLI (`oracle/_ref/Ahsoka_b200 phase -g G -a A -o P`) on a GFA/GAF rendering of a
+"""Stage times of the drop-in CLI (`ahsoka_b200/bin/Ahsoka_b200 phase -g G -a A -o P`) on a GFA/GAF rendering of a
 BASELINE workload sample: reference host translation units for GFA parsing / bubble detection, this repo's
 GAF reader, allele-path enumeration, flattening, CUDA phasing and emission.
-    python tools/cli_e2e.py --workload cfg2 --scale 0.1 [--host reference] [--exe oracle/_ref/Ahsoka_b200]
+    python tools/cli_e2e.py --workload cfg2 --scale 0.1 [--host reference] [--exe ahsoka_b200/bin/Ahsoka_b200]
 Prints one JSON line: {"stages_ms": {...}, "wall_s": ..., "lines": ..., "chains": ...}.
 """
 import argparse
@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--scale", type=float, default=0.1)
     ap.add_argument("--host", default="native", choices=["native", "reference"])
-    ap.add_argument("--exe", default=os.path.join(ROOT, "oracle", "_ref", "Ahsoka_b200"))
+    ap.add_argument("--exe", default=os.path.join(ROOT, "ahsoka_b200", "bin", "Ahsoka_b200"))
     ap.add_argument("--threads", type=int, default=1, help="-t of the CLI (the reader uses all cores when 1)")
     ap.add_argument("--repeat", type=int, default=2, help="runs; the last one is reported (first warms the page cache / CUDA context)")
     a = ap.parse_args()

@@ -34,6 +34,7 @@
 #include "common.cuh"
 #include "device_batch.cuh"
 #include "k_score.cuh"
+#include "k_select.cuh"
 
 namespace ahs {
 
@@ -106,81 +107,68 @@ __device__ __forceinline__ int cc_min_key(int mine, int32_t* cell, int tid, int&
     return r;
 }
 
-// shared-memory footprint of the scoring kernel
-// the last term is the per-warp scratch of the rate sort: the partners of one read, compacted (< nmax keys of 8 bytes)
-__host__ __device__ inline size_t cs_smem_bytes(int nmax, int nt) {
-    return (((size_t)nmax * cc_ns(nmax) * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15) + (size_t)(nt / 32) * nmax * 8;
-}
-
-// ascending bitonic sort of 32*KPL keys (uint32_t or uint64_t) held KPL per lane (element e = s*32 + lane)
-template <int KPL, class T>
-__device__ __forceinline__ void warp_sort(T (&v)[KPL], int lane) {
-#pragma unroll
-    for (int kk = 2; kk <= 32 * KPL; kk <<= 1) {
-#pragma unroll
-        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-            if (jj >= 32) {
-#pragma unroll
-                for (int s = 0; s < KPL; s++) {
-                    if ((s & (jj >> 5)) == 0) {
-                        const int s2 = s | (jj >> 5);
-                        const bool up = ((s * 32) & kk) == 0;          // lane bits are below jj >= 32 <= kk/2
-                        const T a = v[s], b = v[s2];
-                        if ((a > b) == up) { v[s] = b; v[s2] = a; }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int s = 0; s < KPL; s++) {
-                    const bool up = ((s * 32 + lane) & kk) == 0;
-                    const T other = __shfl_xor_sync(0xffffffffu, v[s], jj);
-                    const bool keep_min = ((lane & jj) == 0) == up;
-                    v[s] = keep_min ? (other < v[s] ? other : v[s]) : (other > v[s] ? other : v[s]);
-                }
-            }
-        }
-    }
-}
-
-// Rule R1's pooling for one read: the m partner keys in ws[0..m) (any order) are sorted as 32*K2 >= m keys, the `cut`
-// lowest rates are pooled as same-haplotype pairs, the rest as different-haplotype pairs.  K_BITS / N_SHIFT / MASK give
-// the (k, n) fields of a key.
-template <int K2, class T, int N_SHIFT, int MASK>
-__device__ __forceinline__ void cs_pool(const T* __restrict__ ws, int m, int cut, int lane, int& Ks, int& Ns, int& Kd, int& Nd) {
-    T v[K2];
-#pragma unroll
-    for (int s = 0; s < K2; s++) v[s] = s * 32 + lane < m ? ws[s * 32 + lane] : (T)~(T)0;
-    warp_sort<K2>(v, lane);
-#pragma unroll
-    for (int s = 0; s < K2; s++) if (s * 32 + lane < m) {
-        const int kq = (int)(v[s] & (T)MASK), nq = (int)((v[s] >> N_SHIFT) & (T)MASK);
-        if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
-    }
-}
-template <int KPL, class T, int N_SHIFT, int MASK>
-__device__ __forceinline__ void cs_pool_any(const T* __restrict__ ws, int m, int cut, int lane, int& Ks, int& Ns, int& Kd, int& Nd) {
-    if (m <= 32) cs_pool<1, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
-    else if (KPL >= 2 && m <= 64) cs_pool<(KPL >= 2 ? 2 : 1), T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
-    else if (KPL >= 8 && m <= 128) cs_pool<(KPL >= 8 ? 4 : 1), T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
-    else cs_pool<KPL, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
-}
-
 // ------------------------------------------------------------------------------------------------
 // K2: read-pair scoring of one chain per block (rule R1).  Wout[cw_off[c] + pair number] = Q10 weight,
 // pair number = position of (x,y), x < y, in the row-major upper triangle.
+//
+// Reads are sorted by first position, so the partners y > x of read x form the index band first[y] <= last[x]:
+// only the band is scored (16 lanes per row x, lanes over y; no pair-number arithmetic).
+//   pass 1  every band pair: overlap n and disagreements k by AND / XOR / popcount over the words of the shared
+//           span.  n <= 254 ("narrow": the chain's longest read spans < 255 bubbles): the pair's ORDER KEY
+//           floor(65534 k/n) << 16 | n << 8 | k goes into both triangles of KEY[n][n|1] and (n << 8 | k) into NK16[pair].
+//           Distinct rates with denominators <= 255 differ by more than 1/65534, so the 32-bit key orders exactly like
+//           rule R1's (k/n, n, k); the division is a multiplication by a reciprocal table.
+//   pass 2  local rates, ONE THREAD PER READ: rule R1 needs only the partition of a read's partners at rank
+//           cut = max(1, m/p), not their order, and pairs with equal keys are interchangeable.  The thread finds it by
+//           radix selection over its row of KEY (64-bucket byte histogram per level, most significant 6 bits first;
+//           keys below the threshold bucket are pooled as same-haplotype pairs, keys above as different-haplotype
+//           pairs, the bucket itself is compacted and refined) — fixed trip counts, 32 reads per warp instruction.
+//   pass 3  fixed-point log-likelihood ratio of every band pair from NK16 and the reads' rates; zeros elsewhere.
+// Chains with a read of 255+ bubbles ("wide") keep (n << 16 | k) in KEY and rank by exact cross products.
 // ------------------------------------------------------------------------------------------------
-template <int BITS, int NT, int KPL>
+constexpr int CS_GROUP = 16;                          // lanes per row in the pair passes
+
+__host__ __device__ inline size_t cs_smem_bytes(int nmax, int nt) {
+    size_t b = (size_t)nmax * cc_ns(nmax) * 4;                          // KEY
+    b += ((size_t)nmax * (nmax - 1) / 2 * 2 + 15) & ~(size_t)15;       // NK16
+    b += (size_t)nmax * 17 * 4; (void)nt;                               // per-read byte histograms (64 counters + pad)
+    b += (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 16;              // first, last, es, ed
+    b += 1025 * 4 * 2 + 256 * 4 + 64;                                   // log tables (int32), reciprocals, scalars
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int BITS>
+__device__ __forceinline__ void span_nk(const uint32_t* __restrict__ rx, const uint32_t* __restrict__ ry, int lo_b, int hi_b, int& n, int& k) {
+    constexpr int PW = 32 / BITS;
+    n = 0; k = 0;
+    for (int w = lo_b / PW; w <= hi_b / PW; w++) word_nk<BITS>(__ldg(rx + w), __ldg(ry + w), n, k);
+}
+
+template <int BITS, int NT>
 __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
                                                     int32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char cc_sm[];
-    constexpr int NW = NT / 32;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int ns = cc_ns(nmax);
-    int32_t* W = (int32_t*)cc_sm;
-    int32_t* first = W + (size_t)nmax * ns; int32_t* last = first + nmax;
-    int32_t* scal = last + nmax;
-    uint16_t* es = (uint16_t*)(scal + 16); uint16_t* ed = es + nmax;
-    uint64_t* wkeys = (uint64_t*)(cc_sm + (((size_t)nmax * ns * 4 + (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 64) + 15 & ~(size_t)15)) + (size_t)wid * nmax;
+    uint32_t* KEY; uint16_t* NK16; uint32_t* hist; int32_t *first, *last, *lnS, *ln1S, *scal; uint32_t* rcp; uint16_t *es, *ed;
+    {
+        unsigned char* p = cc_sm;
+        KEY = (uint32_t*)p; p += (size_t)nmax * ns * 4;
+        NK16 = (uint16_t*)p; p += ((size_t)nmax * (nmax - 1) / 2 * 2 + 15) & ~(size_t)15;
+        hist = (uint32_t*)p; p += (size_t)nmax * 17 * 4;
+        first = (int32_t*)p; p += nmax * 4; last = (int32_t*)p; p += nmax * 4;
+        es = (uint16_t*)p; p += nmax * 2; ed = (uint16_t*)p; p += nmax * 2; p = (unsigned char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        lnS = (int32_t*)p; p += 1025 * 4; ln1S = (int32_t*)p; p += 1025 * 4;
+        rcp = (uint32_t*)p; p += 256 * 4;
+        scal = (int32_t*)p;
+    }
+    // tables, once per block: |ln| * 2^20 < 2^23 fits int32; rcp[n] = floor(2^32 / n) + 1 makes __umulhi(a, rcp[n]) = floor(a / n)
+    // for a < 2^24, 2 <= n <= 255 (the error a * (rcp n - 2^32) / (n 2^32) < 2^-8 < 1/n)
+    for (int x = tid; x <= 1024; x += NT) { lnS[x] = (int32_t)d.ln[x]; ln1S[x] = (int32_t)d.ln1[x]; }
+    for (int x = tid; x < 256; x += NT) rcp[x] = cs_rcp((uint32_t)x);
+    const unsigned gm = grp_mask<CS_GROUP>();
+    const int gl = lane % CS_GROUP, grp = tid / CS_GROUP;
+    constexpr int NG = NT / CS_GROUP;
     int64_t pairs_total = 0;
     while (true) {
         __syncthreads();
@@ -191,102 +179,97 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
         const int c = chains[item];
         const int64_t f0 = d.frow_off[c];
         const int n = (int)(d.frow_off[c + 1] - f0);
-        const int tri = n * (n - 1) / 2;
         const int words = d.ch_words[c];
         const uint32_t* rows = d.codes + d.code_off[c];
         int32_t* Wout = d.W + d.cw_off[c];
-        for (int x = tid; x < n; x += NT) { first[x] = d.fr_first[f0 + x]; last[x] = d.fr_last[f0 + x]; W[x * ns + x] = 0; }
+        const bool narrow = d.ch_maxspan[c] < 254;                    // overlaps n <= span <= 254
+        for (int x = tid; x < n; x += NT) { first[x] = d.fr_first[f0 + x]; last[x] = d.fr_last[f0 + x]; }
+        for (int x = tid; x < n * ns; x += NT) KEY[x] = CS_INVALID;
+        if (tid < n) { uint32_t* hw = hist + tid * 17; for (int w = 0; w < 16; w++) hw[w] = 0; }
         __syncthreads();
-        // pair (x0,y0) = pair number tid (row x of the triangle starts at x(2n-x-1)/2); pair number tid + k NT is
-        // reached by stepping NT places along the rows
-        int x0 = 0, y0 = 1;
-        if (tid < tri) {
-            const float tn = (float)(2 * n - 1);
-            int x = (int)((tn - sqrtf(tn * tn - 8.0f * (float)tid)) * 0.5f);
-            x = max(0, min(x, n - 2));
-            while (x > 0 && ((x * (2 * n - x - 1)) >> 1) > tid) x--;
-            while ((((x + 1) * (2 * n - x - 2)) >> 1) <= tid) x++;
-            x0 = x; y0 = x + 1 + tid - ((x * (2 * n - x - 1)) >> 1);
-        }
-        // overlap / disagreement counts, once per pair; W holds (n << 16 | k) for now
-        {
-            int x = x0, y = y0;
-            for (int ti = tid; ti < tri; ti += NT) {
-                int nk = 0;
-                if (first[y] <= last[x]) {                               // reads are sorted by first position
-                    int nn, kk; pair_nk<BITS>(rows + (int64_t)x * words, rows + (int64_t)y * words, first[y], min(last[x], last[y]), nn, kk);
-                    if (nn > 0) nk = (nn << 16) | kk;
+        // ---- pass 1: counts of the band pairs
+        for (int x = grp; x < n - 1; x += NG) {
+            const int lx = last[x];
+            const uint32_t* rx = rows + (int64_t)x * words;
+            const int rowbase = ((x * (2 * n - x - 1)) >> 1) - (x + 1);          // pair number of (x,y) = rowbase + y
+            for (int y0 = x + 1; y0 < n; y0 += CS_GROUP) {
+                const int y = y0 + gl;
+                const bool valid = y < n;
+                const int fy = valid ? first[y] : INT32_MAX;
+                const bool inband = fy <= lx;
+                if (inband) {
+                    int nn, kk; span_nk<BITS>(rx, rows + (int64_t)y * words, fy, min(lx, last[y]), nn, kk);
+                    if (narrow) {
+                        NK16[rowbase + y] = (uint16_t)((nn << 8) | kk);
+                        if (nn > 0) { const uint32_t key = cs_order_key((uint32_t)nn, (uint32_t)kk, rcp[nn]); KEY[x * ns + y] = key; KEY[y * ns + x] = key; }
+                    } else if (nn > 0) { const uint32_t nk = ((uint32_t)nn << 16) | (uint32_t)kk; KEY[x * ns + y] = nk; KEY[y * ns + x] = nk; }
+                    else KEY[x * ns + y] = 0u;                                    // wide: in band, no shared position (pass 3 reads KEY)
                 }
-                W[x * ns + y] = nk; W[y * ns + x] = nk;
-                if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
+                if (!__any_sync(gm, inband)) break;                               // first[] ascends: the rest of the row is out of band too
             }
         }
         __syncthreads();
-        // local rates per read (one warp per read): the partners' Hamming rates are sorted in registers, the
-        // cut = max(1, m/p) lowest are pooled as same-haplotype pairs, the rest as different-haplotype pairs.
-        // A chain of at most 255 bubbles has overlaps n <= 255: (floor(65535 k / n), n, k) then fits 32 bits and
-        // orders exactly like the 62-bit key (two distinct rates with denominators <= 255 differ by > 1/65535).
-        {
-            int pl = 0;
-            const bool narrow = d.bubble_off[c + 1] - d.bubble_off[c] <= 255;
-            for (int i = wid; i < n; i += NW) {
-                int m = 0, Ks = 0, Ns = 0, Kd = 0, Nd = 0;
-                // the partners' keys are compacted into the warp's scratch first: a read of a 75-read chain has ~35
-                // partners, so 32 or 64 keys are sorted instead of 32*KPL
-                if (narrow) {
-                    uint32_t* ws = (uint32_t*)wkeys;
-#pragma unroll
-                    for (int s = 0; s < KPL; s++) {
-                        const int j = s * 32 + lane;
-                        const int nk = j < n ? W[i * ns + j] : 0;
-                        const uint32_t nq = (uint32_t)nk >> 16, kq = (uint32_t)nk & 0xffffu;
-                        const uint32_t bal = __ballot_sync(0xffffffffu, nk != 0);
-                        if (nk) ws[m + __popc(bal & ((1u << lane) - 1u))] = (((kq * 65535u) / nq) << 16) | (nq << 8) | kq;
-                        m += __popc(bal);
+        // ---- pass 2: local rates, one thread per read
+        if (tid < n) {
+            uint32_t* row = KEY + tid * ns;
+            int Ks = 0, Ns = 0, Kd = 0, Nd = 0, m = 0;
+            if (narrow) {
+                cs_pool_select(row, n, d.ploidy, hist + tid * 17, Ks, Ns, Kd, Nd, m);
+            } else {
+                // wide: exact order (k_a n_b < k_b n_a, then n, then k) by counting, O(m^2)
+                for (int j = 0; j < n; j++) { const uint32_t v = row[j]; m += (v != CS_INVALID && v != 0u) ? 1 : 0; }
+                const int cut = m ? max(1, m / d.ploidy) : 0;
+                for (int a = 0; a < n && m; a++) {
+                    const uint32_t va = row[a];
+                    if (va == CS_INVALID || va == 0u) continue;
+                    const long long na = va >> 16, ka = va & 0xffffu;
+                    int r = 0;
+                    for (int b = 0; b < n; b++) {
+                        const uint32_t vb = row[b];
+                        if (vb == CS_INVALID || vb == 0u) continue;
+                        const long long nb = vb >> 16, kb = vb & 0xffffu;
+                        const long long l = kb * na, rr = ka * nb;                // b before a ?
+                        const bool less = l != rr ? l < rr : (nb != na ? nb < na : (kb != ka ? kb < ka : b < a));
+                        r += less ? 1 : 0;
                     }
-                    __syncwarp();
-                    if (m > 0) cs_pool_any<KPL, uint32_t, 8, 0xff>(ws, m, max(1, m / d.ploidy), lane, Ks, Ns, Kd, Nd);
-                } else {
-                    uint64_t* ws = wkeys;
-#pragma unroll
-                    for (int s = 0; s < KPL; s++) {
-                        const int j = s * 32 + lane;
-                        const int nk = j < n ? W[i * ns + j] : 0;
-                        const uint32_t bal = __ballot_sync(0xffffffffu, nk != 0);
-                        if (nk) ws[m + __popc(bal & ((1u << lane) - 1u))] = rate_key(nk >> 16, nk & 0xffff);
-                        m += __popc(bal);
-                    }
-                    __syncwarp();
-                    if (m > 0) cs_pool_any<KPL, uint64_t, 15, 0x7fff>(ws, m, max(1, m / d.ploidy), lane, Ks, Ns, Kd, Nd);
+                    if (r < cut) { Ks += (int)ka; Ns += (int)na; } else { Kd += (int)ka; Nd += (int)na; }
                 }
-                __syncwarp();                                   // the scratch is rewritten for the warp's next read
-                uint32_t es_i = 0, ed_i = 0;
-                if (m > 0) {
-                    Ks = warp_sum_i32(Ks); Ns = warp_sum_i32(Ns); Kd = warp_sum_i32(Kd); Nd = warp_sum_i32(Nd);
-                    if (narrow) {                               // sums of < CC_MAXN values <= 255: the numerators fit 32 bits
-                        es_i = ((uint32_t)Ks * 1024u + (uint32_t)Ns / 2u) / (uint32_t)Ns;
-                        ed_i = Nd > 0 ? ((uint32_t)Kd * 1024u + (uint32_t)Nd / 2u) / (uint32_t)Nd : es_i;
-                    } else {
-                        es_i = (uint32_t)(((int64_t)Ks * 1024 + Ns / 2) / Ns);
-                        ed_i = Nd > 0 ? (uint32_t)(((int64_t)Kd * 1024 + Nd / 2) / Nd) : es_i;
-                    }
-                }
-                if (lane == 0) { es[i] = (uint16_t)es_i; ed[i] = (uint16_t)ed_i; }
-                pl += m;
             }
-            if (lane == 0) pairs_total += pl;
+            uint32_t es_i = 0, ed_i = 0;
+            if (m > 0) {
+                es_i = (uint32_t)(((int64_t)Ks * 1024 + Ns / 2) / Ns);
+                ed_i = Nd > 0 ? (uint32_t)(((int64_t)Kd * 1024 + Nd / 2) / Nd) : es_i;
+            }
+            es[tid] = (uint16_t)es_i; ed[tid] = (uint16_t)ed_i;
+            pairs_total += m;
         }
         __syncthreads();
-        // pair weights (fixed-point log likelihood ratio), 4 B per pair to HBM
-        {
-            int x = x0, y = y0;
-            for (int ti = tid; ti < tri; ti += NT) {
-                const int nk = W[x * ns + y];
-                Wout[ti] = nk ? pair_weight(d, nk >> 16, nk & 0xffff, es[x], ed[x], es[y], ed[y]) : 0;
-                if (ti + NT < tri) { y += NT; while (y >= n) { y = y - n + x + 2; x++; } }
+        // ---- pass 3: pair weights (fixed-point log likelihood ratio), 4 B per pair to HBM
+        for (int x = grp; x < n - 1; x += NG) {
+            const int lx = last[x];
+            const int esx = es[x], edx = ed[x];
+            const int rowbase = ((x * (2 * n - x - 1)) >> 1) - (x + 1);
+            for (int y = x + 1 + gl; y < n; y += CS_GROUP) {
+                int w = 0;
+                if (first[y] <= lx) {
+                    int nn, kk;
+                    if (narrow) { const int nk = NK16[rowbase + y]; nn = nk >> 8; kk = nk & 255; }
+                    else { const uint32_t nk = KEY[x * ns + y]; nn = (int)(nk >> 16); kk = (int)(nk & 0xffffu); }      // this triangle is not permuted in the wide path
+                    if (nn > 0) {
+                        int e1 = (esx + es[y]) >> 1, e2 = (edx + ed[y]) >> 1;
+                        e1 = min(max(e1, 10), 460);
+                        e2 = min(max(e2, e1 + 51), 972);
+                        const int64_t s20 = (int64_t)kk * (lnS[e1] - lnS[e2]) + (int64_t)(nn - kk) * (ln1S[e1] - ln1S[e2]);
+                        int64_t wv = floordiv1024(s20);
+                        wv = wv > W_CLAMP ? W_CLAMP : (wv < -W_CLAMP ? -W_CLAMP : wv);
+                        w = (int)wv;
+                    }
+                }
+                Wout[rowbase + y] = w;
             }
         }
     }
+    pairs_total = warp_sum_i64(pairs_total);
     if (lane == 0 && pairs_total) atomicAdd((unsigned long long*)d.tot_pairs, (unsigned long long)pairs_total);
 }
 

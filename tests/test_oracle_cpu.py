@@ -165,3 +165,13 @@ def test_golden_fixtures():
         got = oracle_phase(b)
         for k in got.ARRAYS:
             assert np.array_equal(getattr(got, k), want[k]), (case["name"], k)
+
+
+def test_radix_selection_of_the_scoring_kernel_equals_rule_r1_by_sorting(tmp_path):
+    # the product's own statements (ahsoka_b200/csrc/k_select.cuh, host-compilable) against a sort-based restatement
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "select_harness")
+    subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "native", "select_harness.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe, "60000"], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout

@@ -107,6 +107,59 @@ __device__ __forceinline__ int cc_min_key(int mine, int32_t* cell, int tid, int&
     return r;
 }
 
+// ascending bitonic sort of 32*KPL keys (uint32_t or uint64_t) held KPL per lane (element e = s*32 + lane)
+template <int KPL, class T>
+__device__ __forceinline__ void warp_sort(T (&v)[KPL], int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= 32 * KPL; kk <<= 1) {
+#pragma unroll
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            if (jj >= 32) {
+#pragma unroll
+                for (int s = 0; s < KPL; s++) {
+                    if ((s & (jj >> 5)) == 0) {
+                        const int s2 = s | (jj >> 5);
+                        const bool up = ((s * 32) & kk) == 0;          // lane bits are below jj >= 32 <= kk/2
+                        const T a = v[s], b = v[s2];
+                        if ((a > b) == up) { v[s] = b; v[s2] = a; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < KPL; s++) {
+                    const bool up = ((s * 32 + lane) & kk) == 0;
+                    const T other = __shfl_xor_sync(0xffffffffu, v[s], jj);
+                    const bool keep_min = ((lane & jj) == 0) == up;
+                    v[s] = keep_min ? (other < v[s] ? other : v[s]) : (other > v[s] ? other : v[s]);
+                }
+            }
+        }
+    }
+}
+
+// Rule R1's pooling for one read: the m partner keys in ws[0..m) (any order) are sorted as 32*K2 >= m keys, the `cut`
+// lowest rates are pooled as same-haplotype pairs, the rest as different-haplotype pairs.  K_BITS / N_SHIFT / MASK give
+// the (k, n) fields of a key.
+template <int K2, class T, int N_SHIFT, int MASK>
+__device__ __forceinline__ void cs_pool(const T* __restrict__ ws, int m, int cut, int lane, int& Ks, int& Ns, int& Kd, int& Nd) {
+    T v[K2];
+#pragma unroll
+    for (int s = 0; s < K2; s++) v[s] = s * 32 + lane < m ? ws[s * 32 + lane] : (T)~(T)0;
+    warp_sort<K2>(v, lane);
+#pragma unroll
+    for (int s = 0; s < K2; s++) if (s * 32 + lane < m) {
+        const int kq = (int)(v[s] & (T)MASK), nq = (int)((v[s] >> N_SHIFT) & (T)MASK);
+        if (s * 32 + lane < cut) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; }
+    }
+}
+template <int KPL, class T, int N_SHIFT, int MASK>
+__device__ __forceinline__ void cs_pool_any(const T* __restrict__ ws, int m, int cut, int lane, int& Ks, int& Ns, int& Kd, int& Nd) {
+    if (m <= 32) cs_pool<1, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+    else if (KPL >= 2 && m <= 64) cs_pool<(KPL >= 2 ? 2 : 1), T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+    else if (KPL >= 8 && m <= 128) cs_pool<(KPL >= 8 ? 4 : 1), T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+    else cs_pool<KPL, T, N_SHIFT, MASK>(ws, m, cut, lane, Ks, Ns, Kd, Nd);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: read-pair scoring of one chain per block (rule R1).  Wout[cw_off[c] + pair number] = Q10 weight,
 // pair number = position of (x,y), x < y, in the row-major upper triangle.
@@ -118,11 +171,11 @@ __device__ __forceinline__ int cc_min_key(int mine, int32_t* cell, int tid, int&
 //           floor(65534 k/n) << 16 | n << 8 | k goes into both triangles of KEY[n][n|1] and (n << 8 | k) into NK16[pair].
 //           Distinct rates with denominators <= 255 differ by more than 1/65534, so the 32-bit key orders exactly like
 //           rule R1's (k/n, n, k); the division is a multiplication by a reciprocal table.
-//   pass 2  local rates, ONE THREAD PER READ: rule R1 needs only the partition of a read's partners at rank
-//           cut = max(1, m/p), not their order, and pairs with equal keys are interchangeable.  The thread finds it by
-//           radix selection over its row of KEY (64-bucket byte histogram per level, most significant 6 bits first;
-//           keys below the threshold bucket are pooled as same-haplotype pairs, keys above as different-haplotype
-//           pairs, the bucket itself is compacted and refined) — fixed trip counts, 32 reads per warp instruction.
+//   pass 2  local rates, one warp per read: the valid keys of the read's row are compacted (ballot) and sorted in
+//           registers (bitonic, 32 / 64 / 128 / 32 KPL keys as needed); the cut = max(1, m/p) lowest are pooled as
+//           same-haplotype pairs, the rest as different-haplotype pairs.  (A one-thread-per-read radix selection —
+//           k_select.cuh, kept with its host harness — needs 36 % fewer instructions but leaves most warps of the
+//           block waiting at the barrier: measured 2.1 ms against 1.9 ms for this pass structure on cfg2.)
 //   pass 3  fixed-point log-likelihood ratio of every band pair from NK16 and the reads' rates; zeros elsewhere.
 // Chains with a read of 255+ bubbles ("wide") keep (n << 16 | k) in KEY and rank by exact cross products.
 // ------------------------------------------------------------------------------------------------
@@ -131,9 +184,9 @@ constexpr int CS_GROUP = 16;                          // lanes per row in the pa
 __host__ __device__ inline size_t cs_smem_bytes(int nmax, int nt) {
     size_t b = (size_t)nmax * cc_ns(nmax) * 4;                          // KEY
     b += ((size_t)nmax * (nmax - 1) / 2 * 2 + 15) & ~(size_t)15;       // NK16
-    b += (size_t)nmax * 17 * 4; (void)nt;                               // per-read byte histograms (64 counters + pad)
+    b += (size_t)(nt / 32) * nmax * 4;                                  // per-warp scratch of the rate sort: the compacted keys of one read
     b += (size_t)nmax * 4 * 2 + (size_t)nmax * 2 * 2 + 16;              // first, last, es, ed
-    b += 1025 * 4 * 2 + 256 * 4 + 64;                                   // log tables (int32), reciprocals, scalars
+    b += 256 * 4 + 64;                                                  // reciprocals, scalars
     return (b + 15) & ~(size_t)15;
 }
 
@@ -141,51 +194,53 @@ template <int BITS>
 __device__ __forceinline__ void span_nk(const uint32_t* __restrict__ rx, const uint32_t* __restrict__ ry, int lo_b, int hi_b, int& n, int& k) {
     constexpr int PW = 32 / BITS;
     n = 0; k = 0;
-    for (int w = lo_b / PW; w <= hi_b / PW; w++) word_nk<BITS>(__ldg(rx + w), __ldg(ry + w), n, k);
+    const int w1 = hi_b / PW;
+    for (int w = lo_b / PW; w <= w1; w += 2) {                         // two words per trip: four independent loads in flight
+        const bool two = w + 1 <= w1;
+        const uint32_t x0 = __ldg(rx + w), y0 = __ldg(ry + w);
+        const uint32_t x1 = two ? __ldg(rx + w + 1) : 0u, y1 = two ? __ldg(ry + w + 1) : 0u;
+        word_nk<BITS>(x0, y0, n, k); word_nk<BITS>(x1, y1, n, k);
+    }
 }
 
-template <int BITS, int NT>
+template <int BITS, int NT, int KPL>
 __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restrict__ chains, int n_list, int nmax,
                                                     int32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char cc_sm[];
-    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ns = cc_ns(nmax);
-    uint32_t* KEY; uint16_t* NK16; uint32_t* hist; int32_t *first, *last, *lnS, *ln1S, *scal; uint32_t* rcp; uint16_t *es, *ed;
+    uint32_t* KEY; uint16_t* NK16; uint32_t* hist; int32_t *first, *last, *scal; uint32_t* rcp; uint16_t *es, *ed;
     {
         unsigned char* p = cc_sm;
         KEY = (uint32_t*)p; p += (size_t)nmax * ns * 4;
         NK16 = (uint16_t*)p; p += ((size_t)nmax * (nmax - 1) / 2 * 2 + 15) & ~(size_t)15;
-        hist = (uint32_t*)p; p += (size_t)nmax * 17 * 4;
+        hist = (uint32_t*)p + (size_t)wid * nmax; p += (size_t)NW * nmax * 4;      // this warp's sort scratch
         first = (int32_t*)p; p += nmax * 4; last = (int32_t*)p; p += nmax * 4;
         es = (uint16_t*)p; p += nmax * 2; ed = (uint16_t*)p; p += nmax * 2; p = (unsigned char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-        lnS = (int32_t*)p; p += 1025 * 4; ln1S = (int32_t*)p; p += 1025 * 4;
         rcp = (uint32_t*)p; p += 256 * 4;
         scal = (int32_t*)p;
     }
-    // tables, once per block: |ln| * 2^20 < 2^23 fits int32; rcp[n] = floor(2^32 / n) + 1 makes __umulhi(a, rcp[n]) = floor(a / n)
-    // for a < 2^24, 2 <= n <= 255 (the error a * (rcp n - 2^32) / (n 2^32) < 2^-8 < 1/n)
-    for (int x = tid; x <= 1024; x += NT) { lnS[x] = (int32_t)d.ln[x]; ln1S[x] = (int32_t)d.ln1[x]; }
+    // reciprocal table, once per block (k_select.cuh)
     for (int x = tid; x < 256; x += NT) rcp[x] = cs_rcp((uint32_t)x);
     const unsigned gm = grp_mask<CS_GROUP>();
     const int gl = lane % CS_GROUP, grp = tid / CS_GROUP;
     constexpr int NG = NT / CS_GROUP;
     int64_t pairs_total = 0;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) scal[3] = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int item = scal[3];
-        if (item >= n_list) break;
+    (void)work_counter; (void)scal;
+    // static round robin over the class's chains (they are sorted by read count: neighbours cost the same); no work counter,
+    // so a block's next chain is known ahead and its descriptors are already on their way when the current chain ends
+    for (int item = blockIdx.x; item < n_list; item += gridDim.x) {
         const int c = chains[item];
         const int64_t f0 = d.frow_off[c];
         const int n = (int)(d.frow_off[c + 1] - f0);
+        __syncthreads();                                              // the previous chain's last pass is done with the shared arrays
         const int words = d.ch_words[c];
         const uint32_t* rows = d.codes + d.code_off[c];
         int32_t* Wout = d.W + d.cw_off[c];
         const bool narrow = d.ch_maxspan[c] < 254;                    // overlaps n <= span <= 254
         for (int x = tid; x < n; x += NT) { first[x] = d.fr_first[f0 + x]; last[x] = d.fr_last[f0 + x]; }
         for (int x = tid; x < n * ns; x += NT) KEY[x] = CS_INVALID;
-        if (tid < n) { uint32_t* hw = hist + tid * 17; for (int w = 0; w < 16; w++) hw[w] = 0; }
         __syncthreads();
         // ---- pass 1: counts of the band pairs
         for (int x = grp; x < n - 1; x += NG) {
@@ -209,31 +264,51 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
             }
         }
         __syncthreads();
-        // ---- pass 2: local rates, one thread per read
-        if (tid < n) {
-            uint32_t* row = KEY + tid * ns;
-            int Ks = 0, Ns = 0, Kd = 0, Nd = 0, m = 0;
-            if (narrow) {
-                cs_pool_select(row, n, d.ploidy, hist + tid * 17, Ks, Ns, Kd, Nd, m);
-            } else {
-                // wide: exact order (k_a n_b < k_b n_a, then n, then k) by counting, O(m^2)
-                for (int j = 0; j < n; j++) { const uint32_t v = row[j]; m += (v != CS_INVALID && v != 0u) ? 1 : 0; }
-                const int cut = m ? max(1, m / d.ploidy) : 0;
-                for (int a = 0; a < n && m; a++) {
-                    const uint32_t va = row[a];
-                    if (va == CS_INVALID || va == 0u) continue;
-                    const long long na = va >> 16, ka = va & 0xffffu;
-                    int r = 0;
-                    for (int b = 0; b < n; b++) {
-                        const uint32_t vb = row[b];
-                        if (vb == CS_INVALID || vb == 0u) continue;
-                        const long long nb = vb >> 16, kb = vb & 0xffffu;
-                        const long long l = kb * na, rr = ka * nb;                // b before a ?
-                        const bool less = l != rr ? l < rr : (nb != na ? nb < na : (kb != ka ? kb < ka : b < a));
-                        r += less ? 1 : 0;
-                    }
-                    if (r < cut) { Ks += (int)ka; Ns += (int)na; } else { Kd += (int)ka; Nd += (int)na; }
+        // ---- pass 2: local rates
+        if (narrow) {
+            const unsigned lt = (1u << lane) - 1u;
+            for (int i = wid; i < n; i += NW) {
+                const uint32_t* row = KEY + i * ns;
+                int m = 0, Ks = 0, Ns = 0, Kd = 0, Nd = 0;
+#pragma unroll
+                for (int s5 = 0; s5 < KPL; s5++) {
+                    const int j = s5 * 32 + lane;
+                    const uint32_t key = j < n ? row[j] : CS_INVALID;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, key != CS_INVALID);
+                    if (key != CS_INVALID) hist[m + __popc(bal & lt)] = key;
+                    m += __popc(bal);
                 }
+                __syncwarp();
+                if (m > 0) cs_pool_any<KPL, uint32_t, 8, 0xff>(hist, m, max(1, m / d.ploidy), lane, Ks, Ns, Kd, Nd);
+                __syncwarp();                                   // the scratch is rewritten for the warp's next read
+                uint32_t es_i = 0, ed_i = 0;
+                if (m > 0) {
+                    Ks = warp_sum_i32(Ks); Ns = warp_sum_i32(Ns); Kd = warp_sum_i32(Kd); Nd = warp_sum_i32(Nd);
+                    es_i = ((uint32_t)Ks * 1024u + (uint32_t)Ns / 2u) / (uint32_t)Ns;          // sums of < CC_MAXN values <= 255: 32 bits
+                    ed_i = Nd > 0 ? ((uint32_t)Kd * 1024u + (uint32_t)Nd / 2u) / (uint32_t)Nd : es_i;
+                }
+                if (lane == 0) { es[i] = (uint16_t)es_i; ed[i] = (uint16_t)ed_i; pairs_total += m; }
+            }
+        } else if (tid < n) {
+            // wide (a read of 255+ bubbles): exact order (k_a n_b < k_b n_a, then n, then k) by counting, one thread per read, O(m^2)
+            const uint32_t* row = KEY + tid * ns;
+            int Ks = 0, Ns = 0, Kd = 0, Nd = 0, m = 0;
+            for (int j = 0; j < n; j++) { const uint32_t v = row[j]; m += (v != CS_INVALID && v != 0u) ? 1 : 0; }
+            const int cut = m ? max(1, m / d.ploidy) : 0;
+            for (int a = 0; a < n && m; a++) {
+                const uint32_t va = row[a];
+                if (va == CS_INVALID || va == 0u) continue;
+                const long long na = va >> 16, ka = va & 0xffffu;
+                int r = 0;
+                for (int b = 0; b < n; b++) {
+                    const uint32_t vb = row[b];
+                    if (vb == CS_INVALID || vb == 0u) continue;
+                    const long long nb = vb >> 16, kb = vb & 0xffffu;
+                    const long long l = kb * na, rr = ka * nb;                // b before a ?
+                    const bool less = l != rr ? l < rr : (nb != na ? nb < na : (kb != ka ? kb < ka : b < a));
+                    r += less ? 1 : 0;
+                }
+                if (r < cut) { Ks += (int)ka; Ns += (int)na; } else { Kd += (int)ka; Nd += (int)na; }
             }
             uint32_t es_i = 0, ed_i = 0;
             if (m > 0) {
@@ -259,10 +334,9 @@ __global__ void __launch_bounds__(NT) k_score_chain(DB d, const int32_t* __restr
                         int e1 = (esx + es[y]) >> 1, e2 = (edx + ed[y]) >> 1;
                         e1 = min(max(e1, 10), 460);
                         e2 = min(max(e2, e1 + 51), 972);
-                        const int64_t s20 = (int64_t)kk * (lnS[e1] - lnS[e2]) + (int64_t)(nn - kk) * (ln1S[e1] - ln1S[e2]);
-                        int64_t wv = floordiv1024(s20);
-                        wv = wv > W_CLAMP ? W_CLAMP : (wv < -W_CLAMP ? -W_CLAMP : wv);
-                        w = (int)wv;
+                        const int64_t s20 = (int64_t)kk * (int)(__ldg(d.ln + e1) - __ldg(d.ln + e2)) + (int64_t)(nn - kk) * (int)(__ldg(d.ln1 + e1) - __ldg(d.ln1 + e2));      // |ln| 2^20 < 2^23: the differences fit 32 bits
+                        w = narrow ? (int)(s20 >> 10) : (int)max(min(s20 >> 10, (int64_t)W_CLAMP), (int64_t)-W_CLAMP);      // narrow: |s20| < 2^34, the quotient fits 32 bits
+                        w = min(max(w, -W_CLAMP), W_CLAMP);
                     }
                 }
                 Wout[rowbase + y] = w;

@@ -17,6 +17,14 @@ constexpr uint32_t CS_INVALID = 0xffffffffu;
 // rcp[n] = floor(2^32 / n) + 1 for 2 <= n <= 255: high word of a * rcp[n] = floor(a / n) for a < 2^24
 // (the error a * (rcp[n] n - 2^32) / (n 2^32) < 2^-8 is below 1/n, the smallest gap to the next integer)
 AHS_HD uint32_t cs_rcp(uint32_t n) { return n >= 2 ? 0xffffffffu / n + 1u : 0u; }
+// counter b (8 bits, 4 per word) += 1.  On the device a shared-memory reduction: no load-to-use dependency in the scan loop.
+AHS_HD void cs_hist_inc(uint32_t* hw, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(&hw[b >> 2], 1u << ((b & 3u) * 8u));
+#else
+    hw[b >> 2] += 1u << ((b & 3u) * 8u);
+#endif
+}
 AHS_HD uint32_t cs_mulhi(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -39,13 +47,12 @@ AHS_HD uint32_t cs_order_key(uint32_t n, uint32_t k, uint32_t rcp_n) {
 // 6 bits per level from the top — byte histogram of 64 buckets in hw[16] (must be all zero on entry, is all zero on
 // exit), the bucket holding the cut-th key is compacted to the front of the row and refined.  The row is overwritten.
 AHS_HD void cs_pool_select(uint32_t* row, int len, int ploidy, uint32_t* hw, int& Ks, int& Ns, int& Kd, int& Nd, int& m) {
-    uint8_t* hb = (uint8_t*)hw;
     Ks = Ns = Kd = Nd = m = 0;
     int cc = len, need = 0;
     for (int shift = 26; ; shift -= 6) {
         const int sh = shift > 0 ? shift : 0; const uint32_t bm = shift >= 0 ? 63u : 3u;      // last level: the two lowest bits
         int cnt = 0;
-        for (int j = 0; j < cc; j++) { const uint32_t key = row[j]; if (key != CS_INVALID) { hb[(key >> sh) & bm]++; cnt++; } }
+        for (int j = 0; j < cc; j++) { const uint32_t key = row[j]; if (key != CS_INVALID) { cs_hist_inc(hw, (key >> sh) & bm); cnt++; } }
         if (shift == 26) { m = cnt; if (m == 0) return; need = m / ploidy; if (need < 1) need = 1; }
         // threshold bucket tb: the one holding the need-th smallest key (byte prefix sums of a word by one multiply: counts <= 255 in total)
         int cum = 0, fw = 16, fcum = 0; uint32_t fx = 0;
@@ -59,13 +66,20 @@ AHS_HD void cs_pool_select(uint32_t* row, int len, int ploidy, uint32_t* hw, int
         int tb = fw * 4, before = fcum;
         if (before + b0 < need) { tb++; before += b0; if (before + b1 < need) { tb++; before += b1; if (before + b2 < need) { tb++; before += b2; } } }
         need -= before;
-        int wr = 0;
+        // below the threshold bucket -> same, above -> diff, inside -> kept (compacted to the front of the row).  Branch free:
+        // (k, n) travel as k | n << 16 (the sums stay below 2^16: at most 255 keys of n, k <= 255); the store is unconditional,
+        // the write cursor only moves for a kept key and never passes the read cursor.
+        int wr = 0; uint32_t Ss = 0, Sd = 0;
         for (int j = 0; j < cc; j++) {
             const uint32_t key = row[j];
-            if (key == CS_INVALID) continue;
-            const int b = (int)((key >> sh) & bm), kq = (int)(key & 255u), nq = (int)((key >> 8) & 255u);
-            if (b < tb) { Ks += kq; Ns += nq; } else if (b > tb) { Kd += kq; Nd += nq; } else row[wr++] = key;
+            const bool valid = key != CS_INVALID;
+            const uint32_t b = (key >> sh) & bm;
+            const uint32_t v = valid ? ((key & 255u) | ((key & 0xff00u) << 8)) : 0u;
+            Ss += b < (uint32_t)tb ? v : 0u; Sd += b > (uint32_t)tb ? v : 0u;
+            row[wr] = key;
+            wr += (valid && b == (uint32_t)tb) ? 1 : 0;
         }
+        Ks += (int)(Ss & 0xffffu); Ns += (int)(Ss >> 16); Kd += (int)(Sd & 0xffffu); Nd += (int)(Sd >> 16);
         cc = wr;                                                      // >= need >= 1 keys share the threshold bucket
         if (need == cc || shift < 0) {                                // all of them are pooled as same, or all are equal: split by count
             for (int j = 0; j < cc; j++) { const uint32_t key = row[j]; const int kq = (int)(key & 255u), nq = (int)((key >> 8) & 255u); if (j < need) { Ks += kq; Ns += nq; } else { Kd += kq; Nd += nq; } }

@@ -87,20 +87,20 @@ static const ClusterClass kCluster[] = {{16, 32, 8}, {23, 32, 8}, {28, 64, 8}, {
                                     {101, 768, 8}, {111, 768, 8}, {120, 1024, 8}, {128, 1024, 8},
                                     {136, 1024, 9}, {148, 1024, 11}, {160, 1024, 13}};
 constexpr int N_CLUSTER = (int)(sizeof(kCluster) / sizeof(kCluster[0]));
-// Scoring: (largest n, threads per block >= n: one thread per read in the rate pass)
-struct ScoreClass { int nmax, nt; };
-static const ScoreClass kScore[] = {{32, 64}, {48, 128}, {64, 128}, {96, 256}, {128, 256}, {160, 256}};
+// Scoring: (largest n, threads per block >= n, sort keys per lane)
+struct ScoreClass { int nmax, nt, kpl; };
+static const ScoreClass kScore[] = {{32, 64, 1}, {48, 128, 2}, {64, 128, 2}, {96, 256, 4}, {128, 256, 4}, {160, 256, 8}};
 constexpr int N_SCORE = (int)(sizeof(kScore) / sizeof(kScore[0]));
 
 #define AHS_FOR_EACH_NT(X) X(32, 8) X(64, 8) X(96, 8) X(128, 8) X(192, 8) X(256, 8) X(384, 8) X(512, 8) X(768, 8) X(1024, 8) X(256, 12) X(1024, 9) X(1024, 11) X(1024, 13)
-#define AHS_FOR_EACH_SC(X) X(64) X(128) X(256)
+#define AHS_FOR_EACH_SC(X) X(64, 1) X(128, 2) X(256, 4) X(256, 8)
 static void chain_kernel_attributes(size_t optin) {
 #define X(NT, PER) CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
                    CK(cudaFuncSetAttribute(k_cluster_chain<NT, PER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     AHS_FOR_EACH_NT(X)
 #undef X
-#define X(NT) CK(cudaFuncSetAttribute(k_score_chain<2, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
-              CK(cudaFuncSetAttribute(k_score_chain<4, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
+#define X(NT, KPL) CK(cudaFuncSetAttribute(k_score_chain<2, NT, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)); \
+                   CK(cudaFuncSetAttribute(k_score_chain<4, NT, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin));
     AHS_FOR_EACH_SC(X)
 #undef X
 }
@@ -110,8 +110,8 @@ static void cluster_launch(int nt, int per, unsigned grid, size_t smem, cudaStre
 #undef X
     throw ArgFail{"cluster_launch: no kernel for this block size"};
 }
-template <int BITS> static void score_launch(int nt, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
-#define X(NT) if (nt == NT) { k_score_chain<BITS, NT><<<grid, NT, smem, st>>>(d, list, len, nmax, counter); return; }
+template <int BITS> static void score_launch(int nt, int kpl, unsigned grid, size_t smem, cudaStream_t st, const DB& d, const int32_t* list, int len, int nmax, int32_t* counter) {
+#define X(NT, KPL) if (nt == NT && kpl == KPL) { k_score_chain<BITS, NT, KPL><<<grid, NT, smem, st>>>(d, list, len, nmax, counter); return; }
     AHS_FOR_EACH_SC(X)
 #undef X
     throw ArgFail{"score_launch: no kernel for this block size"};
@@ -126,7 +126,7 @@ static void check_classes(size_t smem_optin) {
         if (kCluster[k].nmax > 128 && !(kCluster[k].nt == 1024 && kCluster[k].per > 8)) throw std::logic_error("cluster class table: classes above 128 reads need the five-stride kernels");
     }
     if (kCluster[N_CLUSTER - 1].nmax != CC_MAXN || kScore[N_SCORE - 1].nmax != CC_MAXN) throw std::logic_error("class tables do not end at CC_MAXN");
-    for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > kScore[k].nt || cs_smem_bytes(kScore[k].nmax, kScore[k].nt) > smem_optin) throw std::logic_error("score class table");
+    for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > kScore[k].nt || kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax, kScore[k].nt) > smem_optin) throw std::logic_error("score class table");
 }
 
 static Ctx* get_ctx(int device) {
@@ -508,16 +508,20 @@ struct Pipeline {
         // ---- scoring
         if (nf_big) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (nf_big) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
-        // chains up to CC_MAXN reads: scoring out of shared memory, 4 B per pair to HBM (every chain of BASELINE config 2)
-        for (int k = N_SCORE - 1; k >= 0; k--) {
+        // chains up to CC_MAXN reads: scoring out of shared memory, 4 B per pair to HBM (every chain of BASELINE config 2).
+        // The size classes run side by side on the side streams: one class alone leaves issue slots idle (barrier waits).
+        CK(cudaEventRecord(ln->ev_fork, st));
+        for (auto& t : cx->side) CK(cudaStreamWaitEvent(t, ln->ev_fork, 0));
+        for (int k = N_SCORE - 1, q = 0; k >= 0; k--) {
             int first, len; range_of(k ? kScore[k - 1].nmax + 1 : 1, kScore[k].nmax, first, len);
             if (!len) continue;
             const int nt = kScore[k].nt;
             const size_t smem = cs_smem_bytes(kScore[k].nmax, kScore[k].nt);
             const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(16, 2048 / nt), (228 * 1024) / (smem + 1024)));
             const unsigned grid = (unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm);
-            score_launch<BITS>(nt, grid, smem, st, d, dv_order + first, len, kScore[k].nmax, counters + 8 + k); n_launches += 1;
+            score_launch<BITS>(nt, kScore[k].kpl, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kScore[k].nmax, counters + 8 + k); n_launches += 1;
         }
+        for (int i = 0; i < 8; i++) { CK(cudaEventRecord(ln->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, ln->ev_join[i], 0)); }
         CK(cudaEventRecord(ln->ev[3], st));
         // ---- cluster editing out of shared memory
         CK(cudaEventRecord(ln->ev[10], st));

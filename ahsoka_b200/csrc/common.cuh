@@ -8,8 +8,9 @@ namespace ahs {
 constexpr uint64_t KEY_NONE    = ~0ull;
 constexpr int32_t  W_CLAMP     = 1 << 17;
 constexpr int      MAX_ALLELES = 15;                 // mask bits 0..14, bit 15 = full-containment flag
-constexpr int      MAX_PLOIDY  = 4;
-constexpr int      MAX_K       = 2 * MAX_PLOIDY;     // clusters per column (alignmentstoreadset.cpp:766)
+constexpr int      MAX_PLOIDY  = 6;
+constexpr int      MAX_K       = 2 * MAX_PLOIDY;     // |covMap[pos]| <= 2p (alignmentstoreadset.cpp:766)
+constexpr int      PR_K        = 8;                  // clusters per DP column kept in a PosRec: 2p up to ploidy 4, p + 2 above (rule R3c)
 constexpr int      DP_INF      = 1 << 29;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

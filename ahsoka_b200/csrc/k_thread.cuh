@@ -87,12 +87,16 @@ __global__ void __launch_bounds__(128) k_consensus(DB d) {
             int k = min(ncl, 2 * p);
             for (int i = p; i < min(ncl, 2 * p); i++)
                 if ((uint64_t)s_cnt[wib][s_idx[wib][i]] * (uint64_t)(8 * p) < (uint64_t)total) { k = i; break; }   // cov < 1/(8p), :768
-            r.k = (uint8_t)k;
+            // the DP column: all of covMap[pos] up to ploidy 4, its first p + 2 entries above (rule R3c); the consensus list
+            // is the one of ALL covMap clusters in ascending id order (A#12), of which the column reads the first r.k entries
+            const int kr = p > 4 ? min(k, p + 2) : k;
+            r.k = (uint8_t)kr;
             int sel[MAX_K];
-            for (int l = 0; l < MAX_K; l++) { r.gid[l] = -1; r.cnt_asc[l] = 0; r.cons_asc[l] = 0; r.cons_cm[l] = 0; }
-            for (int l = 0; l < k; l++) { sel[l] = s_idx[wib][l]; r.gid[l] = s_id[wib][sel[l]]; r.cons_cm[l] = s_cons[wib][sel[l]]; r.cnt_asc[l] = (uint32_t)s_cnt[wib][l]; }
+            for (int l = 0; l < PR_K; l++) { r.gid[l] = -1; r.cnt_asc[l] = 0; r.cons_asc[l] = 0; r.cons_cm[l] = 0; }
+            for (int l = 0; l < k; l++) sel[l] = s_idx[wib][l];
+            for (int l = 0; l < kr; l++) { r.gid[l] = s_id[wib][sel[l]]; r.cons_cm[l] = s_cons[wib][sel[l]]; r.cnt_asc[l] = (uint32_t)s_cnt[wib][l]; }
             for (int x = 1; x < k; x++) { int v = sel[x], y = x - 1; while (y >= 0 && sel[y] > v) { sel[y + 1] = sel[y]; y--; } sel[y + 1] = v; }
-            for (int l = 0; l < k; l++) r.cons_asc[l] = s_cons[wib][sel[l]];
+            for (int l = 0; l < kr; l++) r.cons_asc[l] = s_cons[wib][sel[l]];
             d.rec[gp] = r;
         }
         __syncwarp(gm);
@@ -149,12 +153,14 @@ __global__ void __launch_bounds__(128) k_consensus_chain(DB d) {
                 int k = min(m, 2 * p);
                 for (int i = p; i < min(m, 2 * p); i++)
                     if ((uint64_t)cn[idx[i]] * (uint64_t)(8 * p) < (uint64_t)total) { k = i; break; }          // cov < 1/(8p), :768
-                r.k = (uint8_t)k;
+                const int kr = p > 4 ? min(k, p + 2) : k;             // see k_consensus
+                r.k = (uint8_t)kr;
                 int sel[MAX_K];
-                for (int l = 0; l < MAX_K; l++) { r.gid[l] = -1; r.cnt_asc[l] = 0; r.cons_asc[l] = 0; r.cons_cm[l] = 0; }
-                for (int l = 0; l < k; l++) { sel[l] = idx[l]; r.gid[l] = ids[sel[l]]; r.cons_cm[l] = cons[sel[l]]; r.cnt_asc[l] = (uint32_t)cn[l]; }
+                for (int l = 0; l < PR_K; l++) { r.gid[l] = -1; r.cnt_asc[l] = 0; r.cons_asc[l] = 0; r.cons_cm[l] = 0; }
+                for (int l = 0; l < k; l++) sel[l] = idx[l];
+                for (int l = 0; l < kr; l++) { r.gid[l] = ids[sel[l]]; r.cons_cm[l] = cons[sel[l]]; r.cnt_asc[l] = (uint32_t)cn[l]; }
                 for (int x = 1; x < k; x++) { int v = sel[x], y = x - 1; while (y >= 0 && sel[y] > v) { sel[y + 1] = sel[y]; y--; } sel[y + 1] = v; }
-                for (int l = 0; l < k; l++) r.cons_asc[l] = cons[sel[l]];
+                for (int l = 0; l < kr; l++) r.cons_asc[l] = cons[sel[l]];
                 d.rec[p0 + q] = r;
             }
             __syncwarp();

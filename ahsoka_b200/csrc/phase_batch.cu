@@ -24,6 +24,7 @@
 #include "k_chain.cuh"
 #include "k_cluster_big.cuh"
 #include "k_thread.cuh"
+#include "k_thread_canon.cuh"
 
 namespace ahs {
 
@@ -71,6 +72,7 @@ constexpr int N_LANES = 4;
 struct Ctx {
     int device = -1; Lane lanes[N_LANES]; cudaStream_t side[8]; Pool dev{false}, pin{true}, outp{true};
     int64_t *d_ln = nullptr, *d_ln1 = nullptr; int sms = 148; bool out_busy = false;
+    CanonTables canon{};                                     // neighbour tables of k_thread_canon (ploidy 5, 6)
     size_t smem_optin = 0;
     std::mutex mu;
 };
@@ -129,6 +131,56 @@ static void check_classes(size_t smem_optin) {
     for (int k = 0; k < N_SCORE; k++) if (kScore[k].nmax > kScore[k].nt || kScore[k].nmax > 32 * kScore[k].kpl || cs_smem_bytes(kScore[k].nmax, kScore[k].nt) > smem_optin) throw std::logic_error("score class table");
 }
 
+// neighbour tables of the sub-multiset lattice (k_thread_canon.cuh), built once per device
+static void build_canon_tables(CanonTables& tb) {
+    std::vector<uint32_t> tup; std::vector<uint16_t> add, del;
+    for (int j = 0; j <= CN_P; j++) for (int k = 0; k <= CN_K; k++) tb.nn[j][k] = cn_count(j, k);
+    tb.base[0] = 0;
+    for (int k = 1; k <= CN_K; k++) {
+        tb.base[k] = (int32_t)tup.size();
+        int off = 0;
+        for (int j = 0; j <= CN_P; j++) {
+            tb.lvl[k][j] = off;
+            const int cnt = cn_count(j, k);
+            std::vector<int> x(j, 0);
+            for (int e = 0; e < cnt; e++) {
+                uint8_t t[CN_P + 1]; uint32_t packed = 0;
+                for (int i = 0; i < j; i++) { t[i] = (uint8_t)x[i]; packed |= (uint32_t)x[i] << (4 * i); }
+                if (cn_rank(t, j, k, tb.nn) != e) throw std::logic_error("canonical tuple tables: rank");
+                tup.push_back(packed);
+                for (int g = 0; g < 8; g++) {                  // insert g
+                    uint16_t r = 0;
+                    if (j < CN_P && g < k) {
+                        uint8_t y[CN_P + 1]; int w = 0; bool done = false;
+                        for (int i = 0; i < j; i++) { if (!done && g < t[i]) { y[w++] = (uint8_t)g; done = true; } y[w++] = t[i]; }
+                        if (!done) y[w++] = (uint8_t)g;
+                        r = (uint16_t)cn_rank(y, j + 1, k, tb.nn);
+                    }
+                    add.push_back(r);
+                }
+                for (int i = 0; i < 6; i++) {                  // delete element i
+                    uint16_t r = 0;
+                    if (i < j) { uint8_t y[CN_P + 1]; int w = 0; for (int u = 0; u < j; u++) if (u != i) y[w++] = t[u]; r = (uint16_t)cn_rank(y, j - 1, k, tb.nn); }
+                    del.push_back(r);
+                }
+                // next non-decreasing tuple
+                int i = j - 1;
+                while (i >= 0 && x[i] == k - 1) i--;
+                if (i >= 0) { const int v = x[i] + 1; for (int u = i; u < j; u++) x[u] = v; }
+            }
+            off += cnt;
+        }
+        tb.lvl[k][CN_P + 1] = off;
+    }
+    for (int j = 0; j <= CN_P + 1; j++) tb.lvl[0][j] = 0;
+    uint32_t* d_tup; uint16_t *d_add, *d_del;
+    CK(cudaMalloc(&d_tup, tup.size() * 4)); CK(cudaMalloc(&d_add, add.size() * 2)); CK(cudaMalloc(&d_del, del.size() * 2));
+    CK(cudaMemcpy(d_tup, tup.data(), tup.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_add, add.data(), add.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_del, del.data(), del.size() * 2, cudaMemcpyHostToDevice));
+    tb.tup = d_tup; tb.add = d_add; tb.del = d_del;
+}
+
 static Ctx* get_ctx(int device) {
     std::lock_guard<std::mutex> g(g_ctx_mu);
     if (device < 0 || device >= 64) throw ArgFail{"device ordinal out of range"};
@@ -158,6 +210,8 @@ static Ctx* get_ctx(int device) {
     CK(cudaMemcpy(c->d_ln, ln.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_ln1, ln1.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * 4096 + 64));
+    CK(cudaFuncSetAttribute(k_thread_canon, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    build_canon_tables(c->canon);
     c->smem_optin = prop.sharedMemPerBlockOptin;
     check_classes(c->smem_optin);
     CK(cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
@@ -416,6 +470,7 @@ struct Pipeline {
         const int TB = 256;
         const int per_word = 32 / BITS;
         int64_t S_max = 1; for (int i = 0; i < in->ploidy; i++) S_max *= 2 * in->ploidy;
+        if (in->ploidy > 4) S_max = cn_count(in->ploidy, in->ploidy + 2);      // canonical tuples over p + 2 clusters (rule R3c)
         d.S_max = (int32_t)S_max;
         Stage sg; sg.h = sg_h; sg.dv = sg_d;
         int64_t *dv_frow, *dv_pos, *dv_code, *dv_cw, *dv_back; int32_t *dv_words, *dv_order, *dv_status; uint8_t* dv_small;
@@ -558,7 +613,8 @@ struct Pipeline {
         }
         CK(cudaEventRecord(ln->ev[5], st));
         if (NP && in->ploidy == 2) { k_thread2<<<(unsigned)std::min<int64_t>((C + 7) / 8, (int64_t)sms * 8), 256, 0, st>>>(d, counters + 1); n_launches += 1; }
-        else if (NP) { k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1; }
+        else if (NP && in->ploidy <= 4) { k_thread<<<std::min<int64_t>(C, (int64_t)sms * 8), DP_THREADS, 21 * (size_t)S_max + 64, st>>>(d, counters + 1); n_launches += 1; }
+        else if (NP) { k_thread_canon<<<std::min<int64_t>(C, (int64_t)sms * 4), CN_THREADS, 64 * 1024, st>>>(d, cx->canon, counters + 1); n_launches += 1; }
         CK(cudaEventRecord(ln->ev[6], st));
         CK(cudaEventRecord(ln->ev[7], st));
         CK(cudaGetLastError());
@@ -871,6 +927,11 @@ static void phase_on_devices(const ahs_batch_in* in, ahs_batch_out* out, const i
     if (!out) throw ArgFail{"null output"};
     if (!devs || G < 1) throw ArgFail{"no devices"};
     for (int g = 0; g < G; g++) for (int h = 0; h < g; h++) if (devs[g] == devs[h]) throw ArgFail{"ahs_phase_batch_multi: a device id is listed twice"};
+    struct RestoreDevice {          // the caller's current device is the caller's business: put it back on every way out
+        int dev = -1;
+        RestoreDevice() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+        ~RestoreDevice() { if (dev >= 0) cudaSetDevice(dev); }
+    } restore_device;
     Sizes sz = validate(in);
     const int64_t C = sz.C; const int p = in->ploidy;
     std::vector<DeviceJob> jobs(G);

@@ -306,10 +306,10 @@ def main():
     cells_local = cells
     if dist is not None:
         import torch
-        v = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
+        v = torch.tensor([ms_step, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(v[0]), float(v[1])
-        s = torch.tensor([cells, chains_ok], device="cuda", dtype=torch.int64)
+        s = torch.tensor([cells, chains_ok], device=f"cuda:{local}", dtype=torch.int64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
         cells, chains_ok = int(s[0]), int(s[1])
     if rank != 0:

@@ -66,10 +66,28 @@
 //                       + affineSwitchCost * [any h switched].
 //   * D_q[t] = covcost(t) + min_s (D_{q-1}[s] + trans); predecessor ties and the final
 //     column minimum take the lowest code.  Output path[q][h] = covMap[q][t_h].
+//
+// R3c. Haplotype threading for ploidy > 4 (no reference behaviour at all: the reference fixes p = 2; k^p ordered
+//     tuples with k <= 2p is 2.99 M states per column at p = 6).  Same costs on CANONICAL tuples:
+//   * Column q uses the first k_q = min(|covMap[q]|, p + 2) entries of covMap[q] (descending coverage).
+//   * States = multisets of p local indices, written as non-decreasing tuples t_0 <= ... <= t_{p-1}; the state's
+//     index is the tuple's rank in lexicographic order.  Conformity and coverage cost are R3's (they depend on the
+//     multiset only).
+//   * Transition s->t = switchCost * (p - |G(s) n G(t)|) + affineSwitchCost * [G(s) != G(t)], G(.) = the multiset of
+//     GLOBAL cluster ids: the minimum of R3's transition cost over all ways of labelling the haplotypes.
+//   * D_q[t], predecessor ties and the final minimum: lowest index.
+//   * Haplotype labels are threaded along the chain: path[0][h] = covMap[0][t_h]; at q > 0, for h = 0..p-1 in turn,
+//     haplotype h keeps its cluster while G(t) still holds an unclaimed copy of it, then the haplotypes left over
+//     take the unclaimed elements of t in ascending local index.  (Exactly p - |G(s) n G(t)| haplotypes switch.)
+//   Two implementations below: thread_paths_canonical_direct (the definition, all pairs of states) and
+//   thread_paths_canonical (sub-multiset DP, what the parity tests use at size); tests/test_oracle_cpu.py checks
+//   that they agree.
 // ---------------------------------------------------------------------------------------
 #pragma once
 #include <algorithm>
+#include <array>
 #include <cassert>
+#include <cstdio>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -343,7 +361,7 @@ struct ThreadResult {
     double cost = 0.0;
 };
 
-inline ThreadResult thread_paths(uint32_t ploidy, double switchCost, double affineSwitchCost,
+inline ThreadResult thread_paths_ordered(uint32_t ploidy, double switchCost, double affineSwitchCost,
                                  uint32_t start, uint32_t end,
                                  const std::vector<std::vector<uint32_t>>& covMap,
                                  const std::vector<std::vector<double>>& coverage,
@@ -421,6 +439,230 @@ inline ThreadResult thread_paths(uint32_t ploidy, double switchCost, double affi
         if (q > 0) cur = (uint64_t)back[q][cur];
     }
     return res;
+}
+
+// ------------------------------------------------------------------ R3c threading on canonical tuples (ploidy > 4)
+struct Canon {
+    // N(j, k) = number of non-decreasing j-tuples over k symbols = C(k + j - 1, j)
+    static int64_t N(int j, int k) {
+        if (j == 0) return 1;
+        if (k <= 0) return 0;
+        int64_t r = 1;
+        for (int i = 1; i <= j; i++) r = r * (k - 1 + i) / i;
+        return r;
+    }
+    static int rank(const uint8_t* x, int j, int k) {          // lexicographic rank of a non-decreasing tuple
+        int64_t r = 0; int prev = 0;
+        for (int i = 0; i < j; i++) { for (int v = prev; v < x[i]; v++) r += N(j - 1 - i, k - v); prev = x[i]; }
+        return (int)r;
+    }
+    static std::vector<std::array<uint8_t, 8>> tuples(int j, int k) {      // in rank order
+        std::vector<std::array<uint8_t, 8>> out;
+        std::array<uint8_t, 8> t{};
+        if (j == 0) { out.push_back(t); return out; }
+        if (k <= 0) return out;
+        std::vector<int> x(j, 0);
+        while (true) {
+            for (int i = 0; i < j; i++) t[i] = (uint8_t)x[i];
+            out.push_back(t);
+            int i = j - 1;
+            while (i >= 0 && x[i] == k - 1) i--;
+            if (i < 0) break;
+            const int v = x[i] + 1;
+            for (int u = i; u < j; u++) x[u] = v;
+        }
+        return out;
+    }
+};
+
+static const int CANON_INF = 1 << 29;
+
+// per-state column cost: coverage cost if the tuple is allowed, -1 - cost if it does not conform (R3's rules)
+inline void canon_column(uint32_t p, uint32_t pos, int k, const std::vector<std::array<uint8_t, 8>>& T,
+                         const std::vector<std::vector<double>>& coverage, const std::vector<std::vector<uint32_t>>& consensus,
+                         const std::vector<std::unordered_map<uint32_t, uint32_t>>& genotypes, std::vector<int>& cc, bool& any) {
+    (void)k;
+    cc.assign(T.size(), 0); any = false;
+    const bool have_gt = pos < genotypes.size() && !genotypes[pos].empty();
+    for (size_t c = 0; c < T.size(); c++) {
+        const uint8_t* t = T[c].data();
+        bool ok;
+        if (have_gt) {
+            std::unordered_map<uint32_t, uint32_t> cnt;
+            for (uint32_t h = 0; h < p; h++) cnt[consensus[pos][t[h]]]++;
+            ok = cnt.size() == genotypes[pos].size();
+            if (ok) for (auto& kv : cnt) { auto it = genotypes[pos].find(kv.first); if (it == genotypes[pos].end() || it->second != kv.second) { ok = false; break; } }
+        } else {
+            ok = false;
+            for (uint32_t h = 1; h < p; h++) if (consensus[pos][t[h]] != consensus[pos][t[0]]) ok = true;
+        }
+        int cost = 0;
+        for (uint32_t h = 0; h < p; h++) {
+            uint32_t m = 0; for (uint32_t g = 0; g < p; g++) if (t[g] == t[h]) m++;
+            const double cov = coverage[pos][t[h]];
+            const double lo = (2.0 * m - 1.0) / (2.0 * p), hi = (2.0 * m + 1.0) / (2.0 * p);
+            if (cov < lo || cov > hi) cost++;
+        }
+        cc[c] = ok ? cost : -1 - cost;
+        any |= ok;
+    }
+}
+
+inline ThreadResult canon_backtrace(uint32_t p, uint32_t start, uint32_t L, const std::vector<std::vector<uint32_t>>& covMap,
+                                    const std::vector<int>& kq, const std::vector<std::vector<std::array<uint8_t, 8>>>& tup,
+                                    const std::vector<int>& Dlast, const std::vector<std::vector<int32_t>>& back) {
+    ThreadResult res;
+    int best = INT32_MAX; int cur = 0;
+    for (size_t c = 0; c < Dlast.size(); c++) if (Dlast[c] < best) { best = Dlast[c]; cur = (int)c; }
+    res.cost = (double)best;
+    std::vector<int> state(L);
+    for (int q = (int)L - 1; q >= 0; q--) { state[q] = cur; if (q > 0) cur = back[q][cur]; }
+    res.path.assign(L, std::vector<uint32_t>(p));
+    for (uint32_t q = 0; q < L; q++) {
+        const uint32_t pos = start + q;
+        const uint8_t* t = tup[q][state[q]].data();
+        (void)kq;
+        if (q == 0) { for (uint32_t h = 0; h < p; h++) res.path[0][h] = covMap[pos][t[h]]; continue; }
+        std::vector<char> claimed(p, 0), placed(p, 0);
+        for (uint32_t h = 0; h < p; h++)                       // keep the cluster while an unclaimed copy is left
+            for (uint32_t e = 0; e < p; e++) if (!claimed[e] && covMap[pos][t[e]] == res.path[q - 1][h]) { claimed[e] = 1; placed[h] = 1; res.path[q][h] = res.path[q - 1][h]; break; }
+        uint32_t e = 0;
+        for (uint32_t h = 0; h < p; h++) if (!placed[h]) { while (claimed[e]) e++; res.path[q][h] = covMap[pos][t[e]]; claimed[e] = 1; }
+    }
+    return res;
+}
+
+// the definition: all pairs of states
+inline ThreadResult thread_paths_canonical_direct(uint32_t p, double switchCost, double affineSwitchCost, uint32_t start, uint32_t end,
+                                                  const std::vector<std::vector<uint32_t>>& covMap, const std::vector<std::vector<double>>& coverage,
+                                                  const std::vector<std::vector<uint32_t>>& consensus,
+                                                  const std::vector<std::unordered_map<uint32_t, uint32_t>>& genotypes) {
+    if (end <= start) return ThreadResult();
+    const uint32_t L = end - start; const int sw = (int)switchCost, aff = (int)affineSwitchCost;
+    std::vector<int> kq(L); std::vector<std::vector<std::array<uint8_t, 8>>> tup(L);
+    std::vector<std::vector<int32_t>> back(L);
+    std::vector<int> Dprev, Dcur, cc;
+    for (uint32_t q = 0; q < L; q++) {
+        const uint32_t pos = start + q;
+        kq[q] = (int)std::min<size_t>(covMap[pos].size(), p + 2);
+        tup[q] = Canon::tuples((int)p, kq[q]);
+        const size_t S = tup[q].size();
+        bool any; canon_column(p, pos, kq[q], tup[q], coverage, consensus, genotypes, cc, any);
+        Dcur.assign(S, CANON_INF); back[q].assign(S, -1);
+        std::vector<std::vector<uint32_t>> G(S), Gp;
+        for (size_t c = 0; c < S; c++) { for (uint32_t h = 0; h < p; h++) G[c].push_back(covMap[pos][tup[q][c][h]]); std::sort(G[c].begin(), G[c].end()); }
+        if (q > 0) { Gp.resize(tup[q - 1].size()); for (size_t c = 0; c < Gp.size(); c++) { for (uint32_t h = 0; h < p; h++) Gp[c].push_back(covMap[pos - 1][tup[q - 1][c][h]]); std::sort(Gp[c].begin(), Gp[c].end()); } }
+        for (size_t c = 0; c < S; c++) {
+            const bool allowed = cc[c] >= 0 || !any;
+            const int cost = cc[c] >= 0 ? cc[c] : -1 - cc[c];
+            if (!allowed) continue;
+            if (q == 0) { Dcur[c] = cost; continue; }
+            int best = INT32_MAX; int arg = -1;
+            for (size_t d = 0; d < Gp.size(); d++) {
+                size_t x = 0, y = 0; int common = 0;
+                while (x < p && y < p) { if (Gp[d][x] < G[c][y]) x++; else if (Gp[d][x] > G[c][y]) y++; else { common++; x++; y++; } }
+                const int dist = (int)p - common;
+                const int v = Dprev[d] + sw * dist + (dist ? aff : 0);
+                if (v < best) { best = v; arg = (int)d; }
+            }
+            Dcur[c] = std::min(best + cost, CANON_INF); back[q][c] = arg;
+        }
+        Dprev = Dcur;
+    }
+    return canon_backtrace(p, start, L, covMap, kq, tup, Dprev, back);
+}
+
+// sub-multiset DP: E_j[c] = min D[s] over the states s that contain the j-multiset c (down pass over the previous
+// column's indices), G_j[c] = min over c' inside c of E[c'] + switchCost * (j - |c'|) (up pass over this column's
+// indices; a multiset takes part as c' only if all its clusters exist in the previous column).  Values are
+// (cost, predecessor index) pairs under lexicographic minimum, so ties resolve to the lowest index as in the definition.
+inline ThreadResult thread_paths_canonical(uint32_t p, double switchCost, double affineSwitchCost, uint32_t start, uint32_t end,
+                                           const std::vector<std::vector<uint32_t>>& covMap, const std::vector<std::vector<double>>& coverage,
+                                           const std::vector<std::vector<uint32_t>>& consensus,
+                                           const std::vector<std::unordered_map<uint32_t, uint32_t>>& genotypes) {
+    if (end <= start) return ThreadResult();
+    const uint32_t L = end - start; const int sw = (int)switchCost, aff = (int)affineSwitchCost;
+    typedef std::pair<int, int> VA;                              // (value, predecessor)
+    const VA NONE(INT32_MAX, INT32_MAX);
+    std::vector<int> kq(L); std::vector<std::vector<std::array<uint8_t, 8>>> tup(L);
+    std::vector<std::vector<int32_t>> back(L);
+    std::vector<int> Dprev, Dcur, cc;
+    for (uint32_t q = 0; q < L; q++) {
+        const uint32_t pos = start + q;
+        const int kc = kq[q] = (int)std::min<size_t>(covMap[pos].size(), p + 2);
+        tup[q] = Canon::tuples((int)p, kc);
+        const size_t S = tup[q].size();
+        bool any; canon_column(p, pos, kc, tup[q], coverage, consensus, genotypes, cc, any);
+        Dcur.assign(S, CANON_INF); back[q].assign(S, -1);
+        if (q == 0) { for (size_t c = 0; c < S; c++) if (cc[c] >= 0 || !any) Dcur[c] = cc[c] >= 0 ? cc[c] : -1 - cc[c]; Dprev = Dcur; continue; }
+        const int kp = kq[q - 1];
+        // down pass
+        std::vector<std::vector<VA>> E(p + 1);
+        E[p].resize(Dprev.size());
+        for (size_t s = 0; s < Dprev.size(); s++) E[p][s] = VA(Dprev[s], (int)s);
+        for (int j = (int)p - 1; j >= 0; j--) {
+            auto Tj = Canon::tuples(j, kp);
+            E[j].assign(Tj.size(), NONE);
+            for (size_t c = 0; c < Tj.size(); c++)
+                for (int g = 0; g < kp; g++) {
+                    uint8_t x[8]; int w = 0; bool done = false;
+                    for (int i = 0; i < j; i++) { if (!done && g < Tj[c][i]) { x[w++] = (uint8_t)g; done = true; } x[w++] = Tj[c][i]; }
+                    if (!done) x[w++] = (uint8_t)g;
+                    E[j][c] = std::min(E[j][c], E[j + 1][Canon::rank(x, j + 1, kp)]);
+                }
+        }
+        // this column's local index -> previous column's local index of the same global cluster
+        std::vector<int> mp(kc, -1);
+        for (int l = 0; l < kc; l++) for (int m = 0; m < kp; m++) if (covMap[pos - 1][m] == covMap[pos][l]) { mp[l] = m; break; }
+        auto mapped = [&](const uint8_t* c, int j, VA& out) {
+            uint8_t x[8];
+            for (int i = 0; i < j; i++) { if (mp[c[i]] < 0) return false; x[i] = (uint8_t)mp[c[i]]; }
+            std::sort(x, x + j);
+            out = E[j][Canon::rank(x, j, kp)];
+            return true;
+        };
+        // up pass
+        std::vector<std::vector<VA>> G(p + 1);
+        G[0].assign(1, E[0][0]);
+        for (int j = 1; j <= (int)p; j++) {
+            auto Tj = Canon::tuples(j, kc);
+            G[j].assign(Tj.size(), NONE);
+            for (size_t c = 0; c < Tj.size(); c++) {
+                VA best = NONE, m;
+                if (mapped(Tj[c].data(), j, m)) best = m;
+                for (int i = 0; i < j; i++) {
+                    if (i > 0 && Tj[c][i] == Tj[c][i - 1]) continue;
+                    uint8_t x[8]; int w = 0;
+                    for (int u = 0; u < j; u++) if (u != i) x[w++] = Tj[c][u];
+                    VA g = G[j - 1][Canon::rank(x, j - 1, kc)];
+                    if (g.first < CANON_INF) g.first += sw; else g = NONE;
+                    best = std::min(best, g);
+                }
+                G[j][c] = best;
+            }
+        }
+        for (size_t c = 0; c < S; c++) {
+            const bool allowed = cc[c] >= 0 || !any;
+            const int cost = cc[c] >= 0 ? cc[c] : -1 - cc[c];
+            if (!allowed) continue;
+            VA a = G[p][c];
+            if (a.first < CANON_INF) a.first += aff; else a = NONE;
+            VA b;
+            if (mapped(tup[q][c].data(), (int)p, b)) a = std::min(a, b);
+            Dcur[c] = std::min(a.first + cost, CANON_INF); back[q][c] = a.second;
+        }
+        Dprev = Dcur;
+    }
+    return canon_backtrace(p, start, L, covMap, kq, tup, Dprev, back);
+}
+
+// computePaths: rule R3 on ordered tuples up to ploidy 4 (the reference runs ploidy 2), rule R3c above
+inline ThreadResult thread_paths(uint32_t ploidy, double switchCost, double affineSwitchCost, uint32_t start, uint32_t end,
+                                 const std::vector<std::vector<uint32_t>>& covMap, const std::vector<std::vector<double>>& coverage,
+                                 const std::vector<std::vector<uint32_t>>& consensus,
+                                 const std::vector<std::unordered_map<uint32_t, uint32_t>>& genotypes) {
+    if (ploidy > 4) return thread_paths_canonical(ploidy, switchCost, affineSwitchCost, start, end, covMap, coverage, consensus, genotypes);
+    return thread_paths_ordered(ploidy, switchCost, affineSwitchCost, start, end, covMap, coverage, consensus, genotypes);
 }
 
 }  // namespace ahs_oracle

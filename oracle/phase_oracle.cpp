@@ -333,6 +333,32 @@ void ahs_oracle_antiqsort(int32_t n, int32_t* keys_out) {
     for (int i = 0; i < n; i++) keys_out[i] = val[i];
 }
 
+// Rule R3c two ways (the definition over all pairs of states / the sub-multiset DP) on one random instance: returns 0 if
+// cost and paths agree.  n_pos columns, k[q] clusters per column drawn from `n_ids` global ids.
+int ahs_oracle_canonical_selfcheck(int ploidy, int n_pos, int n_ids, uint64_t seed, double* cost_out) {
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    std::vector<std::vector<uint32_t>> covMap(n_pos), consensus(n_pos); std::vector<std::vector<double>> coverage(n_pos);
+    std::vector<std::unordered_map<uint32_t, uint32_t>> genotypes(n_pos + 1);
+    for (int q = 0; q < n_pos; q++) {
+        const int k = 1 + (int)(rnd() % (2 * ploidy));
+        std::vector<uint32_t> ids; for (int i = 0; i < n_ids; i++) ids.push_back(i);
+        for (int i = 0; i < k && !ids.empty(); i++) { const size_t j = rnd() % ids.size(); covMap[q].push_back(ids[j]); ids.erase(ids.begin() + j); }
+        const int tot = 1 + (int)(rnd() % 60); int left = tot;
+        const size_t kk = covMap[q].size();
+        for (size_t i = 0; i < std::max<size_t>(kk, 2 * ploidy); i++) {           // coverage lists every cluster at the position (A#12): at least k entries
+            const int cnt = i + 1 == kk ? left : (int)(rnd() % (left + 1)); left -= std::min(left, cnt);
+            coverage[q].push_back((double)cnt / tot);
+        }
+        for (size_t i = 0; i < kk; i++) consensus[q].push_back((uint32_t)(rnd() % 3));
+    }
+    ThreadResult a = thread_paths_canonical_direct(ploidy, 32.0, 8.0, 0, n_pos, covMap, coverage, consensus, genotypes);
+    ThreadResult b = thread_paths_canonical(ploidy, 32.0, 8.0, 0, n_pos, covMap, coverage, consensus, genotypes);
+    if (cost_out) *cost_out = a.cost;
+    if (a.cost != b.cost || a.path != b.path) return 1;
+    return 0;
+}
+
 int ahs_oracle_log_tables(int64_t* ln, int64_t* ln1) {
     const LogTables& T = log_tables();
     memcpy(ln, T.ln, sizeof(T.ln)); memcpy(ln1, T.ln1, sizeof(T.ln1));

@@ -70,9 +70,24 @@ def test_multiline_reads():
     _check(synth.generate(synth.params(2, 30, 1, 30, depth=25.0, dup_lines=300, seed=21)))
 
 
-@pytest.mark.parametrize("ploidy,seed", [(3, 31), (4, 41)])
+@pytest.mark.parametrize("ploidy,seed", [(3, 31), (4, 41), (5, 51), (6, 61)])
 def test_polyploid(ploidy, seed):
-    _check(synth.generate(synth.params(ploidy, 12, 1, 30, depth=10.0 * ploidy, seed=seed)))
+    # ploidy 3, 4: ordered tuples (rule R3); ploidy 5, 6: canonical tuples over the first p + 2 clusters (rule R3c)
+    got = _check(synth.generate(synth.params(ploidy, 12, 1, 30, depth=10.0 * ploidy, seed=seed)))
+    assert got.n_chains_ok == 12
+
+
+def test_hexaploid_many_alleles_and_short_chains():
+    _check(synth.generate(synth.params(6, 40, 1, 8, min_len=1, depth=50.0, max_alleles=12, seed=62)))
+    _check(synth.generate(synth.params(5, 10, 1, 60, depth=30.0, max_alleles=3, seed=52)))          # 2-bit codes at ploidy 5
+
+
+def test_cfg5_sample_hexaploid_skewed_chain_sizes():
+    # BASELINE configs[4] at reduced chain length: ploidy 6, 80x, Zipf-skewed sizes with one forced 600-bubble chain
+    # (~2,000 final reads: the big-chain cluster editing + the canonical-tuple DP over 600 columns)
+    b = synth.generate(synth.params(6, 24, 2, 500, 2, 600, 1.2, 1, depth=80.0, seed=0xA450CA05))
+    got = _check(b)
+    assert got.n_chains_ok >= 20 and int(np.diff(got.read_off).max()) > 1500
 
 
 def test_four_bit_codes_diploid_many_alleles():
@@ -242,7 +257,7 @@ def test_randomised_shapes_twice_each():
 def test_build_limits_are_reported_not_mis_phased():
     import copy
     b = synth.generate(synth.params(2, 6, 1, 12, depth=20.0, seed=97))
-    b5 = copy.copy(b); b5.ploidy = 5
+    b5 = copy.copy(b); b5.ploidy = 7
     with pytest.raises(RuntimeError, match=r"failed \(3\).*ploidy"):          # AHS_ERR_LIMIT
         api.phase_batch(b5)
     # a bubble with 16 alleles: more than the 4-bit codes hold

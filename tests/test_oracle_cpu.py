@@ -175,3 +175,15 @@ def test_radix_selection_of_the_scoring_kernel_equals_rule_r1_by_sorting(tmp_pat
     subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "native", "select_harness.cpp"), "-o", exe], check=True)
     r = subprocess.run([exe, "60000"], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+
+
+@pytest.mark.parametrize("ploidy", [5, 6])
+def test_rule_r3c_definition_equals_sub_multiset_dp(ploidy):
+    # canonical-tuple threading (ploidy > 4): the all-pairs definition against the sub-multiset DP the parity tests use at size
+    import ctypes as C
+    lib = load()
+    lib.ahs_oracle_canonical_selfcheck.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_double)]
+    for seed in range(12):
+        cost = C.c_double()
+        assert lib.ahs_oracle_canonical_selfcheck(ploidy, 10, 9, seed, C.byref(cost)) == 0
+        assert cost.value > 0

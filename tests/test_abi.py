@@ -43,7 +43,7 @@ def test_struct_layout_matches_the_header():
 
 def test_limits_and_cost_model():
     lim = api.limits()
-    assert lim.max_ploidy == 4 and lim.max_alleles == 15 and lim.max_positions == 32767 and lim.max_reads_cluster >= 128
+    assert lim.max_ploidy == 6 and lim.max_clusters_position == 128 and lim.max_alleles == 15 and lim.max_positions == 32767 and lim.max_reads_cluster >= 128
     lib = api.load_library()
     assert lib.ahs_chain_cost(40, 75, 2500, 2) < lib.ahs_chain_cost(400, 750, 25000, 2)
 

@@ -38,6 +38,7 @@ typedef std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<
 ChainAlleles ChainsToReadsetDetailed(Graph graph);     // reference src/chainstoreadset.cpp:161
 void alignmentsToReadset(AlignmentReader&, Graph&, ChainAlleles&, string, bool, std::vector<std::pair<int, int>>&, std::mutex&);
 void alignmentsToReadset(const ahs_host::GafStore&, Graph&, ChainAlleles&, string, bool, std::vector<std::pair<int, int>>&, std::mutex&);
+namespace ahs_host { int unphased_chains(); }
 namespace ahs_host {
 ChainAlleles chain_alleles(const Graph& graph);
 int read_gfa(const std::string& filename, Graph& graph, std::string& err);
@@ -140,8 +141,9 @@ int main(int argc, char* argv[]) {
     auto leave = [&]() -> int {
         if (warm.joinable()) warm.join();
         cout.flush(); cerr.flush(); fflush(nullptr);
-        _exit(0);
-        return 0;
+        const int rc = ahs_host::unphased_chains() > 0 ? 3 : 0;      // a chain beyond a build limit was not phased: say so in the exit code
+        _exit(rc);
+        return rc;
     };
     if (cmd == "only-bubbles") return leave();
 

@@ -11,8 +11,12 @@
 //   2. call ahs_phase_batch() — the sm_100a CUDA path; there is no CPU path behind it;
 //   3. write <prefix>-result.txt, <prefix>-chain<id>-result.txt and the stdout "hap:" lines with
 //      the semantics of src/alignmentstoreadset.cpp:70-83 and :411-486.
-// Not reproduced: ./logfile.log and the -readset*.txt debugging dumps (third-party
-// ReadSet::toString() text), see INTEGRATION.md.
+//      and <prefix>-chain<id>-readset_final.txt (:298-303; the text of ReadSet::toString() is third-party and
+//      unverifiable here: the format is the one of oracle/whatshap_shim, to which the tests pin it).
+// Not reproduced: ./logfile.log and <prefix>-chain<id>-readset.txt (:284-293: dumps of the stage-A read sets, which the
+// device reduces to two scalars per chain, SURVEY A#23), see INTEGRATION.md.
+// A chain that exceeds a build limit (status >= AHS_CHAIN_TOO_LARGE) is reported on stderr, gets header-only output like
+// an empty chain, and makes the process exit with code 3 (ahs_host::unphased_chains()).
 #include <algorithm>
 #include <atomic>
 #include <charconv>
@@ -176,9 +180,14 @@ static inline void put_int(std::string& s, long v) {
     s.append(buf, (size_t)(r.ptr - buf));
 }
 
+static std::atomic<int> g_unphased{0};
+int unphased_chains() { return g_unphased.load(); }
+
 void emit(const ahs_batch_out& out, Graph& graph,
           std::unordered_map<int, std::unordered_map<int, std::vector<std::vector<int>>>>& pathToAlleles,
-          std::vector<std::pair<int, int>>& size_sorting, const std::string& prefix) {
+          std::vector<std::pair<int, int>>& size_sorting, const std::string& prefix,
+          const std::vector<std::vector<std::string>>& read_names) {
+    const bool dumps = getenv("AHSOKA_NO_READSET_DUMPS") == nullptr;
     const int ploidy = out.ploidy;
     const size_t C = size_sorting.size();
     // chains are independent: worker threads format a chain's text and write its <prefix>-chain<id>-result.txt; the
@@ -231,6 +240,22 @@ void emit(const ahs_batch_out& out, Graph& graph,
                     full += line;
                 }
                 resfile.close();
+                if (dumps) {                                                                 // :298-303, the final (sorted) read set
+                    std::string rs;
+                    const int64_t r0 = out.read_off[c], r1 = out.read_off[c + 1];
+                    rs += "readset size: "; put_int(rs, (long)(r1 - r0)); rs += "\nReadSet:\n";
+                    for (int64_t r = r0; r < r1; r++) {
+                        rs += "  "; rs += read_names[c][(size_t)out.read_id[r]]; rs += " (";
+                        for (int64_t x = out.cell_off[r]; x < out.cell_off[r + 1]; x++) {
+                            if (x > out.cell_off[r]) rs += ';';
+                            rs += '['; put_int(rs, out.cell_pos[x]); rs += ','; put_int(rs, (long)out.cell_allele[x]); rs += ",30]";      // quality 30: :118, :235
+                        }
+                        rs += ")\n";
+                    }
+                    rs += '\n';
+                    std::ofstream rsf(prefix + "-chain" + std::to_string(chainid) + "-readset_final.txt");
+                    rsf.write(rs.data(), (std::streamsize)rs.size());
+                }
                 std::string& haps = haps_of[c];
                 for (int i = 0; i < ploidy; i++) {                                           // :479-486
                     haps += "hap: \n";
@@ -254,8 +279,11 @@ void emit(const ahs_batch_out& out, Graph& graph,
     std::ofstream full_output(prefix + "-result.txt", std::ios_base::app);        // append, :72
     for (size_t c = 0; c < C; c++) {
         full_output.write(full_of[c].data(), (std::streamsize)full_of[c].size());
-        if (out.status[c] >= AHS_CHAIN_TOO_LARGE)
-            std::cerr << "ahsoka_b200: chain " << size_sorting[c].second << " not phased (status " << out.status[c] << ")" << std::endl;
+        if (out.status[c] >= AHS_CHAIN_TOO_LARGE) {
+            g_unphased++;
+            std::cerr << "ahsoka_b200: chain " << size_sorting[c].second << " exceeds a build limit and was NOT phased (status " << out.status[c]
+                      << "): header-only output; the process will exit with code 3" << std::endl;
+        }
         std::cout.write(haps_of[c].data(), (std::streamsize)haps_of[c].size());
     }
     std::cout.flush();
@@ -304,7 +332,7 @@ static void phase_and_emit(FlatBatch& fb, int ploidy, Graph& graph, ChainAlleles
     }
     {
         StageTimer t("emit");
-        emit(out, graph, pathToAlleles, size_sorting, prefix);
+        emit(out, graph, pathToAlleles, size_sorting, prefix, fb.read_names);
     }
     ahs_free_out(&out);
 }

@@ -64,6 +64,8 @@ def config(name: str, scale: float = 1.0) -> SynthParams:
         return params(4, n(10000), 1, 80, depth=60.0, seed=0xA450CA04)
     if name == "cfg5":      # hexaploid, Zipf-skewed chain sizes up to 10k bubbles, 80x
         return params(6, n(2000), 2, 500, 2, 10000, 1.2, max(1, n(4)), depth=80.0, seed=0xA450CA05)
+    if name == "cfg5cap":   # cfg5 with the chain length capped at 1000 bubbles (<= ~3,600 final reads per chain: inside the cluster-editing limit)
+        return params(6, n(2000), 2, 500, 2, 1000, 1.2, max(1, n(4)), depth=80.0, seed=0xA450CA05)
     if name == "zipf2":     # diploid, Zipf-skewed chain sizes up to 10k bubbles, 30x: the load-balancing stress of SURVEY 8e
         return params(2, n(4000), 2, 500, 2, 10000, 1.2, max(1, n(4)), depth=30.0, seed=0xA450CA06)
     raise KeyError(name)

@@ -98,6 +98,7 @@ WORKLOAD_NAMES = {"cfg1": "cfg1: BASELINE.json configs[0] one chain of 1k bubble
                   "cfg3": "cfg3: BASELINE.json configs[2] synthetic triploid graph",
                   "cfg4": "cfg4: BASELINE.json configs[3] synthetic tetraploid graph",
                   "cfg5": "cfg5: BASELINE.json configs[4] synthetic hexaploid graph, Zipf-skewed chain sizes",
+                  "cfg5cap": "cfg5cap: BASELINE.json configs[4] with chain length capped at 1000 bubbles",
                   "zipf2": "zipf2: diploid, Zipf-skewed chain sizes up to 10k bubbles (load-balancing stress)"}
 
 

@@ -128,3 +128,32 @@ def test_cfg1_b200_cli_matches_reference_verbatim():
     if not os.path.exists(B200_CLI):
         pytest.skip("ahsoka_b200/bin/Ahsoka_b200 not built (needs /root/reference at build time)")
     _cfg1_cli(B200_CLI)
+
+
+# ---- <prefix>-chain<id>-readset_final.txt (reference src/alignmentstoreadset.cpp:298-303): pinned to what Ahsoka_ref
+# (reference sources verbatim + shim) writes for the same fixture; ReadSet::toString() itself is the shim's format.
+def _readset_dumps(exe, case):
+    import glob
+    with tempfile.TemporaryDirectory() as td:
+        _stage(case, td)
+        _run_cli(exe, case, td)
+        return {os.path.basename(p): open(p).read() for p in sorted(glob.glob(os.path.join(td, "out-chain*-readset_final.txt")))}
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_flat_oracle_cli_readset_final_dumps_match_reference_verbatim(case):
+    ref, exe = os.path.join(REF_DIR, "Ahsoka_ref"), os.path.join(REF_DIR, "Ahsoka_flat_oracle")
+    if not (os.path.exists(ref) and os.path.exists(exe)):
+        pytest.skip("oracle/_ref binaries not built (need /root/reference at build time)")
+    want = _readset_dumps(ref, case)
+    assert want and _readset_dumps(exe, case) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_b200_cli_readset_final_dumps_match_reference_verbatim(case):
+    ref = os.path.join(REF_DIR, "Ahsoka_ref")
+    if not (os.path.exists(ref) and os.path.exists(B200_CLI)):
+        pytest.skip("binaries not built (need /root/reference at build time)")
+    want = _readset_dumps(ref, case)
+    assert want and _readset_dumps(B200_CLI, case) == want

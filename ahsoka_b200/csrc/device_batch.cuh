@@ -40,6 +40,7 @@ struct DB {
     int32_t *ch_status, *ch_maxpos, *ch_flags, *ch_T, *ch_nfinal, *ch_npos, *ch_maxspan, *ch_words, *ch_nclusters;
     int64_t *tot_cells, *tot_pairs; int32_t *err_flags;
     unsigned long long *ch_cells;                         // [C] cells of the chain's final reads
+    unsigned long long *ch_pairs2;                        // [C] twice the scored pairs of a chain above CC_MAXN reads (k_read_rates): sizes its edge slots
     // ---- final reads (after the host computed the offsets)
     int64_t *frow_off, *pos_off, *code_off, *cw_off;      // [C+1],[C+1],[C],[C]
     int32_t *fr_chain, *fr_first, *fr_last, *fr_mapq, *fr_id, *fr_nv, *fr_cluster;

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_read_rates(DB d) {
             ed = Nd > 0 ? (uint32_t)((Kd * 1024 + Nd / 2) / Nd) : es;
         }
         __syncwarp();
-        if (lane == 0) { d.es[f] = (uint16_t)es; d.ed[f] = (uint16_t)ed; pairs_local += m; }
+        if (lane == 0) { d.es[f] = (uint16_t)es; d.ed[f] = (uint16_t)ed; pairs_local += m; if (m) atomicAdd(&d.ch_pairs2[c], (unsigned long long)m); }
     }
     if (lane == 0 && pairs_local) atomicAdd((unsigned long long*)d.tot_pairs, (unsigned long long)pairs_local);
 }

@@ -23,6 +23,7 @@
 #include "k_score.cuh"
 #include "k_chain.cuh"
 #include "k_cluster_big.cuh"
+#include "k_cluster_sparse.cuh"
 #include "k_thread.cuh"
 #include "k_thread_canon.cuh"
 
@@ -38,8 +39,10 @@ struct LimitFail { std::string msg; };
 struct ArgFail { std::string msg; };
 struct PassThrough { int rc; std::string msg; };      // failure of one device thread of a multi-device call, re-raised by the caller
 
-constexpr int MAX_READS_CLUSTER = 8191;        // 13-bit node ids in the slot keys of k_cluster_big
+constexpr int MAX_READS_CLUSTER = 65535;       // 16-bit node ids in the edge keys of k_cluster_sparse (chains above CC_MAXN reads)
+constexpr int MAX_READS_CLUSTER_DENSE = 8191;  // k_cluster_big (AHS_CLUSTER_BIG=1: the dense predecessor, kept for comparison)
 constexpr int MAX_POSITIONS = 32767;
+constexpr int64_t MAX_BIG_W_BYTES = (int64_t)48 << 30;       // dense weight matrices of the chains above CC_MAXN reads, per call and device
 
 // ------------------------------------------------------------------ memory pools (persist per device)
 struct Pool {
@@ -215,6 +218,7 @@ static Ctx* get_ctx(int device) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     check_classes(c->smem_optin);
     CK(cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    CK(cudaFuncSetAttribute(k_cluster_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     chain_kernel_attributes(c->smem_optin);
     g_ctx[device] = c;
     return c;
@@ -367,7 +371,7 @@ struct Pipeline {
         d.poscov = dalloc<uint8_t>(sz.NB); d.pos_compact = dalloc<int32_t>(sz.NB);
         d.ch_status = dalloc<int32_t>(C); d.ch_maxpos = dalloc<int32_t>(C); d.ch_flags = dalloc<int32_t>(C); d.ch_T = dalloc<int32_t>(C);
         d.ch_nfinal = dalloc<int32_t>(C); d.ch_npos = dalloc<int32_t>(C); d.ch_maxspan = dalloc<int32_t>(C); d.ch_words = dalloc<int32_t>(C);
-        d.ch_nclusters = dalloc<int32_t>(C); d.ch_cells = dalloc<unsigned long long>(C);
+        d.ch_nclusters = dalloc<int32_t>(C); d.ch_cells = dalloc<unsigned long long>(C); d.ch_pairs2 = dalloc<unsigned long long>(C);
         d.tot_cells = dalloc<int64_t>(1); d.tot_pairs = dalloc<int64_t>(1); d.err_flags = dalloc<int32_t>(1);
         d.ln = cx->d_ln; d.ln1 = cx->d_ln1;
         h_status = cx->pin.get<int32_t>(C); h_nfinal = cx->pin.get<int32_t>(C); h_npos = cx->pin.get<int32_t>(C);
@@ -387,7 +391,7 @@ struct Pipeline {
         CK(cudaMemsetAsync(d.rankA, 0xff, std::max<int64_t>(sz.NB, 1) * 4, st));
         CK(cudaMemsetAsync(d.ch_status, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxpos, 0xff, C * 4, st)); CK(cudaMemsetAsync(d.ch_flags, 0, C * 4, st));
         CK(cudaMemsetAsync(d.ch_nfinal, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_maxspan, 0, C * 4, st)); CK(cudaMemsetAsync(d.ch_nclusters, 0, C * 4, st));
-        CK(cudaMemsetAsync(d.ch_cells, 0, C * 8, st));
+        CK(cudaMemsetAsync(d.ch_cells, 0, C * 8, st)); CK(cudaMemsetAsync(d.ch_pairs2, 0, C * 8, st));
         CK(cudaMemsetAsync(d.tot_cells, 0, 8, st)); CK(cudaMemsetAsync(d.tot_pairs, 0, 8, st)); CK(cudaMemsetAsync(d.err_flags, 0, 4, st));
     }
 
@@ -483,8 +487,17 @@ struct Pipeline {
         bool status_changed = false;
         s_frow[0] = 0; s_pos[0] = 0;
         int64_t nf_big = 0, cells_ok = 0; int n_max = 0;
+        const bool dense_big = getenv("AHS_CLUSTER_BIG") != nullptr;          // the dense predecessor of k_cluster_sparse, for comparison
+        int max_reads = dense_big ? MAX_READS_CLUSTER_DENSE : MAX_READS_CLUSTER;
+        if (const char* e = getenv("AHS_MAX_READS_CLUSTER")) max_reads = std::max(CC_MAXN, std::min(max_reads, atoi(e)));      // tests: exercise the limit cheaply
+        int64_t big_w_bytes = 0;
         for (int64_t c = 0; c < C; c++) {
-            if (h_status[c] == AHS_CHAIN_OK && h_nfinal[c] > MAX_READS_CLUSTER) { h_status[c] = AHS_CHAIN_TOO_LARGE; status_changed = true; }
+            if (h_status[c] == AHS_CHAIN_OK && h_nfinal[c] > CC_MAXN) {
+                // chains above the shared-memory kernels keep a dense n x n weight matrix in HBM: bounded per chain and per call
+                const int64_t wb = (int64_t)h_nfinal[c] * h_nfinal[c] * 4;
+                if (h_nfinal[c] > max_reads || big_w_bytes + wb > MAX_BIG_W_BYTES) { h_status[c] = AHS_CHAIN_TOO_LARGE; status_changed = true; }
+                else big_w_bytes += wb;
+            }
             s_status[c] = h_status[c];
             const bool ok = h_status[c] == AHS_CHAIN_OK;
             const int64_t n = ok ? h_nfinal[c] : 0, np = ok ? h_npos[c] : 0;
@@ -528,9 +541,11 @@ struct Pipeline {
             // HBM-resident path (chains above CC_MAXN reads): dense n x n workspaces
             for (int64_t c = 0; c < C; c++) if (!s_small[c] && h_nfinal[c] > 0)
                 CK(cudaMemsetAsync(d.W + s_cw[c], 0, (size_t)h_nfinal[c] * h_nfinal[c] * 4, st));
-            d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw); d.big_key = dalloc<uint32_t>(n_cw);
-            d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
-            d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
+            if (dense_big) {
+                d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw); d.big_key = dalloc<uint32_t>(n_cw);
+                d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
+                d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
+            }
         }
         d.rec = dalloc<PosRec>(NP); d.back = dalloc<uint16_t>(NP * S_max);
         d.path = dzero<int32_t>(NP * in->ploidy); d.hap_allele = dzero<uint8_t>(NP * in->ploidy); d.dp_cost = dzero<double>(C);
@@ -563,6 +578,46 @@ struct Pipeline {
         // ---- scoring
         if (nf_big) { k_read_rates<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         if (nf_big) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
+        // chains above CC_MAXN reads: edge slots, lists and the maximum tree of k_cluster_sparse.  Their sizes follow from the
+        // number of scored pairs per chain, known after k_read_rates: sync #2 (only when such chains exist).
+        SpArrays sp{}; int sp_nmax = 0, sp_max_leaf = 0; unsigned sp_grid = 0;
+        if (nf_big && !dense_big) {
+            unsigned long long* h_pairs2 = cx->pin.get<unsigned long long>(C);
+            CK(cudaMemcpyAsync(h_pairs2, d.ch_pairs2, C * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::vector<SpChain> chs;
+            int64_t slots = 0, pool = 0, nodes = 0, leaves = 0, sups = 0;
+            int firstb, lenb; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, firstb, lenb);
+            for (int k = 0; k < lenb; k++) {
+                const int c = s_order[firstb + k];
+                SpChain ch{};
+                ch.chain = c; ch.n = h_nfinal[c]; ch.w_off = s_cw[c];
+                const int64_t e0 = (int64_t)(h_pairs2[c] / 2) + 1;
+                if (e0 > ((int64_t)1 << 30)) throw LimitFail{"a chain has more than 2^30 scored read pairs"};
+                ch.slot_off = slots; ch.slot_cap = (int32_t)e0; ch.n_leaf = (int32_t)((e0 + 63) / 64); ch.n_sup = (ch.n_leaf + 63) / 64;
+                ch.list_off = pool; ch.list_cap = 2 * e0 * 9 + 1024;              // the initial lists + room for the lists written by the merges
+                ch.node_off = nodes; ch.leaf_off = leaves; ch.sup_off = sups;
+                slots += e0; pool += ch.list_cap; nodes += ch.n; leaves += ch.n_leaf; sups += ch.n_sup;
+                sp_nmax = std::max(sp_nmax, ch.n); sp_max_leaf = std::max(sp_max_leaf, ch.n_leaf);
+                chs.push_back(ch);
+            }
+            if (sp_smem_bytes(sp_nmax, sp_max_leaf) > cx->smem_optin) throw LimitFail{"a chain's cluster-editing state exceeds the shared memory of a block"};
+            sp.n_chains = (int)chs.size();
+            sp.chains = up_pinned(chs.data(), (int64_t)chs.size());
+            sp.key = dalloc<uint32_t>(slots); sp.flag = dalloc<uint8_t>(slots); sp.F = (long long*)dalloc<int64_t>(slots); sp.P = (long long*)dalloc<int64_t>(slots);
+            sp.pool = dalloc<uint32_t>(pool);
+            sp.lptr = (long long*)dalloc<int64_t>(nodes); sp.llen = dalloc<uint32_t>(nodes); sp.sa = dalloc<uint32_t>(nodes); sp.sb = dalloc<uint32_t>(nodes); sp.up = dalloc<uint32_t>(nodes);
+            sp.wa = dalloc<int32_t>(nodes); sp.wb = dalloc<int32_t>(nodes); sp.nw = dalloc<int32_t>(nodes);
+            sp.frF = (long long*)dalloc<int64_t>(nodes); sp.frP = (long long*)dalloc<int64_t>(nodes);
+            sp.leaf = (SpBest*)cx->dev.alloc((size_t)std::max<int64_t>(leaves, 1) * sizeof(SpBest)); sp.sup = (SpBest*)cx->dev.alloc((size_t)std::max<int64_t>(sups, 1) * sizeof(SpBest));
+            sp.bump = (long long*)dalloc<int64_t>((int64_t)chs.size()); sp.n_slots = dalloc<int32_t>((int64_t)chs.size());
+            sp_grid = (unsigned)std::min<int64_t>((int64_t)sms * 8, std::max<int64_t>(1, nodes / 8));
+            k_sp_degrees<<<sp_grid, TB, 0, st>>>(d, sp); k_sp_scan<<<(unsigned)chs.size(), 1024, 0, st>>>(sp);
+            k_sp_fill<<<sp_grid, TB, 0, st>>>(d, sp); k_sp_init_costs<<<(unsigned)sms * 8, TB, 0, st>>>(d, sp);
+            k_sp_leaves<<<(unsigned)sms * 8, TB, 0, st>>>(sp); k_sp_sups<<<(unsigned)sms * 2, TB, 0, st>>>(sp);
+            n_launches += 6;
+            CK(cudaGetLastError());
+        }
         // chains up to CC_MAXN reads: scoring out of shared memory, 4 B per pair to HBM (every chain of BASELINE config 2).
         // The size classes run side by side on the side streams: one class alone leaves issue slots idle (barrier waits).
         CK(cudaEventRecord(ln->ev_fork, st));
@@ -598,9 +653,12 @@ struct Pipeline {
         // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one 1024-thread block per chain
         if (nf_big) {
             int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
-            if (len) {
+            if (len && dense_big) {
                 const int nbig = std::min<int>(n_max, 8191);
                 k_cluster_big<<<(unsigned)std::min<int64_t>(len, sms), CB_THREADS, cb_smem_bytes(nbig), st>>>(d, dv_order + first, len, nbig, counters + 2);
+                n_launches += 1;
+            } else if (len) {
+                k_cluster_sparse<<<(unsigned)std::min<int64_t>(sp.n_chains, sms), SP_THREADS, sp_smem_bytes(sp_nmax, sp_max_leaf), st>>>(d, sp, sp_nmax, sp_max_leaf, counters + 2);
                 n_launches += 1;
             }
         }

@@ -273,12 +273,25 @@ def test_build_limits_are_reported_not_mis_phased():
     w2 = copy.copy(wide); w2.allele_off, w2.anode_off, w2.anode = new_ao, new_no.astype(np.int64), new_anode.astype(np.int32)
     with pytest.raises(RuntimeError, match=r"failed \(3\).*15 alleles"):
         api.phase_batch(w2)
-    # a chain with more final reads than cluster editing accepts: reported per chain, the other chains are phased
-    big = synth.generate(synth.params(2, 1, 0, 2600, depth=80.0, seed=99))
+    # a chain with more final reads than cluster editing accepts (65,535; lowered here through the testing knob): reported
+    # per chain, the other chains are phased
+    big = synth.generate(synth.params(2, 1, 0, 300, depth=80.0, seed=99))
     small = synth.generate(synth.params(2, 5, 1, 12, depth=20.0, seed=100))
-    got = api.phase_batch(big)
+    os.environ["AHS_MAX_READS_CLUSTER"] = "500"
+    try:
+        got = api.phase_batch(big)
+    finally:
+        del os.environ["AHS_MAX_READS_CLUSTER"]
     assert int(got.status[0]) == 3 and got.read_off[-1] == 0               # AHS_CHAIN_TOO_LARGE, nothing emitted for it
     assert not api.phase_batch(small).diff(oracle_phase(small))
+
+
+def test_chain_of_nine_thousand_reads_beyond_the_dense_kernels():
+    # one chain of 2,600 bubbles at 80x: ~9,100 final reads, 0.36 M edges — above what the dense big-chain kernel of round 1
+    # accepted (8,191); edge slots + lists + maximum tree (k_cluster_sparse) against the dense CPU oracle
+    b = synth.generate(synth.params(2, 1, 0, 2600, depth=80.0, seed=99))
+    got = _check(b)
+    assert got.n_chains_ok == 1 and int(got.read_off[-1]) > 8191
 
 
 @pytest.mark.parametrize("chunks", ["1", "2", "4"])

@@ -24,9 +24,9 @@
 
 namespace ahs {
 
-constexpr int SP_THREADS = 1024;
-constexpr int SP_FLCAP = 2048;                       // flagged edges per forbid round (more wait for the next round: still exact)
-constexpr int SP_SUPCAP = 1024;                      // level-2 entries queued per round
+constexpr int SP_THREADS = 1024;                     // chains above SP_SMALL_N reads; the others run in blocks of SP_THREADS_SMALL
+constexpr int SP_THREADS_SMALL = 256;
+constexpr int SP_SMALL_N = 1024;
 constexpr uint32_t SP_NONE = 0xffffffffu;
 constexpr uint8_t SPF_POS = 1, SPF_DEAD = 2, SPF_FORB = 4, SPF_FLAG = 8;
 
@@ -68,6 +68,9 @@ struct SpChain {
 };
 struct SpArrays {
     const SpChain* chains; int n_chains;
+    int64_t n_nodes, n_slot_cap, n_leaves, n_sups;   // totals over the chains (the chains' ranges are consecutive)
+    uint32_t* fl_slot; int32_t* fl_old;              // per slot capacity: the edges flagged in a forbid round (never truncated)
+    uint32_t* supq;                                  // per level-2 entry: the entries to visit in a round
     uint32_t* key; uint8_t* flag; long long *F, *P;  // slots
     uint32_t* pool;                                  // lists
     long long* lptr; uint32_t *llen, *sa, *sb, *up; int32_t *wa, *wb, *nw; long long *frF, *frP;      // per node
@@ -80,22 +83,27 @@ __device__ __forceinline__ long long sp_tf(int x, int y) { return (long long)max
 __device__ __forceinline__ long long sp_tp(int x, int y) { const int lo = min(x, y), hi = max(x, y); return (long long)max(min(hi, -lo), 0); }
 __device__ __forceinline__ int sp_other(uint32_t key, int x) { const int p = (int)(key >> 16), q = (int)(key & 0xffffu); return p == x ? q : p; }
 
+// chain that owns element x of a per-chain range array (ranges consecutive, `off` = member pointer to the range start)
+template <class F> __device__ __forceinline__ int sp_owner(const SpArrays& sp, int64_t x, F off) {
+    int lo = 0, hi = sp.n_chains - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off(sp.chains[mid]) <= x) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
 // ---------------------------------------------------------------- set-up, grid wide
 // degrees: up[x] = edges (x,y), y > x; llen[x] = all edges at x.  One warp per read, lanes over its partner band.
 __global__ void __launch_bounds__(256) k_sp_degrees(DB d, SpArrays sp) {
     const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int ci = 0; ci < sp.n_chains; ci++) {
-        const SpChain ch = sp.chains[ci];
-        const int n = ch.n; const int32_t* W = d.W + ch.w_off;
+    for (int64_t g = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); g < sp.n_nodes; g += (int64_t)gridDim.x * wpb) {
+        const SpChain ch = sp.chains[sp_owner(sp, g, [](const SpChain& c) { return c.node_off; })];
+        const int n = ch.n, x = (int)(g - ch.node_off); const int32_t* W = d.W + ch.w_off;
         const int64_t f0 = d.frow_off[ch.chain];
         const int32_t* first = d.fr_first + f0; const int32_t* lastp = d.fr_last + f0;
-        for (int x = blockIdx.x * wpb + (threadIdx.x >> 5); x < n; x += gridDim.x * wpb) {
-            int lo, hi; partner_band(d, ch.chain, x, n, first, first[x], lastp[x], lo, hi);
-            int nu = 0, na = 0;
-            for (int y = lo + lane; y <= hi; y += 32) if (y != x && W[(int64_t)x * n + y] != 0) { na++; nu += y > x ? 1 : 0; }
-            nu = warp_sum_i32(nu); na = warp_sum_i32(na);
-            if (lane == 0) { sp.up[ch.node_off + x] = (uint32_t)nu; sp.llen[ch.node_off + x] = (uint32_t)na; }
-        }
+        int lo, hi; partner_band(d, ch.chain, x, n, first, first[x], lastp[x], lo, hi);
+        int nu = 0, na = 0;
+        for (int y = lo + lane; y <= hi; y += 32) if (y != x && W[(int64_t)x * n + y] != 0) { na++; nu += y > x ? 1 : 0; }
+        nu = warp_sum_i32(nu); na = warp_sum_i32(na);
+        if (lane == 0) { sp.up[g] = (uint32_t)nu; sp.llen[g] = (uint32_t)na; }
     }
 }
 
@@ -130,27 +138,25 @@ __global__ void __launch_bounds__(1024) k_sp_scan(SpArrays sp) {
 // slots in row-major order (x ascending, y ascending) and the lists
 __global__ void __launch_bounds__(256) k_sp_fill(DB d, SpArrays sp) {
     const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int ci = 0; ci < sp.n_chains; ci++) {
-        const SpChain ch = sp.chains[ci];
-        const int n = ch.n; const int32_t* W = d.W + ch.w_off;
+    for (int64_t g = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); g < sp.n_nodes; g += (int64_t)gridDim.x * wpb) {
+        const SpChain ch = sp.chains[sp_owner(sp, g, [](const SpChain& c) { return c.node_off; })];
+        const int n = ch.n, x = (int)(g - ch.node_off); const int32_t* W = d.W + ch.w_off;
         const int64_t f0 = d.frow_off[ch.chain];
         const int32_t* first = d.fr_first + f0; const int32_t* lastp = d.fr_last + f0;
         uint32_t* pool = sp.pool + ch.list_off;
-        for (int x = blockIdx.x * wpb + (threadIdx.x >> 5); x < n; x += gridDim.x * wpb) {
-            int lo, hi; partner_band(d, ch.chain, x, n, first, first[x], lastp[x], lo, hi);
-            uint32_t base = sp.up[ch.node_off + x];
-            for (int y0 = x + 1; y0 <= hi; y0 += 32) {
-                const int y = y0 + lane;
-                const int w = y <= hi ? W[(int64_t)x * n + y] : 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, w != 0);
-                if (w != 0) {
-                    const uint32_t s = base + __popc(bal & ((1u << lane) - 1u));
-                    sp.key[ch.slot_off + s] = ((uint32_t)x << 16) | (uint32_t)y; sp.flag[ch.slot_off + s] = w > 0 ? SPF_POS : 0;
-                    pool[sp.lptr[ch.node_off + x] + atomicAdd(&sp.llen[ch.node_off + x], 1u)] = s;
-                    pool[sp.lptr[ch.node_off + y] + atomicAdd(&sp.llen[ch.node_off + y], 1u)] = s;
-                }
-                base += __popc(bal);
+        int lo, hi; partner_band(d, ch.chain, x, n, first, first[x], lastp[x], lo, hi);
+        uint32_t base = sp.up[g];
+        for (int y0 = x + 1; y0 <= hi; y0 += 32) {
+            const int y = y0 + lane;
+            const int w = y <= hi ? W[(int64_t)x * n + y] : 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, w != 0);
+            if (w != 0) {
+                const uint32_t s = base + __popc(bal & ((1u << lane) - 1u));
+                sp.key[ch.slot_off + s] = ((uint32_t)x << 16) | (uint32_t)y; sp.flag[ch.slot_off + s] = w > 0 ? SPF_POS : 0;
+                pool[sp.lptr[ch.node_off + x] + atomicAdd(&sp.llen[ch.node_off + x], 1u)] = s;
+                pool[sp.lptr[ch.node_off + y] + atomicAdd(&sp.llen[ch.node_off + y], 1u)] = s;
             }
+            base += __popc(bal);
         }
     }
 }
@@ -158,26 +164,26 @@ __global__ void __launch_bounds__(256) k_sp_fill(DB d, SpArrays sp) {
 // initial induced costs: one warp per slot, lanes over the list of its first node (a common neighbour is in both lists)
 __global__ void __launch_bounds__(256) k_sp_init_costs(DB d, SpArrays sp) {
     const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int ci = 0; ci < sp.n_chains; ci++) {
+    for (int64_t g = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); g < sp.n_slot_cap; g += (int64_t)gridDim.x * wpb) {
+        const int ci = sp_owner(sp, g, [](const SpChain& c) { return c.slot_off; });
         const SpChain ch = sp.chains[ci];
+        const int s = (int)(g - ch.slot_off);
+        if (s >= sp.n_slots[ci]) continue;
         const int n = ch.n; const int32_t* W = d.W + ch.w_off;
         const uint32_t* pool = sp.pool + ch.list_off;
-        const int ns = sp.n_slots[ci];
-        for (int s = blockIdx.x * wpb + (threadIdx.x >> 5); s < ns; s += gridDim.x * wpb) {
-            const uint32_t key = sp.key[ch.slot_off + s];
-            const int x = (int)(key >> 16), y = (int)(key & 0xffffu);
-            const int w = W[(int64_t)x * n + y];
-            const long long lp = sp.lptr[ch.node_off + x]; const int ll = (int)sp.llen[ch.node_off + x];
-            long long f = 0, p = 0;
-            for (int i = lane; i < ll; i += 32) {
-                const int t = sp_other(sp.key[ch.slot_off + pool[lp + i]], x);
-                if (t == y) continue;
-                const int wx = W[(int64_t)x * n + t], wy = W[(int64_t)y * n + t];
-                f += sp_tf(wx, wy); p += sp_tp(wx, wy);
-            }
-            f = warp_sum_i64(f); p = warp_sum_i64(p);
-            if (lane == 0) { sp.F[ch.slot_off + s] = f + max(w, 0); sp.P[ch.slot_off + s] = p + max(-w, 0); }
+        const uint32_t key = sp.key[g];
+        const int x = (int)(key >> 16), y = (int)(key & 0xffffu);
+        const int w = W[(int64_t)x * n + y];
+        const long long lp = sp.lptr[ch.node_off + x]; const int ll = (int)sp.llen[ch.node_off + x];
+        long long f = 0, p = 0;
+        for (int i = lane; i < ll; i += 32) {
+            const int t = sp_other(sp.key[ch.slot_off + pool[lp + i]], x);
+            if (t == y) continue;
+            const int wx = W[(int64_t)x * n + t], wy = W[(int64_t)y * n + t];
+            f += sp_tf(wx, wy); p += sp_tp(wx, wy);
         }
+        f = warp_sum_i64(f); p = warp_sum_i64(p);
+        if (lane == 0) { sp.F[g] = f + max(w, 0); sp.P[g] = p + max(-w, 0); }
     }
 }
 
@@ -200,49 +206,43 @@ __device__ __forceinline__ SpBest sp_sup_maxima(const SpArrays& sp, const SpChai
 
 __global__ void __launch_bounds__(256) k_sp_leaves(SpArrays sp) {
     const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int ci = 0; ci < sp.n_chains; ci++) {
+    for (int64_t g = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); g < sp.n_leaves; g += (int64_t)gridDim.x * wpb) {
+        const int ci = sp_owner(sp, g, [](const SpChain& c) { return c.leaf_off; });
         const SpChain ch = sp.chains[ci];
-        const int ns = sp.n_slots[ci];
-        for (int l = blockIdx.x * wpb + (threadIdx.x >> 5); l < ch.n_leaf; l += gridDim.x * wpb) {
-            const SpBest b = sp_leaf_maxima(sp, ch, l, ns, lane);
-            if (lane == 0) sp.leaf[ch.leaf_off + l] = b;
-        }
+        const SpBest b = sp_leaf_maxima(sp, ch, (int)(g - ch.leaf_off), sp.n_slots[ci], lane);
+        if (lane == 0) sp.leaf[g] = b;
     }
 }
 __global__ void __launch_bounds__(256) k_sp_sups(SpArrays sp) {
     const int wpb = blockDim.x >> 5, lane = lane_id();
-    for (int ci = 0; ci < sp.n_chains; ci++) {
-        const SpChain ch = sp.chains[ci];
-        for (int su = blockIdx.x * wpb + (threadIdx.x >> 5); su < ch.n_sup; su += gridDim.x * wpb) {
-            const SpBest b = sp_sup_maxima(sp, ch, su, lane);
-            if (lane == 0) sp.sup[ch.sup_off + su] = b;
-        }
+    for (int64_t g = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); g < sp.n_sups; g += (int64_t)gridDim.x * wpb) {
+        const SpChain ch = sp.chains[sp_owner(sp, g, [](const SpChain& c) { return c.sup_off; })];
+        const SpBest b = sp_sup_maxima(sp, ch, (int)(g - ch.sup_off), lane);
+        if (lane == 0) sp.sup[g] = b;
     }
 }
 
 // ---------------------------------------------------------------- the greedy loop, one block per chain
 __host__ __device__ inline size_t sp_smem_bytes(int nmax, int max_leaf) {
     size_t b = 32 * sizeof(SpBest) + 256;                           // reduction scratch, scalars
-    b += (size_t)SP_FLCAP * 8;                                      // flagged edges: slot index, old weight
-    b += (size_t)SP_SUPCAP * 4;                                     // level-2 entries to visit in a round
     b += ((size_t)(nmax + 31) / 32) * 4;                            // inS bit set
     b += ((size_t)(max_leaf + 31) / 32) * 4 + ((size_t)(max_leaf / 64 + 32) / 32) * 4;      // dirty leaves, dirty level-2 entries
     b += (size_t)nmax * 2;                                          // labels
     return (b + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(SP_THREADS) k_cluster_sparse(DB d, SpArrays sp, int nmax, int max_leaf, int32_t* __restrict__ work_counter) {
+// chains [c_begin, c_end) of sp.chains (sorted by decreasing read count), one block of NT threads per chain at a time
+template <int NT>
+__global__ void __launch_bounds__(NT) k_cluster_sparse(DB d, SpArrays sp, int c_begin, int c_end, int nmax, int max_leaf, int32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char sp_sm[];
-    constexpr int NT = SP_THREADS, NW = NT / 32;
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    SpBest* red; int32_t* scal; uint32_t *fl_slot, *supq, *inS, *dleaf, *dsup; int32_t* fl_old; uint16_t* label;
+    SpBest* red; int32_t* scal; uint32_t *inS, *dleaf, *dsup; uint16_t* label;
     const int w_ins = (nmax + 31) / 32, w_leaf = (max_leaf + 31) / 32, w_sup = (max_leaf / 64 + 32) / 32;
     {
         unsigned char* p = sp_sm;
         red = (SpBest*)p; p += 32 * sizeof(SpBest);
         scal = (int32_t*)p; p += 256;       // [0] item [1] |S| [2] flagged edges [3] queued level-2 entries [4] new list cursor
-        fl_slot = (uint32_t*)p; p += SP_FLCAP * 4; fl_old = (int32_t*)p; p += SP_FLCAP * 4;
-        supq = (uint32_t*)p; p += SP_SUPCAP * 4;
         inS = (uint32_t*)p; p += (size_t)w_ins * 4; dleaf = (uint32_t*)p; p += (size_t)w_leaf * 4; dsup = (uint32_t*)p; p += (size_t)w_sup * 4;
         label = (uint16_t*)p;
     }
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_cluster_sparse(DB d, SpArrays sp
         __syncthreads();
         if (tid == 0) scal[0] = atomicAdd(work_counter, 1);
         __syncthreads();
-        const int ci = scal[0];
-        if (ci >= sp.n_chains) break;
+        const int ci = c_begin + scal[0];
+        if (ci >= c_end) break;
         const SpChain ch = sp.chains[ci];
         const int n = ch.n, n_slots = sp.n_slots[ci];
         int32_t* W = d.W + ch.w_off;
@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_cluster_sparse(DB d, SpArrays sp
         int32_t* wa = sp.wa + ch.node_off; int32_t* wb = sp.wb + ch.node_off; int32_t* nw = sp.nw + ch.node_off;
         long long* frF = sp.frF + ch.node_off; long long* frP = sp.frP + ch.node_off;
         SpBest* leaf = sp.leaf + ch.leaf_off; SpBest* sup = sp.sup + ch.sup_off;
+        uint32_t* fl_slot = sp.fl_slot + ch.slot_off; int32_t* fl_old = sp.fl_old + ch.slot_off; uint32_t* supq = sp.supq + ch.sup_off;
         for (int x = tid; x < n; x += NT) label[x] = (uint16_t)x;
         for (int x = tid; x < w_ins; x += NT) inS[x] = 0;
         for (int x = tid; x < w_leaf; x += NT) dleaf[x] = 0;
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_cluster_sparse(DB d, SpArrays sp
             b = sp_warp_reduce(b);
             if (lane == 0) red[wid] = b;
             __syncthreads();
-            SpBest r = red[lane];
+            SpBest r; r.clear();
+            if (lane < NW) r = red[lane];
             r = sp_warp_reduce(r);
             return r;
         };
@@ -422,9 +424,9 @@ __global__ void __launch_bounds__(SP_THREADS) k_cluster_sparse(DB d, SpArrays sp
                 // ------------------------------------------------ round: all negative candidates with icp > M at once
                 // (exactness argument: k_chain.cuh).  They are found from the top of the tree.
                 const long long M = so.M;
-                for (int su = tid; su < ch.n_sup; su += NT) if (sup[su].maxPneg > M) { const int q = atomicAdd(&scal[3], 1); if (q < SP_SUPCAP) supq[q] = (uint32_t)su; }
+                for (int su = tid; su < ch.n_sup; su += NT) if (sup[su].maxPneg > M) supq[atomicAdd(&scal[3], 1)] = (uint32_t)su;
                 __syncthreads();
-                const int n_q = min(scal[3], SP_SUPCAP);
+                const int n_q = scal[3];
                 for (int qi = wid; qi < n_q; qi += NW) {
                     const int su = (int)supq[qi];
                     for (int l = su * 64; l < min(ch.n_leaf, su * 64 + 64); l++) {
@@ -435,15 +437,14 @@ __global__ void __launch_bounds__(SP_THREADS) k_cluster_sparse(DB d, SpArrays sp
                             if (s >= n_slots) continue;
                             const uint8_t fl = flag[s];
                             if ((fl & (SPF_DEAD | SPF_FORB | SPF_POS)) || P[s] <= M) continue;
-                            const int q = atomicAdd(&scal[2], 1);
-                            if (q >= SP_FLCAP) continue;                 // left for the next round
+                            const int q = atomicAdd(&scal[2], 1);              // never truncated: a partial round would not be exact
                             flag[s] = fl | SPF_FLAG;
                             fl_slot[q] = (uint32_t)s; fl_old[q] = W[(int64_t)(key[s] >> 16) * n + (key[s] & 0xffffu)];
                         }
                     }
                 }
                 __syncthreads();
-                const int nflag = min(scal[2], SP_FLCAP);
+                const int nflag = scal[2];
                 // growth of the icp of the edges at both ends of every flagged edge (x,y): the term of (x,t) through y grows
                 // from min(|w_xy|, w_ty) to w_ty when w_ty > 0.  sign = -1 undoes it.
                 auto grow = [&](long long sign) {

@@ -218,7 +218,8 @@ static Ctx* get_ctx(int device) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     check_classes(c->smem_optin);
     CK(cudaFuncSetAttribute(k_cluster_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
-    CK(cudaFuncSetAttribute(k_cluster_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    CK(cudaFuncSetAttribute(k_cluster_sparse<SP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
+    CK(cudaFuncSetAttribute(k_cluster_sparse<SP_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin));
     chain_kernel_attributes(c->smem_optin);
     g_ctx[device] = c;
     return c;
@@ -580,7 +581,7 @@ struct Pipeline {
         if (nf_big) { k_pair_scores<BITS><<<grid_for(NF, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
         // chains above CC_MAXN reads: edge slots, lists and the maximum tree of k_cluster_sparse.  Their sizes follow from the
         // number of scored pairs per chain, known after k_read_rates: sync #2 (only when such chains exist).
-        SpArrays sp{}; int sp_nmax = 0, sp_max_leaf = 0; unsigned sp_grid = 0;
+        SpArrays sp{}; int sp_nmax = 0, sp_max_leaf = 0, sp_n_large = 0, sp_nmax_small = 0, sp_leaf_small = 0; unsigned sp_grid = 0;
         if (nf_big && !dense_big) {
             unsigned long long* h_pairs2 = cx->pin.get<unsigned long long>(C);
             CK(cudaMemcpyAsync(h_pairs2, d.ch_pairs2, C * 8, cudaMemcpyDeviceToHost, st));
@@ -599,10 +600,13 @@ struct Pipeline {
                 ch.node_off = nodes; ch.leaf_off = leaves; ch.sup_off = sups;
                 slots += e0; pool += ch.list_cap; nodes += ch.n; leaves += ch.n_leaf; sups += ch.n_sup;
                 sp_nmax = std::max(sp_nmax, ch.n); sp_max_leaf = std::max(sp_max_leaf, ch.n_leaf);
+                if (ch.n > SP_SMALL_N) sp_n_large++;                               // the list is sorted by decreasing read count
+                else { sp_nmax_small = std::max(sp_nmax_small, ch.n); sp_leaf_small = std::max(sp_leaf_small, ch.n_leaf); }
                 chs.push_back(ch);
             }
             if (sp_smem_bytes(sp_nmax, sp_max_leaf) > cx->smem_optin) throw LimitFail{"a chain's cluster-editing state exceeds the shared memory of a block"};
-            sp.n_chains = (int)chs.size();
+            sp.n_chains = (int)chs.size(); sp.n_nodes = nodes; sp.n_slot_cap = slots; sp.n_leaves = leaves; sp.n_sups = sups;
+            sp.fl_slot = dalloc<uint32_t>(slots); sp.fl_old = dalloc<int32_t>(slots); sp.supq = dalloc<uint32_t>(sups);
             sp.chains = up_pinned(chs.data(), (int64_t)chs.size());
             sp.key = dalloc<uint32_t>(slots); sp.flag = dalloc<uint8_t>(slots); sp.F = (long long*)dalloc<int64_t>(slots); sp.P = (long long*)dalloc<int64_t>(slots);
             sp.pool = dalloc<uint32_t>(pool);
@@ -611,10 +615,10 @@ struct Pipeline {
             sp.frF = (long long*)dalloc<int64_t>(nodes); sp.frP = (long long*)dalloc<int64_t>(nodes);
             sp.leaf = (SpBest*)cx->dev.alloc((size_t)std::max<int64_t>(leaves, 1) * sizeof(SpBest)); sp.sup = (SpBest*)cx->dev.alloc((size_t)std::max<int64_t>(sups, 1) * sizeof(SpBest));
             sp.bump = (long long*)dalloc<int64_t>((int64_t)chs.size()); sp.n_slots = dalloc<int32_t>((int64_t)chs.size());
-            sp_grid = (unsigned)std::min<int64_t>((int64_t)sms * 8, std::max<int64_t>(1, nodes / 8));
+            sp_grid = (unsigned)grid_for(nodes, 8, sms);
             k_sp_degrees<<<sp_grid, TB, 0, st>>>(d, sp); k_sp_scan<<<(unsigned)chs.size(), 1024, 0, st>>>(sp);
-            k_sp_fill<<<sp_grid, TB, 0, st>>>(d, sp); k_sp_init_costs<<<(unsigned)sms * 8, TB, 0, st>>>(d, sp);
-            k_sp_leaves<<<(unsigned)sms * 8, TB, 0, st>>>(sp); k_sp_sups<<<(unsigned)sms * 2, TB, 0, st>>>(sp);
+            k_sp_fill<<<sp_grid, TB, 0, st>>>(d, sp); k_sp_init_costs<<<(unsigned)grid_for(slots, 8, sms), TB, 0, st>>>(d, sp);
+            k_sp_leaves<<<(unsigned)grid_for(leaves, 8, sms), TB, 0, st>>>(sp); k_sp_sups<<<(unsigned)grid_for(sups, 8, sms), TB, 0, st>>>(sp);
             n_launches += 6;
             CK(cudaGetLastError());
         }
@@ -648,20 +652,30 @@ struct Pipeline {
             int32_t* scratch = dalloc<int32_t>((int64_t)grid * nt * kCluster[k].per * 3);     // slot-packing areas, one per warp
             cluster_launch(nt, kCluster[k].per, grid, smem, cx->side[q++ & 7], d, dv_order + first, len, kCluster[k].nmax, counters + 8 + N_SCORE + k, scratch); n_launches += 1;
         }
-        for (int i = 0; i < 8; i++) { CK(cudaEventRecord(ln->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, ln->ev_join[i], 0)); }
-        CK(cudaEventRecord(ln->ev[11], st));
-        // ---- cluster editing, HBM-resident (chains above CC_MAXN reads), one 1024-thread block per chain
+        // ---- cluster editing of the chains above CC_MAXN reads, on two of the side streams (next to the shared-memory classes)
         if (nf_big) {
             int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
             if (len && dense_big) {
                 const int nbig = std::min<int>(n_max, 8191);
-                k_cluster_big<<<(unsigned)std::min<int64_t>(len, sms), CB_THREADS, cb_smem_bytes(nbig), st>>>(d, dv_order + first, len, nbig, counters + 2);
+                k_cluster_big<<<(unsigned)std::min<int64_t>(len, sms), CB_THREADS, cb_smem_bytes(nbig), cx->side[7]>>>(d, dv_order + first, len, nbig, counters + 2);
                 n_launches += 1;
             } else if (len) {
-                k_cluster_sparse<<<(unsigned)std::min<int64_t>(sp.n_chains, sms), SP_THREADS, sp_smem_bytes(sp_nmax, sp_max_leaf), st>>>(d, sp, sp_nmax, sp_max_leaf, counters + 2);
-                n_launches += 1;
+                // the few long chains in blocks of 1024 threads, the many short ones (<= 1024 reads) 256 threads each, several per SM:
+                // a greedy step is a chain of dependent memory latencies, which only other chains can hide
+                if (sp_n_large) {
+                    k_cluster_sparse<SP_THREADS><<<(unsigned)std::min<int64_t>(sp_n_large, sms), SP_THREADS, sp_smem_bytes(sp_nmax, sp_max_leaf), cx->side[7]>>>(d, sp, 0, sp_n_large, sp_nmax, sp_max_leaf, counters + 2);
+                    n_launches += 1;
+                }
+                if (sp.n_chains > sp_n_large) {
+                    const size_t sm_small = sp_smem_bytes(sp_nmax_small, sp_leaf_small);
+                    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm_small + 1024)));
+                    k_cluster_sparse<SP_THREADS_SMALL><<<(unsigned)std::min<int64_t>(sp.n_chains - sp_n_large, (int64_t)sms * per_sm), SP_THREADS_SMALL, sm_small, cx->side[6]>>>(d, sp, sp_n_large, sp.n_chains, sp_nmax_small, sp_leaf_small, counters + 3);
+                    n_launches += 1;
+                }
             }
         }
+        for (int i = 0; i < 8; i++) { CK(cudaEventRecord(ln->ev_join[i], cx->side[i])); CK(cudaStreamWaitEvent(st, ln->ev_join[i], 0)); }
+        CK(cudaEventRecord(ln->ev[11], st));
         CK(cudaEventRecord(ln->ev[4], st));
         // ---- coverage / consensus, threading
         if (NP && BITS == 2) { k_consensus_chain<<<grid_for(C, 4, sms), 128, 0, st>>>(d); n_launches += 1; }      // chains with <= 16 clusters

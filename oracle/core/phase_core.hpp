@@ -267,7 +267,7 @@ inline std::vector<std::vector<int32_t>> cluster_edit(int n, const std::vector<P
         F[(size_t)s.i * N + s.j] = f; P[(size_t)s.i * N + s.j] = p; insert_c(s.i, s.j);
     }
     ClusterEditStats st;
-    std::vector<int32_t> S; std::vector<int32_t> newrow;
+    std::vector<int32_t> S; std::vector<int32_t> newrow; std::vector<int32_t> pos_in_S;
     while (!SF.empty()) {
         Key kf = *SF.begin(), kp = *SP.begin();
         int64_t mF = -std::get<0>(kf), mP = -std::get<0>(kp);
@@ -287,14 +287,21 @@ inline std::vector<std::vector<int32_t>> cluster_edit(int n, const std::vector<P
                 int x = S[u]; int32_t wa = w(a, x), wb = w(b, x);
                 newrow[u] = (wa == FORB || wb == FORB) ? FORB : wa + wb;
             }
-            // pairs inside S: swap the terms through a and b for the term through the merged node
-            for (size_t u = 0; u < S.size(); u++) for (size_t v = u + 1; v < S.size(); v++) {
-                int x = S[u], y = S[v];
-                if (!is_cand(x, y)) continue;
-                int64_t df = tf(newrow[u], newrow[v]) - tf(w(x, a), w(y, a)) - tf(w(x, b), w(y, b));
-                int64_t dp = tp(newrow[u], newrow[v]) - tp(w(x, a), w(y, a)) - tp(w(x, b), w(y, b));
-                if (df != 0 || dp != 0) { erase_c(x, y); F[(size_t)x * N + y] += df; P[(size_t)x * N + y] += dp; insert_c(x, y); }
+            // pairs inside S: swap the terms through a and b for the term through the merged node.  A candidate pair (x,y) has
+            // y in the adjacency list of x, so the lists are walked instead of all |S|^2 pairs (same pairs, same arithmetic).
+            if (pos_in_S.size() != N) pos_in_S.assign(N, -1);
+            for (size_t u = 0; u < S.size(); u++) pos_in_S[S[u]] = (int32_t)u;
+            for (size_t u = 0; u < S.size(); u++) {
+                const int x = S[u];
+                for (int y : nbr[x]) {
+                    if (y <= x || pos_in_S[y] < 0 || !is_cand(x, y)) continue;
+                    const size_t v = (size_t)pos_in_S[y];
+                    int64_t df = tf(newrow[u], newrow[v]) - tf(w(x, a), w(y, a)) - tf(w(x, b), w(y, b));
+                    int64_t dp = tp(newrow[u], newrow[v]) - tp(w(x, a), w(y, a)) - tp(w(x, b), w(y, b));
+                    if (df != 0 || dp != 0) { erase_c(x, y); F[(size_t)x * N + y] += df; P[(size_t)x * N + y] += dp; insert_c(x, y); }
+                }
             }
+            for (size_t u = 0; u < S.size(); u++) pos_in_S[S[u]] = -1;
             // drop all candidates touching a or b
             erase_c(a, b);
             for (size_t u = 0; u < S.size(); u++) {

@@ -286,12 +286,15 @@ def test_build_limits_are_reported_not_mis_phased():
     assert not api.phase_batch(small).diff(oracle_phase(small))
 
 
-def test_chain_of_nine_thousand_reads_beyond_the_dense_kernels():
-    # one chain of 2,600 bubbles at 80x: ~9,100 final reads, 0.36 M edges — above what the dense big-chain kernel of round 1
-    # accepted (8,191); edge slots + lists + maximum tree (k_cluster_sparse) against the dense CPU oracle
-    b = synth.generate(synth.params(2, 1, 0, 2600, depth=80.0, seed=99))
+def test_long_chains_of_thousands_of_reads():
+    # a chain of 600 bubbles at 80x (~2,100 final reads, 80 k edges, neighbourhoods of > 1,000 nodes) and chains just above
+    # 1,024 reads: edge slots + lists + maximum tree (k_cluster_sparse), both block sizes
+    b = synth.generate(synth.params(2, 1, 0, 600, depth=80.0, seed=99))
     got = _check(b)
-    assert got.n_chains_ok == 1 and int(got.read_off[-1]) > 8191
+    assert got.n_chains_ok == 1 and int(np.diff(got.read_off).min()) > 2000
+    b = synth.generate(synth.params(3, 3, 0, 700, depth=45.0, seed=98))
+    got = _check(b)
+    assert got.n_chains_ok == 3 and int(np.diff(got.read_off).min()) > 1024
 
 
 @pytest.mark.parametrize("chunks", ["1", "2", "4"])

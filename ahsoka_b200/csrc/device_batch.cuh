@@ -43,6 +43,7 @@ struct DB {
     unsigned long long *ch_pairs2;                        // [C] twice the scored pairs of a chain above CC_MAXN reads (k_read_rates): sizes its edge slots
     // ---- final reads (after the host computed the offsets)
     int64_t *frow_off, *pos_off, *code_off, *cw_off;      // [C+1],[C+1],[C],[C]
+    int64_t *cf_off;                                      // [C] offset of a chain's dense cluster-editing workspaces (k_cluster_big: chains of CC_MAXN+1 .. 1024 reads)
     int32_t *fr_chain, *fr_first, *fr_last, *fr_mapq, *fr_id, *fr_nv, *fr_cluster;
     uint32_t *codes;
     int32_t *pos, *pos_compact, *pos_chain;

@@ -19,8 +19,8 @@
 
 namespace ahs {
 
-constexpr int CB_THREADS = 1024;
-constexpr int CB_FLCAP = 2048;                      // flagged edges per forbid round (more -> several rounds, still exact)
+constexpr int CB_THREADS = 256;                      // several chains per SM: a greedy step is a chain of memory latencies that only other chains hide
+constexpr int CB_FLCAP = 2048;                      // flagged edges per forbid round (more -> the round is abandoned for a sequential step)
 constexpr uint32_t CB_POS = 1u << 31, CB_FLAG = 1u << 30, CB_DEAD = 1u << 29, CB_GONE = CB_FLAG | CB_DEAD, CB_KEY = (1u << 26) - 1u;
 
 __host__ __device__ inline size_t cb_smem_bytes(int nmax) {
@@ -59,12 +59,14 @@ __device__ __forceinline__ CBBest cb_shfl_xor(const CBBest& b, int o) {
 }
 
 // block-wide combination; two barriers
+template <int NW>
 __device__ __forceinline__ CBBest cb_reduce(CBBest b, CBBest* red, int tid) {
     for (int o = 16; o > 0; o >>= 1) { const CBBest t = cb_shfl_xor(b, o); b.merge(t); }
     __syncthreads();                                                   // red is free again
     if ((tid & 31) == 0) red[tid >> 5] = b;
     __syncthreads();
-    CBBest r = red[tid & 31];                                          // 32 warps
+    CBBest r; r.clear();
+    if ((tid & 31) < NW) r = red[tid & 31];
     for (int o = 16; o > 0; o >>= 1) { const CBBest t = cb_shfl_xor(r, o); r.merge(t); }
     return r;
 }
@@ -100,9 +102,9 @@ __global__ void __launch_bounds__(CB_THREADS) k_cluster_big(DB d, const int32_t*
         const int n = (int)(d.frow_off[c + 1] - f0);
         const int64_t nn = (int64_t)n * n;
         int32_t* W = d.W + d.cw_off[c];
-        long long* SF = (long long*)(d.F + d.cw_off[c]); long long* SP = SF + nn / 2;            // slot icf / icp (<= n(n-1)/2 slots)
-        long long* Dm = (long long*)(d.P + d.cw_off[c]);                                         // growth matrix of the rounds / packing area
-        uint32_t* SK = d.big_key + d.cw_off[c];                                                  // slot keys
+        long long* SF = (long long*)(d.F + d.cf_off[c]); long long* SP = SF + nn / 2;            // slot icf / icp (<= n(n-1)/2 slots)
+        long long* Dm = (long long*)(d.P + d.cf_off[c]);                                         // growth matrix of the rounds / packing area
+        uint32_t* SK = d.big_key + d.cf_off[c];                                                  // slot keys
         int32_t* wa = d.ce_list + f0; int32_t* wb = d.ce_newrow + f0; int32_t* nwv = d.ce_label + f0;
         long long* frF = (long long*)(d.ce_rbF + f0); long long* frP = (long long*)(d.ce_rbP + f0);
         int32_t* lo = d.ce_rbFarg + f0; int32_t* hi = d.ce_rbParg + f0;
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_cluster_big(DB d, const int32_t*
             SF[s] = f; SP[s] = p;
             mine.consider(kq, f, p);
         }
-        CBBest so = cb_reduce(mine, red, tid);
+        CBBest so = cb_reduce<NW>(mine, red, tid);
         int live_cap = so.live;
         bool force_single = false;
         while (so.M >= 0) {
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_cluster_big(DB d, const int32_t*
                     mine.consider(kq, f, p);
                 }
                 force_single = false;
-                so = cb_reduce(mine, red, tid);
+                so = cb_reduce<NW>(mine, red, tid);
                 // pack the slot list once half of it is dead (through the growth matrix, free outside a round)
                 if (so.live * 2 <= live_cap && so.live >= NT) {
                     unsigned char* pk = (unsigned char*)Dm;                      // icf | icp | keys of the survivors: 20 B each, <= 5 n^2 B
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_cluster_big(DB d, const int32_t*
                     mine.consider(kq, f, p);
                 }
                 force_single = false;
-                so = cb_reduce(mine, red, tid);
+                so = cb_reduce<NW>(mine, red, tid);
                 if (tid == 0) { W[(int64_t)a * n + b] = CC_FORB; W[(int64_t)b * n + a] = CC_FORB; }
                 __syncthreads();
             } else {
@@ -269,14 +271,25 @@ __global__ void __launch_bounds__(CB_THREADS) k_cluster_big(DB d, const int32_t*
                     if (kq & CB_FLAG) { SK[s] = CB_DEAD; continue; }               // forbidden for good in an earlier round
                     if ((kq & (CB_DEAD | CB_POS)) || SP[s] <= M) continue;
                     const int pos = atomicAdd(&scal[4], 1);
-                    if (pos >= CB_FLCAP) continue;                                 // left for the next round
+                    if (pos >= CB_FLCAP) { SK[s] = kq | CB_FLAG; continue; }       // buffer full: the round is abandoned below
                     const int x = (int)((kq & CB_KEY) >> 13), y = (int)(kq & 0x1fffu);
                     SK[s] = kq | CB_FLAG;
                     fl_ab[pos] = (uint32_t)((x << 16) | y); fl_old[pos] = W[(int64_t)x * n + y];
                     atomicOr(&nodefl[x >> 5], 1u << (x & 31)); atomicOr(&nodefl[y >> 5], 1u << (y & 31));
                 }
                 __syncthreads();
-                const int nflag = min(scal[4], CB_FLCAP);
+                if (scal[4] > CB_FLCAP) {
+                    // more eligible edges than the buffer holds: a partial round is not exact (a positive edge could become the
+                    // maximum between two parts), so nothing is forbidden here and one sequential step is taken instead
+                    for (int s = tid; s < E; s += NT) if (SK[s] & CB_FLAG) SK[s] &= ~CB_FLAG;
+                    for (int x = tid; x < words; x += NT) nodefl[x] = 0;
+                    __syncthreads();
+                    if (tid == 0) scal[4] = 0;
+                    force_single = true;
+                    __syncthreads();
+                    continue;
+                }
+                const int nflag = scal[4];
                 // zero the growth rows of the end nodes, then add the growth through every forbidden edge
                 for (int xw = 0; xw < words; xw++)
                     for (uint32_t bits = nodefl[xw]; bits; bits &= bits - 1) {
@@ -309,7 +322,7 @@ __global__ void __launch_bounds__(CB_THREADS) k_cluster_big(DB d, const int32_t*
                     }
                     mine.consider(kq, SF[s], p);
                 }
-                const CBBest v = cb_reduce(mine, red, tid);
+                const CBBest v = cb_reduce<NW>(mine, red, tid);
                 const bool ok = nflag == 1 || v.maxPpos < 0 || v.M < 0 || v.maxPpos <= v.M;
                 if (ok) so = v;
                 else {

@@ -377,7 +377,7 @@ struct Pipeline {
         d.ln = cx->d_ln; d.ln1 = cx->d_ln1;
         h_status = cx->pin.get<int32_t>(C); h_nfinal = cx->pin.get<int32_t>(C); h_npos = cx->pin.get<int32_t>(C);
         h_cells = cx->pin.get<unsigned long long>(C);
-        sg_cap = (size_t)(C + 2) * (8 * 5 + 4 * 3 + 1) + 512;
+        sg_cap = (size_t)(C + 2) * (8 * 6 + 4 * 3 + 1) + 512;
         sg_h = (char*)cx->pin.alloc(sg_cap); sg_d = (char*)cx->dev.alloc(sg_cap);
     }
 
@@ -478,9 +478,10 @@ struct Pipeline {
         if (in->ploidy > 4) S_max = cn_count(in->ploidy, in->ploidy + 2);      // canonical tuples over p + 2 clusters (rule R3c)
         d.S_max = (int32_t)S_max;
         Stage sg; sg.h = sg_h; sg.dv = sg_d;
-        int64_t *dv_frow, *dv_pos, *dv_code, *dv_cw, *dv_back; int32_t *dv_words, *dv_order, *dv_status; uint8_t* dv_small;
+        int64_t *dv_frow, *dv_pos, *dv_code, *dv_cw, *dv_back, *dv_cf; int32_t *dv_words, *dv_order, *dv_status; uint8_t* dv_small;
         int64_t* s_frow = sg.take<int64_t>(C + 1, &dv_frow); int64_t* s_pos = sg.take<int64_t>(C + 1, &dv_pos);
         int64_t* s_code = sg.take<int64_t>(C, &dv_code); int64_t* s_cw = sg.take<int64_t>(C, &dv_cw); int64_t* s_back = sg.take<int64_t>(C, &dv_back);
+        int64_t* s_cf = sg.take<int64_t>(C, &dv_cf); int64_t n_cf = 0;
         int32_t* s_words = sg.take<int32_t>(C, &dv_words); int32_t* s_order = sg.take<int32_t>(C, &dv_order); int32_t* s_status = sg.take<int32_t>(C, &dv_status);
         uint8_t* s_small = sg.take<uint8_t>(C, &dv_small);
         if (sg.used > sg_cap) throw std::runtime_error("staging block overflow");
@@ -488,8 +489,10 @@ struct Pipeline {
         bool status_changed = false;
         s_frow[0] = 0; s_pos[0] = 0;
         int64_t nf_big = 0, cells_ok = 0; int n_max = 0;
-        const bool dense_big = getenv("AHS_CLUSTER_BIG") != nullptr;          // the dense predecessor of k_cluster_sparse, for comparison
-        int max_reads = dense_big ? MAX_READS_CLUSTER_DENSE : MAX_READS_CLUSTER;
+        // chains above CC_MAXN reads: dense workspaces (k_cluster_big) up to dense_max reads, edge slots + lists (k_cluster_sparse) above
+        const int dense_max = getenv("AHS_CLUSTER_BIG") ? MAX_READS_CLUSTER_DENSE : getenv("AHS_CLUSTER_SPARSE") ? CC_MAXN : SP_SMALL_N;      // env: comparison runs
+        int max_reads = MAX_READS_CLUSTER;
+        int64_t nf_dense = 0, nf_sparse = 0;
         if (const char* e = getenv("AHS_MAX_READS_CLUSTER")) max_reads = std::max(CC_MAXN, std::min(max_reads, atoi(e)));      // tests: exercise the limit cheaply
         int64_t big_w_bytes = 0;
         for (int64_t c = 0; c < C; c++) {
@@ -509,6 +512,8 @@ struct Pipeline {
             s_code[c] = n_code_words; n_code_words += n * s_words[c];
             s_small[c] = (n > 0 && n <= CC_MAXN) ? 1 : 0;
             s_cw[c] = n_cw; n_cw += s_small[c] ? n * (n - 1) / 2 : n * n;
+            s_cf[c] = n_cf;
+            if (n > CC_MAXN && n <= dense_max) { n_cf += n * n; nf_dense += n; } else if (n > dense_max) nf_sparse += n;
             s_back[c] = s_pos[c] * S_max;
             if (!s_small[c]) nf_big += n;
             n_max = std::max<int>(n_max, (int)n);
@@ -530,7 +535,7 @@ struct Pipeline {
         d.NF = NF; d.NP = NP;
         CK(cudaMemcpyAsync(sg.dv, sg.h, sg.used, cudaMemcpyHostToDevice, st));
         d.frow_off = dv_frow; d.pos_off = dv_pos; d.code_off = dv_code; d.cw_off = dv_cw; d.back_off = dv_back;
-        d.ch_words = dv_words; d.ch_small = dv_small;
+        d.ch_words = dv_words; d.ch_small = dv_small; d.cf_off = dv_cf;
         if (status_changed) CK(cudaMemcpyAsync(d.ch_status, dv_status, C * 4, cudaMemcpyDeviceToDevice, st));
         d.fr_chain = dalloc<int32_t>(NF); d.fr_first = dalloc<int32_t>(NF); d.fr_last = dalloc<int32_t>(NF); d.fr_mapq = dalloc<int32_t>(NF);
         d.fr_id = dalloc<int32_t>(NF); d.fr_nv = dalloc<int32_t>(NF); d.fr_cluster = dzero<int32_t>(NF);
@@ -542,8 +547,8 @@ struct Pipeline {
             // HBM-resident path (chains above CC_MAXN reads): dense n x n workspaces
             for (int64_t c = 0; c < C; c++) if (!s_small[c] && h_nfinal[c] > 0)
                 CK(cudaMemsetAsync(d.W + s_cw[c], 0, (size_t)h_nfinal[c] * h_nfinal[c] * 4, st));
-            if (dense_big) {
-                d.F = dalloc<int64_t>(n_cw); d.P = dalloc<int64_t>(n_cw); d.big_key = dalloc<uint32_t>(n_cw);
+            if (nf_dense) {
+                d.F = dalloc<int64_t>(n_cf); d.P = dalloc<int64_t>(n_cf); d.big_key = dalloc<uint32_t>(n_cf);
                 d.ce_list = dalloc<int32_t>(NF); d.ce_newrow = dalloc<int32_t>(NF);
                 d.ce_label = dalloc<int32_t>(NF); d.ce_rbF = dalloc<int64_t>(NF); d.ce_rbP = dalloc<int64_t>(NF); d.ce_rbFarg = dalloc<int32_t>(NF); d.ce_rbParg = dalloc<int32_t>(NF);
             }
@@ -582,13 +587,13 @@ struct Pipeline {
         // chains above CC_MAXN reads: edge slots, lists and the maximum tree of k_cluster_sparse.  Their sizes follow from the
         // number of scored pairs per chain, known after k_read_rates: sync #2 (only when such chains exist).
         SpArrays sp{}; int sp_nmax = 0, sp_max_leaf = 0, sp_n_large = 0, sp_nmax_small = 0, sp_leaf_small = 0; unsigned sp_grid = 0;
-        if (nf_big && !dense_big) {
+        if (nf_sparse) {
             unsigned long long* h_pairs2 = cx->pin.get<unsigned long long>(C);
             CK(cudaMemcpyAsync(h_pairs2, d.ch_pairs2, C * 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             std::vector<SpChain> chs;
             int64_t slots = 0, pool = 0, nodes = 0, leaves = 0, sups = 0;
-            int firstb, lenb; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, firstb, lenb);
+            int firstb, lenb; range_of(dense_max + 1, MAX_READS_CLUSTER, firstb, lenb);
             for (int k = 0; k < lenb; k++) {
                 const int c = s_order[firstb + k];
                 SpChain ch{};
@@ -654,12 +659,14 @@ struct Pipeline {
         }
         // ---- cluster editing of the chains above CC_MAXN reads, on two of the side streams (next to the shared-memory classes)
         if (nf_big) {
-            int first, len; range_of(CC_MAXN + 1, MAX_READS_CLUSTER, first, len);
-            if (len && dense_big) {
-                const int nbig = std::min<int>(n_max, 8191);
-                k_cluster_big<<<(unsigned)std::min<int64_t>(len, sms), CB_THREADS, cb_smem_bytes(nbig), cx->side[7]>>>(d, dv_order + first, len, nbig, counters + 2);
+            int first, len; range_of(CC_MAXN + 1, dense_max, first, len);
+            if (len) {
+                const size_t sm_big = cb_smem_bytes(std::min<int>(n_max, dense_max));
+                const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm_big + 1024)));
+                k_cluster_big<<<(unsigned)std::min<int64_t>(len, (int64_t)sms * per_sm), CB_THREADS, sm_big, cx->side[5]>>>(d, dv_order + first, len, std::min<int>(n_max, dense_max), counters + 4);
                 n_launches += 1;
-            } else if (len) {
+            }
+            if (sp.n_chains) {
                 // the few long chains in blocks of 1024 threads, the many short ones (<= 1024 reads) 256 threads each, several per SM:
                 // a greedy step is a chain of dependent memory latencies, which only other chains can hide
                 if (sp_n_large) {

@@ -340,3 +340,26 @@ def test_deletion_allele_matches_every_entry():
                   cat([s.entry_identity[:ne], np.full(len(reads), 0.99, dtype=np.float32), s.entry_identity[ne:]]))
     got = _check(mixed)
     assert list(got.status) == [0, 0, 0]
+
+
+def test_cfg5_chain_of_five_thousand_bubbles_against_the_truth():
+    # BASELINE configs[4] at its shape: ploidy 6, 80x, one chain of 5,000 bubbles (~17,500 final reads, 0.7 M edges) next to
+    # short ones.  The CPU oracle needs hours for such a chain (dense n x n state), so this is a property test at size: every
+    # chain is phased, the reads of the long chain fall into about ploidy clusters, and the emitted haplotypes carry the
+    # generator's true allele multiset at > 99 % of its positions (labels are arbitrary, the multiset is not).
+    b = synth.generate(synth.params(6, 6, 2, 500, 2, 5000, 1.2, 1, depth=80.0, seed=0xA450CA05))
+    r = api.phase_batch(b)
+    p = 6
+    assert (r.status == 0).all()
+    nr = np.diff(r.read_off)
+    c = int(np.argmax(nr))
+    assert int(np.diff(b.bubble_off)[c]) == 5000 and int(nr[c]) > 15000
+    assert 6 <= int(r.n_clusters[c]) <= 16
+    q0, q1 = int(r.pos_off[c]), int(r.pos_off[c + 1])
+    truth = b.truth["hap_allele"].reshape(-1, p)[int(b.bubble_off[c]) + r.pos[q0:q1]]
+    hap = r.hap_allele[q0 * p:q1 * p].reshape(-1, p)
+    same = int((np.sort(truth, axis=1) == np.sort(hap, axis=1)).all(axis=1).sum())
+    assert q1 - q0 > 4900 and same > 0.99 * (q1 - q0)
+    # every read of the chain has a cluster, cluster ids are dense
+    cl = r.read_cluster[int(r.read_off[c]):int(r.read_off[c + 1])]
+    assert set(np.unique(cl).tolist()) == set(range(int(r.n_clusters[c])))

@@ -71,7 +71,7 @@ def main():
     json.dump({"score_dram_bytes_per_pass": int(score_traffic), "source": f"profiles/{tag}_ncu_full_metrics.csv (k_score_chain rows)"},
               open(os.path.join(P, "traffic.json"), "w"))
     with open(os.path.join(P, f"{tag}_summary.md"), "w") as f:
-        f.write(f"# Round 1, snapshot {tag[-1]} — cfg2 (50k chains, 2.0 M bubbles, 45.7 M cells, 56.9 M pairs), one B200\n\n")
+        f.write(f"# Round {tag[1]}, snapshot {tag[-1]} — cfg2 (50k chains, 2.0 M bubbles, 45.7 M cells, 56.9 M pairs), one B200\n\n")
         f.write("Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 1 --warmup 3 "
                 f"--no-cpu-baseline` -> `{tag}_launches_cfg2.csv` (per-launch times are serialised and cold-cache; the SHARES are what to compare).\n"
                 "One warm pass over the batch:\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")

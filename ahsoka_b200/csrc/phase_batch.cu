@@ -42,6 +42,7 @@ struct PassThrough { int rc; std::string msg; };      // failure of one device t
 constexpr int MAX_READS_CLUSTER = 65535;       // 16-bit node ids in the edge keys of k_cluster_sparse (chains above CC_MAXN reads)
 constexpr int MAX_READS_CLUSTER_DENSE = 8191;  // k_cluster_big (AHS_CLUSTER_BIG=1: the dense predecessor, kept for comparison)
 constexpr int MAX_POSITIONS = 32767;
+constexpr int64_t MAX_READS_CHAIN = (int64_t)1 << 20;        // distinct read names per chain (k_read_rank is quadratic in them)
 constexpr int64_t MAX_BIG_W_BYTES = (int64_t)48 << 30;       // dense weight matrices of the chains above CC_MAXN reads, per call and device
 
 // ------------------------------------------------------------------ memory pools (persist per device)
@@ -257,6 +258,7 @@ static Sizes validate(const ahs_batch_in* in, bool is_view = false) {
     for (int64_t c = 0; c < s.C; c++) {
         const int64_t B = in->bubble_off[c + 1] - in->bubble_off[c], R = in->read_off[c + 1] - in->read_off[c];
         if (B > MAX_POSITIONS) throw LimitFail{"chain with more than 32767 bubbles"};
+        if (R > MAX_READS_CHAIN) throw LimitFail{"chain with more than 2^20 distinct read names (the read order is ranked by pairwise counting)"};
         s.M += (B > 1) ? B * R : 0;
     }
     s.max_k = 0;                                     // filled in from the device at sync #1

@@ -272,6 +272,32 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
+    # ---- N > 1: the north-star split, checked once outside the timed regions.  Rank 0 deals ITS batch over all N
+    # devices of the box inside one process (ahs_phase_batch_multi: heavy chains one by one, the tail in ranges of
+    # consecutive chains, LPT; no inter-GPU traffic; every device writes its ranges straight into the output arrays)
+    # and compares every output array with the single-device result; the other ranks idle at the barrier.
+    def multi_leg(single_ms):
+        devs = list(range(world))
+        single = api.phase_batch(batch, device=local)
+        api.phase_batch(batch, devices=devs, copy=False).release()          # contexts + pools of the other devices
+        mt, ms_dev = [], 0.0
+        for _ in range(3):
+            t0 = time.perf_counter(); rm = api.phase_batch(batch, devices=devs, copy=False); mt.append(time.perf_counter() - t0)
+            bad = rm.diff(single)
+            ms_dev = rm.timings["ms_total_device"]
+            rm.release()
+            if bad:
+                raise SystemExit(f"bench.py: multi-device result differs from the single-device result in {bad}")
+        return {"ms_per_call": 1e3 * min(mt), "single_device_ms_same_inputs": single_ms, "speedup": single_ms / (1e3 * min(mt)),
+                "slowest_device_first_to_last_kernel_ms": ms_dev}
+
+    multi = None
+    do_multi = world > 1 and rank == 0 and lib.ahs_device_count() >= world
+    if do_multi:
+        multi = {"devices": world, "equal_to_single_device": True,
+                 "what": "one batch dealt over all devices by ahs_phase_batch_multi inside rank 0 (strong scaling of one call; the other ranks idle)",
+                 "pinned_inputs": multi_leg(e2e_ms)}
+    barrier()
     # ---- the same call with PAGEABLE input arrays, as a one-shot caller (the drop-in CLI) passes them
     api.unpin_batch(batch)
     api.phase_batch(batch, device=local, copy=False).release()
@@ -281,26 +307,8 @@ def main():
         r2.release()
     e2e_pageable_ms = 1e3 * sum(pg_times) / len(pg_times)
     barrier()
-    # ---- N > 1: the north-star split, checked once outside the timed regions.  Rank 0 deals ITS batch over all N
-    # devices of the box inside one process (ahs_phase_batch_multi: heavy chains one by one, the tail in ranges of
-    # consecutive chains, LPT; no inter-GPU traffic; every device writes its ranges straight into the output arrays)
-    # and compares every output array with the single-device result; the other ranks idle at the barrier.
-    multi = None
-    if world > 1 and rank == 0 and lib.ahs_device_count() >= world:
-        devs = list(range(world))
-        single = api.phase_batch(batch, device=local)
-        api.phase_batch(batch, devices=devs, copy=False).release()          # contexts + pools of the other devices
-        mt = []
-        for _ in range(3):
-            t0 = time.perf_counter(); rm = api.phase_batch(batch, devices=devs, copy=False); mt.append(time.perf_counter() - t0)
-            bad = rm.diff(single)
-            ms_dev = rm.timings["ms_total_device"]
-            rm.release()
-            if bad:
-                raise SystemExit(f"bench.py: multi-device result differs from the single-device result in {bad}")
-        multi = {"devices": world, "equal_to_single_device": True, "ms_per_call_pageable_inputs": 1e3 * min(mt),
-                 "single_device_ms_same_inputs": e2e_pageable_ms, "speedup": e2e_pageable_ms / (1e3 * min(mt)),
-                 "slowest_device_kernel_ms": ms_dev, "what": "one batch dealt over all devices by ahs_phase_batch_multi inside rank 0 (strong scaling of one call)"}
+    if do_multi:
+        multi["pageable_inputs"] = multi_leg(e2e_pageable_ms)
     barrier()
 
     cells, chains_ok = res.n_cells, res.n_chains_ok

@@ -291,12 +291,28 @@ def main():
         return {"ms_per_call": 1e3 * min(mt), "single_device_ms_same_inputs": single_ms, "speedup": single_ms / (1e3 * min(mt)),
                 "slowest_device_first_to_last_kernel_ms": ms_dev}
 
+    # While rank 0 uses every GPU, the other ranks must be off theirs: an NCCL barrier spins ON the device (and two processes
+    # time-slice one GPU), so they wait on the rendezvous store instead — a CPU wait.
+    store = None
+    if dist is not None:
+        from torch.distributed.distributed_c10d import _get_default_store
+        store = _get_default_store()
+
+    def others_wait(tag):
+        if store is None:
+            return
+        if rank == 0:
+            store.set(tag, "1")
+        else:
+            store.wait([tag])
+
     multi = None
     do_multi = world > 1 and rank == 0 and lib.ahs_device_count() >= world
     if do_multi:
         multi = {"devices": world, "equal_to_single_device": True,
-                 "what": "one batch dealt over all devices by ahs_phase_batch_multi inside rank 0 (strong scaling of one call; the other ranks idle)",
+                 "what": "one batch dealt over all devices by ahs_phase_batch_multi inside rank 0 (strong scaling of one call; the other ranks wait off the GPU)",
                  "pinned_inputs": multi_leg(e2e_ms)}
+    others_wait("ahs_multi_pinned_done")
     barrier()
     # ---- the same call with PAGEABLE input arrays, as a one-shot caller (the drop-in CLI) passes them
     api.unpin_batch(batch)
@@ -309,6 +325,7 @@ def main():
     barrier()
     if do_multi:
         multi["pageable_inputs"] = multi_leg(e2e_pageable_ms)
+    others_wait("ahs_multi_pageable_done")
     barrier()
 
     cells, chains_ok = res.n_cells, res.n_chains_ok

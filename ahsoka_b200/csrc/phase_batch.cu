@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "device_batch.cuh"
 #include "k_project.cuh"
+#include "k_front.cuh"
 #include "k_score.cuh"
 #include "k_chain.cuh"
 #include "k_cluster_big.cuh"
@@ -215,6 +216,7 @@ static Ctx* get_ctx(int device) {
     CK(cudaMemcpy(c->d_ln1, ln1.data(), 1025 * 8, cudaMemcpyHostToDevice));
     CK(cudaFuncSetAttribute(k_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, 21 * 4096 + 64));
     CK(cudaFuncSetAttribute(k_thread_canon, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_chain_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM_CAP));
     build_canon_tables(c->canon);
     c->smem_optin = prop.sharedMemPerBlockOptin;
     check_classes(c->smem_optin);
@@ -284,6 +286,8 @@ struct Pipeline {
     int64_t cell_base = 0;                                                      // cells of the chunks before this one (cell_off is global)
     static constexpr int N_EN = 6; int64_t en_cut[N_EN + 1] = {0};              // entry ranges whose alignment nodes are uploaded as one slice
     int64_t n_code_words = 0, n_cw = 0, h_tot_cells = 0, h_slots = 0;
+    size_t front_smem = 0; bool use_front = false;                              // one block per chain for projection + rows (k_front.cuh)
+    std::vector<uint32_t> front_need;                                           // per chain: shared memory of its block
     float ms[8] = {0};
     int n_launches = 0;
 
@@ -347,13 +351,22 @@ struct Pipeline {
         d.mrow_off = (int64_t*)up_pinned(h_mrow_off.data(), C);
         // per-chain trigger tables: power of two >= 4 x alleles of the chain (most probes are misses: they end at the first empty slot)
         std::vector<int64_t> hoff(C); std::vector<uint32_t> hmaskc(C);
-        h_slots = 0;
+        h_slots = 0; front_need.assign(C, 0); front_smem = 0;
         for (int64_t c = 0; c < C; c++) {
             const int64_t nal = in->allele_off[in->bubble_off[c + 1]] - in->allele_off[in->bubble_off[c]];
             if (nal < 0 || nal > sz.NA) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
             int64_t cap = 4; while (cap < 4 * nal) cap <<= 1;
             hoff[c] = h_slots; hmaskc[c] = (uint32_t)(cap - 1); h_slots += cap;
+            const int64_t B = in->bubble_off[c + 1] - in->bubble_off[c], R = in->read_off[c + 1] - in->read_off[c], NEc = in->entry_off[c + 1] - in->entry_off[c];
+            const int64_t e_lo = in->entry_off[c], e_hi = in->entry_off[c + 1];
+            if (e_lo < 0 || e_hi < e_lo || e_hi > sz.NE) throw ArgFail{"entry_off out of range"};
+            const int64_t NENc = in->enode_off[e_hi] - in->enode_off[e_lo];
+            if (B > 1) {
+                if (NENc < 0 || NENc > sz.NEN || R * B > ((int64_t)1 << 24) || cap > (1 << 20)) front_smem = SIZE_MAX / 2;
+                else { front_need[c] = fr_layout((int)B, (int)R, (int)nal, (int)NEc, (int)NENc, (int)cap).total; front_smem = std::max(front_smem, (size_t)front_need[c]); }
+            }
         }
+        use_front = front_smem <= FR_SMEM_CAP && getenv("AHS_NO_FRONT") == nullptr;
         d.hoff = up_pinned(hoff.data(), C); d.hmaskc = up_pinned(hmaskc.data(), C);
         (void)st;
     }
@@ -417,34 +430,59 @@ struct Pipeline {
         init_phase1();
         int32_t* d_maxk = dzero<int32_t>(1);
         k_validate<<<grid_for(std::max(sz.NE, std::max(sz.NA, sz.NB)), TB, sms), TB, 0, st>>>(d, d_maxk); n_launches += 1;
-        // ---- owner maps + trigger table
-        if (sz.NB) k_owner<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d.bubble_off, (int)C, sz.NB, d.bubble_chain); n_launches += 1;
-        if (sz.NA) k_owner<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d.allele_off, (int)sz.NB, sz.NA, d.allele_bubble); n_launches += 1;
-        if (sz.NE) k_owner<<<grid_for(sz.NE, TB, sms), TB, 0, st>>>(d.entry_off, (int)C, sz.NE, d.entry_chain); n_launches += 1;
-        if (sz.NR) k_owner<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d.read_off, (int)C, sz.NR, d.read_chain); n_launches += 1;
-        k_validate_owned<<<grid_for(std::max(sz.NE, sz.NB), TB, sms), TB, 0, st>>>(d); n_launches += 1;
-        if (sz.NB) k_rank_a<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1;
-        if (sz.NB && d.stage_a_order) { k_validate_perm<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1; }
-        if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d); n_launches += 1;
-        // ---- projection
-        for (int i = 0; i < N_EN; i++) {
-            CK(cudaStreamWaitEvent(st, ln->ev_en[i], 0));
-            const int64_t ne = en_cut[i + 1] - en_cut[i];
-            if (ne > 0) {
-                if (sz.NEN <= 48 * sz.NE) k_project<16><<<grid_for(ne, 16, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]);      // short alignments
-                else k_project<32><<<grid_for(ne, 8, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]);
-                n_launches += 1;
+        if (use_front) {
+            // every chain's working set fits a block's shared memory: projection, stage A / B, filter and read order in ONE
+            // kernel, one block per chain (k_front.cuh); the chain's alignment nodes arrive by a bulk asynchronous copy
+            for (int i = 0; i < N_EN; i++) CK(cudaStreamWaitEvent(st, ln->ev_en[i], 0));
+            // ranges of chains by shared-memory need (more resident blocks for the many small chains): cut where the largest need of
+            // the remaining chains falls below a threshold
+            std::vector<uint32_t> sufmax(C + 1, 0);
+            for (int64_t c = C - 1; c >= 0; c--) sufmax[c] = std::max(sufmax[c + 1], front_need[c]);
+            int32_t* fcount = dzero<int32_t>(4);
+            int64_t c_begin = 0; int seg = 0;
+            for (uint32_t thr : {54u << 10, 26u << 10, 12u << 10, 0u}) {
+                int64_t c_end = C;
+                if (thr) { c_end = c_begin; while (c_end < C && sufmax[c_end] > thr) c_end++; }       // first chain from which everything fits `thr`
+                if (c_end > c_begin) {
+                    const size_t smem = std::max<size_t>(sufmax[c_begin], 1024);
+                    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+                    k_chain_front<<<(unsigned)std::min<int64_t>(c_end - c_begin, (int64_t)sms * per_sm), FR_THREADS, smem, st>>>(d, (int)c_begin, (int)c_end, fcount + seg);
+                    n_launches += 1;
+                }
+                c_begin = c_end; seg++;
+                if (c_begin >= C) break;
             }
+            CK(cudaEventRecord(ln->ev[1], st));
+        } else {
+            // ---- owner maps + trigger table
+            if (sz.NB) k_owner<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d.bubble_off, (int)C, sz.NB, d.bubble_chain); n_launches += 1;
+            if (sz.NA) k_owner<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d.allele_off, (int)sz.NB, sz.NA, d.allele_bubble); n_launches += 1;
+            if (sz.NE) k_owner<<<grid_for(sz.NE, TB, sms), TB, 0, st>>>(d.entry_off, (int)C, sz.NE, d.entry_chain); n_launches += 1;
+            if (sz.NR) k_owner<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d.read_off, (int)C, sz.NR, d.read_chain); n_launches += 1;
+            k_validate_owned<<<grid_for(std::max(sz.NE, sz.NB), TB, sms), TB, 0, st>>>(d); n_launches += 1;
+            if (sz.NB) k_rank_a<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+            if (sz.NB && d.stage_a_order) { k_validate_perm<<<grid_for(sz.NB, TB, sms), TB, 0, st>>>(d); n_launches += 1; }
+            if (sz.NA) k_build_triggers<<<grid_for(sz.NA, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+            // ---- projection
+            for (int i = 0; i < N_EN; i++) {
+                CK(cudaStreamWaitEvent(st, ln->ev_en[i], 0));
+                const int64_t ne = en_cut[i + 1] - en_cut[i];
+                if (ne > 0) {
+                    if (sz.NEN <= 48 * sz.NE) k_project<16><<<grid_for(ne, 16, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]);      // short alignments
+                    else k_project<32><<<grid_for(ne, 8, sms), TB, 0, st>>>(d, en_cut[i], en_cut[i + 1]);
+                    n_launches += 1;
+                }
+            }
+            CK(cudaEventRecord(ln->ev[1], st));
+            const bool small_rows = sz.NB <= 96 * C;        // short chains: 8 lanes per read, 4 reads in flight per warp
+            if (sz.NR) { if (small_rows) k_read_stage_a<8><<<grid_for(sz.NR, 32, sms), TB, 0, st>>>(d); else k_read_stage_a<32><<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
+            if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+            k_chain_T<<<grid_for(C, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+            if (sz.NR) { if (small_rows) k_read_rows<8><<<grid_for(sz.NR, 32, sms), TB, 0, st>>>(d); else k_read_rows<32><<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
+            if (sz.NR) k_read_rank<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
+            k_chain_sort<<<grid_for(C, 64, sms), 64, 0, st>>>(d); n_launches += 1;
+            k_count_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         }
-        CK(cudaEventRecord(ln->ev[1], st));
-        const bool small_rows = sz.NB <= 96 * C;        // short chains: 8 lanes per read, 4 reads in flight per warp
-        if (sz.NR) { if (small_rows) k_read_stage_a<8><<<grid_for(sz.NR, 32, sms), TB, 0, st>>>(d); else k_read_stage_a<32><<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
-        if (sz.NR) k_chain_flags<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
-        k_chain_T<<<grid_for(C, TB, sms), TB, 0, st>>>(d); n_launches += 1;
-        if (sz.NR) { if (small_rows) k_read_rows<8><<<grid_for(sz.NR, 32, sms), TB, 0, st>>>(d); else k_read_rows<32><<<grid_for(sz.NR, 8, sms), TB, 0, st>>>(d); n_launches += 1; }
-        if (sz.NR) k_read_rank<<<grid_for(sz.NR, TB, sms), TB, 0, st>>>(d); n_launches += 1;
-        k_chain_sort<<<grid_for(C, 64, sms), 64, 0, st>>>(d); n_launches += 1;
-        k_count_pos<<<grid_for(C, 8, sms), TB, 0, st>>>(d); n_launches += 1;
         CK(cudaGetLastError());
         // ---- sync #1: per-chain sizes -> offsets of the per-chain workspaces
         int32_t h_err = 0;
@@ -1117,11 +1155,14 @@ int ahs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
 const char* ahs_last_error(void) { return g_err; }
 
 double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_nodes, int ploidy) {
-    // projection ~ entry nodes; scoring ~ reads x depth; cluster editing ~ reads^2 (dense workspace);
-    // threading ~ positions x states x ploidy x k
-    const double reads = (double)n_entries, depth = n_bubbles > 0 ? (double)n_entry_nodes / (2.0 * n_bubbles) : 0.0;
-    double S = 1; for (int i = 0; i < ploidy; i++) S *= ploidy + 1;
-    return (double)n_entry_nodes + 4.0 * reads * depth + 0.05 * reads * reads + (double)n_bubbles * S * ploidy;
+    // Milliseconds of one SM-resident block, calibrated on B200: projection / rows / scoring stream the
+    // alignment nodes; cluster editing dominates and is cubic in the final reads (~0.7 x the entries) while a merge is adjacent
+    // to most of the chain, linear in them (x neighbourhood size) on long chains; the threading DP is per position x states.
+    const double nf = 0.7 * (double)n_entries;
+    const double nn = nf < 400.0 ? nf : 400.0;
+    double S = 1; for (int i = 0; i < ploidy && i < 4; i++) S *= 2 * ploidy;
+    if (ploidy > 4) S = 1716;
+    return 7e-8 * (double)n_entry_nodes + 4e-6 * nn * nn * nf + 2e-7 * (double)n_bubbles * S;
 }
 
 int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int device) {

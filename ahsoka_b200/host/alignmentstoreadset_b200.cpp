@@ -321,10 +321,13 @@ static void phase_and_emit(FlatBatch& fb, int ploidy, Graph& graph, ChainAlleles
     if (const char* dump = getenv("AHSOKA_DUMP_BATCH")) dump_batch(fb, ploidy, dump);
     ahs_batch_out out;
     const char* dv = getenv("AHSOKA_DEVICE");
+    std::vector<int> devices;                                 // AHSOKA_DEVICES=0,1,...: the chains are dealt over these GPUs
+    if (const char* dl = getenv("AHSOKA_DEVICES")) for (const char* q = dl; *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
     int rc;
     {
         StageTimer t("phase_batch");
-        rc = ahs_phase_batch(&fb.view, &out, dv ? atoi(dv) : 0);
+        if (devices.size() > 1) rc = ahs_phase_batch_multi(&fb.view, &out, devices.data(), (int)devices.size());
+        else rc = ahs_phase_batch(&fb.view, &out, !devices.empty() ? devices[0] : dv ? atoi(dv) : 0);
     }
     if (rc != AHS_OK) {
         std::cerr << "ahsoka_b200: phasing failed (" << rc << "): " << ahs_last_error() << std::endl;

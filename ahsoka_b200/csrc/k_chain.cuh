@@ -457,15 +457,20 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
             }
         }
         CCBest so = cc_reduce<NT>(mine, red, tid, phase);
-        bool force_single = false;
+        bool force_single = false, repacked = false;        // repacked: this warp's slots changed lanes since `mine` was taken
         int wk = PER;                                       // slot indices below wk may be live in this warp
         while (so.M >= 0) {
+            // a thread's own maxima of the last pass tell whether it can hold the block's best pair: only those threads look for
+            // the tie key (after a rolled-back round `mine` is stale: then every thread looks)
+            const bool may_F = force_single || repacked || mine.M == so.M, may_P = force_single || repacked || mine.maxP == so.maxP;
+            repacked = false;
             mine.clear();
             if (so.M >= so.maxP) {
                 // ------------------------------------------------ merge (a,b) into a: the pair with the largest icf
                 int kmine = 0xffff;
+                if (may_F)
 #pragma unroll
-                for (int k = 0; k < PER; k++) if (k < wk && !(key[k] & CC_GONE) && F[k] == so.M) kmine = min(kmine, (int)(key[k] & 0xffffu));
+                    for (int k = 0; k < PER; k++) if (k < wk && !(key[k] & CC_GONE) && F[k] == so.M) kmine = min(kmine, (int)(key[k] & 0xffffu));
                 const int kF = cc_min_key(kmine, scal + 4, tid, kphase);
                 const int a = kF >> 8, b = kF & 0xff;
                 for (int t = tid; t < n; t += NT) {
@@ -550,13 +555,15 @@ __global__ void __launch_bounds__(NT, cc_min_blocks(NT, PER)) k_cluster_chain(DB
                         else key[k] = CC_DEAD;
                     }
                     wk = (base + 31) >> 5;
+                    repacked = true;
                     __syncwarp();
                 }
             } else if (force_single || so.maxPpos > so.M) {
                 // ------------------------------------------------ one sequential forbid: the edge with the largest icp
                 int kmine = 0xffff;
+                if (may_P)
 #pragma unroll
-                for (int k = 0; k < PER; k++) if (k < wk && !(key[k] & CC_GONE) && P[k] == so.maxP) kmine = min(kmine, (int)(key[k] & 0xffffu));
+                    for (int k = 0; k < PER; k++) if (k < wk && !(key[k] & CC_GONE) && P[k] == so.maxP) kmine = min(kmine, (int)(key[k] & 0xffffu));
                 const int kP = cc_min_key(kmine, scal + 4, tid, kphase);
                 const int a = kP >> 8, b = kP & 0xff;
                 const int old = W[a * ns + b];                  // set to forbidden after the step's last barrier

@@ -51,7 +51,7 @@ __device__ __forceinline__ bool fr_entry_has(const int32_t* nodes, int L, int32_
 
 // scal[]: 0 maxpos 1 flags 2 T 3 nfinal 4 status 5 npos 6,7 cells (u64) 8 work item 9 err
 // chains [c_begin, c_end): one launch per range of chains with a similar shared-memory need (the chains arrive largest first)
-__global__ void __launch_bounds__(FR_THREADS) k_chain_front(DB d, int c_begin, int c_end, int32_t* __restrict__ work_counter) {
+__global__ void __launch_bounds__(FR_THREADS, 5) k_chain_front(DB d, int c_begin, int c_end, int32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char fr_sm[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_item;
@@ -317,10 +317,11 @@ __global__ void __launch_bounds__(FR_THREADS) k_chain_front(DB d, int c_begin, i
             ord[rank] = r; okey[rank] = rd[r].y;
         }
         __syncthreads();
+        // thread 0 replays the sort (serial by nature) while the other warps write the matrix and the per-read results out
         if (tid == 0 && scal[4] == AHS_CHAIN_OK) {
             const int n = scal[3];
             if (n == 0) scal[4] = AHS_CHAIN_EMPTY;                                     // :279-282
-            else { KV a; a.k = okey; a.v = ord; kv_std_sort<false>(a, n); }
+            else if (n > 16) { KV a; a.k = okey; a.v = ord; kv_std_sort<false>(a, n); }      // up to 16 keys: insertion sort of an ascending sequence, the identity (A#22)
         }
         if (tid >= 32 && tid < 64) {
             int np = 0;
@@ -328,19 +329,21 @@ __global__ void __launch_bounds__(FR_THREADS) k_chain_front(DB d, int c_begin, i
             np = warp_sum_i32(np);
             if (lane == 0) scal[5] = np;
         }
-        __syncthreads();
         // ---- S7: results to HBM: the matrix once, as final codes
-        {
+        if (tid >= 32) {
             uint32_t* gmask = (uint32_t*)(d.mask + d.mrow_off[c]);                    // chain bases are 4-byte aligned
             const int words = (R * B + 1) / 2;
-            for (int i = tid; i < words; i += FR_THREADS) gmask[i] = ((uint32_t*)mask)[i];
-            for (int r = tid; r < R; r += FR_THREADS) {
+            for (int i = tid - 32; i < words; i += FR_THREADS - 32) gmask[i] = ((uint32_t*)mask)[i];
+            for (int r = tid - 32; r < R; r += FR_THREADS - 32) {
                 const int4 q = rd[r];
                 d.rd_nv[r0g + r] = q.x; d.rd_first[r0g + r] = q.y; d.rd_last[r0g + r] = q.z; d.rd_mapq[r0g + r] = q.w; d.rd_pass[r0g + r] = pass[r];
             }
+            for (int b = tid - 32; b < B; b += FR_THREADS - 32) d.poscov[b0g + b] = poscov[b];
+        }
+        __syncthreads();
+        {
             const int n = scal[3];
             for (int i = tid; i < n; i += FR_THREADS) { d.ord[r0g + i] = ord[i]; d.okey[r0g + i] = okey[i]; }
-            for (int b = tid; b < B; b += FR_THREADS) d.poscov[b0g + b] = poscov[b];
             if (tid == 0) {
                 d.ch_status[c] = scal[4]; d.ch_maxpos[c] = scal[0]; d.ch_flags[c] = scal[1]; d.ch_T[c] = scal[2];
                 d.ch_nfinal[c] = n; d.ch_npos[c] = scal[5];

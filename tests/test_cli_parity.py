@@ -157,3 +157,24 @@ def test_b200_cli_readset_final_dumps_match_reference_verbatim(case):
         pytest.skip("binaries not built (need /root/reference at build time)")
     want = _readset_dumps(ref, case)
     assert want and _readset_dumps(B200_CLI, case) == want
+
+
+@pytest.mark.gpu
+def test_b200_cli_exit_code_tells_when_a_chain_exceeds_a_build_limit():
+    # a chain beyond a build limit is reported on stderr, gets header-only output — and the process exits with code 3, so that
+    # a dropped chain cannot be mistaken for an empty one (the limit is lowered through the library's testing knob)
+    if not os.path.exists(B200_CLI):
+        pytest.skip("ahsoka_b200/bin/Ahsoka_b200 not built (needs /root/reference at build time)")
+    import sys
+    sys.path.insert(0, ROOT)
+    from ahsoka_b200 import synth
+    with tempfile.TemporaryDirectory() as td:
+        synth.generate(synth.params(2, 3, 0, 60, depth=80.0, seed=7), os.path.join(td, "s"))
+        cmd = [B200_CLI, "phase", "-g", "s.gfa", "-a", "s.gaf", "-o", "out", "-t", "1"]
+        ok = subprocess.run(cmd, cwd=td, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert ok.returncode == 0 and "haplotype 0:" in open(os.path.join(td, "out-result.txt")).read()
+        os.remove(os.path.join(td, "out-result.txt"))
+        env = dict(os.environ, AHS_MAX_READS_CLUSTER="180")
+        r = subprocess.run(cmd, cwd=td, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+        assert r.returncode == 3 and "NOT phased" in r.stderr
+        assert "haplotype 0:" not in open(os.path.join(td, "out-result.txt")).read()

@@ -10,3 +10,4 @@ extern "C" int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int) 
 extern "C" void ahs_free_out(ahs_batch_out* o) { ahs_oracle_free_out(o); }
 extern "C" int ahs_warmup(int, uint64_t, uint64_t) { return 0; }
 extern "C" const char* ahs_last_error(void) { return "oracle backend"; }
+extern "C" int ahs_phase_batch_multi(const ahs_batch_in* in, ahs_batch_out* out, const int*, int) { return ahs_oracle_phase_batch(in, out, 1); }

@@ -1213,7 +1213,7 @@ int ahs_warmup(int device, uint64_t device_bytes, uint64_t pinned_bytes) {
 
 int ahs_pin_host(const void* ptr, uint64_t bytes) {
     if (!ptr || !bytes) return AHS_OK;
-    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
     if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) { set_err("ahs_pin_host: %s", cudaGetErrorString(e)); cudaGetLastError(); return AHS_ERR_CUDA; }
     cudaGetLastError();
     return AHS_OK;

@@ -883,6 +883,8 @@ struct DeviceJob {
         CK(cudaSetDevice(device));
         CK(cudaEventRecord(e0, cx->lanes[0].stream));
         bool first = true;
+        // all uploads are enqueued first (the copy engine streams range after range without waiting for the host), then phase 1 /
+        // sync #1 / phase 2 of every range in turn: range k+1 uploads and projects under the clustering of range k
         for (int k = 0; k < n; k++) {
             Pipeline& pl = pls[k];
             pl.cx = cx; pl.ln = &cx->lanes[k % N_LANES]; pl.early_out = iters == 0;
@@ -893,6 +895,10 @@ struct DeviceJob {
             pl.upload();
             if (first) { CK(cudaEventRecord(e1, pl.ln->stream)); tr.mark("upload_enqueue"); first = false; }
             pl.alloc_phase1();
+        }
+        for (int k = 0; k < n; k++) {
+            Pipeline& pl = pls[k];
+            if (pl.sz.C == 0) continue;
             // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
             std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
             const int total = iters > 0 ? warmup + iters : 1;
@@ -1015,7 +1021,7 @@ static std::vector<std::vector<Range>> plan_devices(const ahs_batch_in* in, cons
         if (cost[c] >= grain) { items.push_back(Item{c, c + 1, cost[c]}); c++; continue; }
         Item it{c, c, 0.0};
         while (c < C && cost[c] < grain && it.cost + cost[c] <= grain) { it.cost += cost[c]; c++; }
-        if (it.c1 == it.c0 && c < C) { it.cost = cost[c]; c++; }
+        if (c == it.c0) { it.cost = cost[c]; c++; }              // (cannot happen: a chain below the grain always fits an empty block)
         it.c1 = c;
         items.push_back(it);
     }
@@ -1155,14 +1161,18 @@ int ahs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
 const char* ahs_last_error(void) { return g_err; }
 
 double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_nodes, int ploidy) {
-    // Milliseconds of one SM-resident block, calibrated on B200: projection / rows / scoring stream the
-    // alignment nodes; cluster editing dominates and is cubic in the final reads (~0.7 x the entries) while a merge is adjacent
-    // to most of the chain, linear in them (x neighbourhood size) on long chains; the threading DP is per position x states.
+    // SM-milliseconds of one chain, calibrated on B200 from the per-class launch times of cfg2 and the stage times of the other
+    // configurations.  nf = final reads ~ 0.7 x entries.  Projection / rows / scoring / consensus stream
+    // the alignment nodes; cluster editing dominates: ~nf^2 in the shared-memory kernel (its parallel width grows with the
+    // pairs), ~nf^3 in the dense big-chain kernel, ~nf x neighbourhood in the sparse one; the threading DP is per position x states.
     const double nf = 0.7 * (double)n_entries;
-    const double nn = nf < 400.0 ? nf : 400.0;
+    double cluster;
+    if (nf <= 160.0) cluster = 2.9e-5 * nf * nf;
+    else if (nf <= 1024.0) cluster = 9e-7 * nf * nf * nf;
+    else cluster = 9e-7 * 1024.0 * 1024.0 * 1024.0 + 0.3 * (nf - 1024.0);
     double S = 1; for (int i = 0; i < ploidy && i < 4; i++) S *= 2 * ploidy;
     if (ploidy > 4) S = 1716;
-    return 7e-8 * (double)n_entry_nodes + 4e-6 * nn * nn * nf + 2e-7 * (double)n_bubbles * S;
+    return 1e-5 * (double)n_entry_nodes + cluster + 1e-7 * (double)n_bubbles * S;
 }
 
 int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int device) {

@@ -70,7 +70,7 @@ struct Pool {
 // and projecting while chunk k clusters)
 struct Lane {
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev[12], ev_cells = nullptr, ev_en[8], ev_fork = nullptr, ev_join[8];
+    cudaEvent_t ev[12], ev_cells = nullptr, ev_en[8], ev_fork = nullptr, ev_join[8], ev_up = nullptr;
 };
 constexpr int N_LANES = 4;
 
@@ -201,6 +201,7 @@ static Ctx* get_ctx(int device) {
         CK(cudaEventCreateWithFlags(&ln.ev_cells, cudaEventDisableTiming));
         for (auto& e : ln.ev_en) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ln.ev_up, cudaEventDisableTiming));
         for (auto& e : ln.ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     for (auto& t : c->side) CK(cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking));
@@ -306,9 +307,12 @@ struct Pipeline {
     template <class T> T* dzero(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0, std::max<int64_t>(n, 1) * sizeof(T), ln->stream)); return p; }
     template <class T> T* dfill_ff(int64_t n) { T* p = dalloc<T>(n); CK(cudaMemsetAsync(p, 0xff, std::max<int64_t>(n, 1) * sizeof(T), ln->stream)); return p; }
 
-    void upload() {
+    // `after`: lane whose upload must be through first — uploads of successive ranges share the copy engines, and run one
+    // after the other so that the first range is complete (and its projection starts) as early as possible
+    void upload(Lane* after = nullptr) {
         cudaStream_t st = ln->stream;
         const int64_t C = sz.C;
+        if (after && after != ln) { CK(cudaStreamWaitEvent(ln->stream, after->ev_up, 0)); CK(cudaStreamWaitEvent(ln->stream2, after->ev_up, 0)); }
         d.C = (int32_t)C; d.ploidy = in->ploidy; d.bits = 2;      // code width is decided at sync #1 (largest allele count)
         d.NB = sz.NB; d.NA = sz.NA; d.NAN_ = sz.NAN_; d.NR = sz.NR; d.NE = sz.NE; d.NEN = sz.NEN;
         d.bubble_off = up(in->bubble_off, C + 1); d.allele_off = up(in->allele_off, sz.NB + 1); d.anode_off = up(in->anode_off, sz.NA + 1);
@@ -368,7 +372,8 @@ struct Pipeline {
         }
         use_front = front_smem <= FR_SMEM_CAP && getenv("AHS_NO_FRONT") == nullptr;
         d.hoff = up_pinned(hoff.data(), C); d.hmaskc = up_pinned(hmaskc.data(), C);
-        (void)st;
+        CK(cudaStreamWaitEvent(st, ln->ev_en[N_EN - 1], 0));
+        CK(cudaEventRecord(ln->ev_up, st));
     }
 
     // allocate and initialise everything phase 1 writes; called once per run (also per resident iteration)
@@ -882,22 +887,28 @@ struct DeviceJob {
         e0 = cx->lanes[0].ev[8]; e1 = cx->lanes[0].ev[9];
         CK(cudaSetDevice(device));
         CK(cudaEventRecord(e0, cx->lanes[0].stream));
-        bool first = true;
-        // all uploads are enqueued first (the copy engine streams range after range without waiting for the host), then phase 1 /
-        // sync #1 / phase 2 of every range in turn: range k+1 uploads and projects under the clustering of range k
-        for (int k = 0; k < n; k++) {
+        bool first = true; Lane* last_up = nullptr;
+        // range k+1 is uploaded after sync #1 of range k, under its clustering.  AHS_UPLOAD_AHEAD=1 enqueues it before phase 1 of
+        // range k instead: measured slower on one device (47.1 vs 43.2 ms end to end on cfg2: the copy competes with the
+        // HBM-bound projection of range k), so it is an experiment knob only
+        auto prepare = [&](int k) {
             Pipeline& pl = pls[k];
             pl.cx = cx; pl.ln = &cx->lanes[k % N_LANES]; pl.early_out = iters == 0;
             if (n == 1 && ranges[0].c0 == 0 && ranges[0].c1 == in->n_chains) { pl.in = in; pl.sz = validate(in); }
             else { views[k].make(in, ranges[k].c0, ranges[k].c1); pl.in = &views[k].v; pl.sz = validate(pl.in, true); }
             szs[k] = pl.sz;
-            if (pl.sz.C == 0) continue;
-            pl.upload();
+            if (pl.sz.C == 0) return;
+            pl.upload(last_up);
+            last_up = pl.ln;
             if (first) { CK(cudaEventRecord(e1, pl.ln->stream)); tr.mark("upload_enqueue"); first = false; }
             pl.alloc_phase1();
-        }
+        };
+        static const bool ahead = getenv("AHS_UPLOAD_AHEAD") && atoi(getenv("AHS_UPLOAD_AHEAD")) != 0;
+        prepare(0);
         for (int k = 0; k < n; k++) {
             Pipeline& pl = pls[k];
+            if (ahead && k + 1 < n) prepare(k + 1);
+            struct Later { std::function<void()> f; ~Later() { f(); } } later{[&] { if (!ahead && k + 1 < n) prepare(k + 1); }};
             if (pl.sz.C == 0) continue;
             // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
             std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);

@@ -201,7 +201,7 @@ static Ctx* get_ctx(int device) {
         CK(cudaEventCreateWithFlags(&ln.ev_cells, cudaEventDisableTiming));
         for (auto& e : ln.ev_en) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ln.ev_up, cudaEventDisableTiming));
+        CK(cudaEventCreate(&ln.ev_up));
         for (auto& e : ln.ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     for (auto& t : c->side) CK(cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking));
@@ -268,6 +268,10 @@ static Sizes validate(const ahs_batch_in* in, bool is_view = false) {
     return s;
 }
 
+__global__ void k_fetch_host(const int4* __restrict__ src, int4* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 static inline int grid_for(int64_t items, int per_block, int sms) {
     int64_t g = (items + per_block - 1) / per_block;
     int64_t cap = (int64_t)sms * 16;
@@ -279,6 +283,7 @@ struct Pipeline {
     Ctx* cx; Lane* ln; const ahs_batch_in* in; Sizes sz; DB d{};
     std::vector<int64_t> h_mrow_off, h_frow_off, h_pos_off, h_code_off, h_cw_off, h_back_off;
     int32_t *h_status = nullptr, *h_nfinal = nullptr, *h_npos = nullptr;      // pinned: D2H targets of sync #1
+    int64_t* h_sc = nullptr;                                                   // pinned scalars of sync #1: cells, error flags, largest allele count
     unsigned long long* h_cells = nullptr;
     char *sg_h = nullptr, *sg_d = nullptr; size_t sg_cap = 0;                   // pinned / device staging block of phase 2
     float ms_smem_cluster = 0;
@@ -318,9 +323,6 @@ struct Pipeline {
         d.bubble_off = up(in->bubble_off, C + 1); d.allele_off = up(in->allele_off, sz.NB + 1); d.anode_off = up(in->anode_off, sz.NA + 1);
         d.read_off = up(in->read_off, C + 1); d.entry_off = up(in->entry_off, C + 1); d.enode_off = up(in->enode_off, sz.NE + 1);
         base_allele = in->allele_off[0]; base_anode = in->anode_off[0]; base_enode = in->enode_off[0];
-        if (base_allele) k_rebase<<<grid_for(sz.NB + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.allele_off, sz.NB + 1, base_allele);
-        if (base_anode) k_rebase<<<grid_for(sz.NA + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.anode_off, sz.NA + 1, base_anode);
-        if (base_enode) k_rebase<<<grid_for(sz.NE + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.enode_off, sz.NE + 1, base_enode);
         // the alignment nodes are 3/4 of the batch: they go up in N_EN slices on the second stream, and the projection of
         // slice i runs under the upload of slice i+1
         base_enode = in->enode_off[0];
@@ -373,7 +375,11 @@ struct Pipeline {
         use_front = front_smem <= FR_SMEM_CAP && getenv("AHS_NO_FRONT") == nullptr;
         d.hoff = up_pinned(hoff.data(), C); d.hmaskc = up_pinned(hmaskc.data(), C);
         CK(cudaStreamWaitEvent(st, ln->ev_en[N_EN - 1], 0));
-        CK(cudaEventRecord(ln->ev_up, st));
+        CK(cudaEventRecord(ln->ev_up, st));                    // the copies are through: the next range's may start
+        // a view's interior offsets are rebased on the device — after the event, so that a kernel waiting for a free SM never holds up a copy
+        if (base_allele) k_rebase<<<grid_for(sz.NB + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.allele_off, sz.NB + 1, base_allele);
+        if (base_anode) k_rebase<<<grid_for(sz.NA + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.anode_off, sz.NA + 1, base_anode);
+        if (base_enode) k_rebase<<<grid_for(sz.NE + 1, 256, cx->sms), 256, 0, st>>>((int64_t*)d.enode_off, sz.NE + 1, base_enode);
     }
 
     // allocate and initialise everything phase 1 writes; called once per run (also per resident iteration)
@@ -395,7 +401,7 @@ struct Pipeline {
         d.ch_nclusters = dalloc<int32_t>(C); d.ch_cells = dalloc<unsigned long long>(C); d.ch_pairs2 = dalloc<unsigned long long>(C);
         d.tot_cells = dalloc<int64_t>(1); d.tot_pairs = dalloc<int64_t>(1); d.err_flags = dalloc<int32_t>(1);
         d.ln = cx->d_ln; d.ln1 = cx->d_ln1;
-        h_status = cx->pin.get<int32_t>(C); h_nfinal = cx->pin.get<int32_t>(C); h_npos = cx->pin.get<int32_t>(C);
+        h_status = cx->pin.get<int32_t>(C); h_nfinal = cx->pin.get<int32_t>(C); h_npos = cx->pin.get<int32_t>(C); h_sc = cx->pin.get<int64_t>(4);
         h_cells = cx->pin.get<unsigned long long>(C);
         sg_cap = (size_t)(C + 2) * (8 * 6 + 4 * 3 + 1) + 512;
         sg_h = (char*)cx->pin.alloc(sg_cap); sg_d = (char*)cx->dev.alloc(sg_cap);
@@ -426,8 +432,8 @@ struct Pipeline {
         CK(cudaGetLastError());
     }
 
-    // phase 1: validation, projection, final rows per read, read order; ends with sync #1 (per-chain sizes)
-    void run_phase1() {
+    // phase 1: validation, projection, final rows per read, read order — enqueued, with the copies of sync #1 behind it
+    void run_phase1_enqueue() {
         cudaStream_t st = ln->stream; const int sms = cx->sms; const int64_t C = sz.C;
         const int TB = 256;
         n_launches = 0;
@@ -490,16 +496,20 @@ struct Pipeline {
         }
         CK(cudaGetLastError());
         // ---- sync #1: per-chain sizes -> offsets of the per-chain workspaces
-        int32_t h_err = 0;
+        h_sc[0] = 0; h_sc[1] = 0; h_sc[2] = 0;
         CK(cudaMemcpyAsync(h_status, d.ch_status, C * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_nfinal, d.ch_nfinal, C * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_npos, d.ch_npos, C * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h_cells, d.ch_cells, C * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&h_tot_cells, d.tot_cells, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&h_err, d.err_flags, 4, cudaMemcpyDeviceToHost, st));
-        int32_t h_maxk = 0;
-        CK(cudaMemcpyAsync(&h_maxk, d_maxk, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpyAsync(&h_sc[0], d.tot_cells, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_sc[1], d.err_flags, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&h_sc[2], d_maxk, 4, cudaMemcpyDeviceToHost, st));
+    }
+    // sync #1: per-chain sizes on the host
+    void run_phase1_finish() {
+        CK(cudaStreamSynchronize(ln->stream));
+        h_tot_cells = h_sc[0];
+        const int32_t h_err = (int32_t)h_sc[1], h_maxk = (int32_t)h_sc[2];
         if (h_err & 4) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
         if (h_err & 1) throw ArgFail{"empty allele path"};
         if (h_err & 2) throw LimitFail{"a bubble has more than 15 alleles"};
@@ -578,7 +588,9 @@ struct Pipeline {
         h_frow_off.assign(s_frow, s_frow + C + 1); h_pos_off.assign(s_pos, s_pos + C + 1);
         const int64_t NF = s_frow[C], NP = s_pos[C];
         d.NF = NF; d.NP = NP;
-        CK(cudaMemcpyAsync(sg.dv, sg.h, sg.used, cudaMemcpyHostToDevice, st));
+        // the staging block is fetched by a kernel straight from page-locked host memory: a copy-engine transfer would queue behind the
+        // bulk upload of the next range
+        { const int64_t n16 = (int64_t)((sg.used + 15) / 16); k_fetch_host<<<grid_for(n16, 256, sms), 256, 0, st>>>((const int4*)sg.h, (int4*)sg.dv, n16); n_launches += 1; }
         d.frow_off = dv_frow; d.pos_off = dv_pos; d.code_off = dv_code; d.cw_off = dv_cw; d.back_off = dv_back;
         d.ch_words = dv_words; d.ch_small = dv_small; d.cf_off = dv_cf;
         if (status_changed) CK(cudaMemcpyAsync(d.ch_status, dv_status, C * 4, cudaMemcpyDeviceToDevice, st));
@@ -744,7 +756,8 @@ struct Pipeline {
         CK(cudaGetLastError());
     }
 
-    void run() { run_phase1(); if (d.bits == 2) run_bits<2>(); else run_bits<4>(); }
+    void run_phase2() { if (d.bits == 2) run_bits<2>(); else run_bits<4>(); }
+    void run() { run_phase1_enqueue(); run_phase1_finish(); run_phase2(); }
 
     void collect_times() {
         float t;
@@ -818,8 +831,10 @@ struct HostTrace {       // AHS_TRACE=1: wall-clock of the host-side steps of on
 struct Range { int64_t c0, c1; };
 
 struct ChainView {
-    ahs_batch_in v; std::vector<int64_t> bubble_off, read_off, entry_off;
-    void make(const ahs_batch_in* in, int64_t c0, int64_t c1) {
+    // the three rebased offset arrays live in page-locked staging: an async copy from pageable memory would first drain the
+    // stream it is enqueued on (and with it the upload of the range before)
+    ahs_batch_in v; int64_t *bubble_off = nullptr, *read_off = nullptr, *entry_off = nullptr;
+    void make(const ahs_batch_in* in, int64_t c0, int64_t c1, Pool& pin) {
         const int64_t C = in->n_chains, NB = in->bubble_off[C], NE = in->entry_off[C];
         const int64_t n = c1 - c0, b0 = in->bubble_off[c0], e0 = in->entry_off[c0];
         // the interior offsets dereferenced below are checked here; everything else is validated on the device
@@ -828,11 +843,11 @@ struct ChainView {
         const int64_t NAN_ = in->anode_off[NA], an0 = in->anode_off[a0], an1 = in->anode_off[a1];
         const int64_t NEN = in->enode_off[NE], en0 = in->enode_off[e0], en1 = in->enode_off[in->entry_off[c1]];
         if (an0 < 0 || an1 < an0 || an1 > NAN_ || en0 < 0 || en1 < en0 || en1 > NEN) throw ArgFail{"allele_off / anode_off / enode_off not monotone"};
-        bubble_off.resize(n + 1); read_off.resize(n + 1); entry_off.resize(n + 1);
+        bubble_off = pin.get<int64_t>((size_t)n + 1); read_off = pin.get<int64_t>((size_t)n + 1); entry_off = pin.get<int64_t>((size_t)n + 1);
         for (int64_t c = 0; c <= n; c++) { bubble_off[c] = in->bubble_off[c0 + c] - b0; read_off[c] = in->read_off[c0 + c] - in->read_off[c0]; entry_off[c] = in->entry_off[c0 + c] - e0; }
         v = *in;
         v.n_chains = (int32_t)n; v.chain_id = in->chain_id ? in->chain_id + c0 : nullptr;
-        v.bubble_off = bubble_off.data(); v.read_off = read_off.data(); v.entry_off = entry_off.data();
+        v.bubble_off = bubble_off; v.read_off = read_off; v.entry_off = entry_off;
         v.allele_off = in->allele_off + b0; v.anode_off = in->anode_off + a0; v.anode = in->anode + an0;
         v.stage_a_order = in->stage_a_order ? in->stage_a_order + b0 : nullptr;
         v.enode_off = in->enode_off + e0; v.enode = in->enode + en0;
@@ -888,14 +903,14 @@ struct DeviceJob {
         CK(cudaSetDevice(device));
         CK(cudaEventRecord(e0, cx->lanes[0].stream));
         bool first = true; Lane* last_up = nullptr;
-        // range k+1 is uploaded after sync #1 of range k, under its clustering.  AHS_UPLOAD_AHEAD=1 enqueues it before phase 1 of
-        // range k instead: measured slower on one device (47.1 vs 43.2 ms end to end on cfg2: the copy competes with the
-        // HBM-bound projection of range k), so it is an experiment knob only
+        // range k+1 is prepared and its upload enqueued once phase 2 of range k is enqueued: it travels under the clustering of
+        // range k.  AHS_UPLOAD_AHEAD=1 does it one step earlier, under phase 1 of range k (the uploads then follow each other
+        // on the copy engine without gaps); measured 1 ms slower end to end on one device (cfg2: 42.6 vs 41.6 ms), kept as a knob.
         auto prepare = [&](int k) {
             Pipeline& pl = pls[k];
             pl.cx = cx; pl.ln = &cx->lanes[k % N_LANES]; pl.early_out = iters == 0;
             if (n == 1 && ranges[0].c0 == 0 && ranges[0].c1 == in->n_chains) { pl.in = in; pl.sz = validate(in); }
-            else { views[k].make(in, ranges[k].c0, ranges[k].c1); pl.in = &views[k].v; pl.sz = validate(pl.in, true); }
+            else { views[k].make(in, ranges[k].c0, ranges[k].c1, cx->pin); pl.in = &views[k].v; pl.sz = validate(pl.in, true); }
             szs[k] = pl.sz;
             if (pl.sz.C == 0) return;
             pl.upload(last_up);
@@ -903,26 +918,28 @@ struct DeviceJob {
             if (first) { CK(cudaEventRecord(e1, pl.ln->stream)); tr.mark("upload_enqueue"); first = false; }
             pl.alloc_phase1();
         };
-        static const bool ahead = getenv("AHS_UPLOAD_AHEAD") && atoi(getenv("AHS_UPLOAD_AHEAD")) != 0;
+        const bool ahead = getenv("AHS_UPLOAD_AHEAD") && atoi(getenv("AHS_UPLOAD_AHEAD")) != 0;
         prepare(0);
         for (int k = 0; k < n; k++) {
             Pipeline& pl = pls[k];
-            if (ahead && k + 1 < n) prepare(k + 1);
-            struct Later { std::function<void()> f; ~Later() { f(); } } later{[&] { if (!ahead && k + 1 < n) prepare(k + 1); }};
-            if (pl.sz.C == 0) continue;
-            // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
-            std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
-            const int total = iters > 0 ? warmup + iters : 1;
-            for (int it = 0; it < total; it++) {
-                if (iters > 0) for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
-                pl.run();                                     // ends with phase 2 enqueued; sync #1 inside waited for this range's upload only
-                tr.mark("run_enqueue");
-                if (iters > 0) {
+            if (iters > 0) {
+                if (pl.sz.C == 0) continue;
+                // the device pool is bump-allocated: remember the mark so that resident iterations reuse phase-2 space
+                std::vector<size_t> mark; for (auto& c : cx->dev.chunks) mark.push_back(c.used);
+                for (int it = 0; it < warmup + iters; it++) {
+                    for (size_t i = 0; i < cx->dev.chunks.size(); i++) cx->dev.chunks[i].used = i < mark.size() ? mark[i] : 0;
+                    pl.run();
                     CK(cudaStreamSynchronize(pl.ln->stream));
                     pl.collect_times();
                     if (it >= warmup) for (int i = 0; i < 8; i++) acc[i] += pl.ms[i];
                 }
+                if (k + 1 < n) prepare(k + 1);
+                continue;
             }
+            if (pl.sz.C) { pl.run_phase1_enqueue(); tr.mark("phase1_enqueue"); }
+            if (ahead && k + 1 < n) { prepare(k + 1); tr.mark("prepare"); }            // host work and upload of the next range under this range's phase 1
+            if (pl.sz.C) { pl.run_phase1_finish(); tr.mark("sync1"); pl.run_phase2(); tr.mark("phase2_enqueue"); }
+            if (!ahead && k + 1 < n) { prepare(k + 1); tr.mark("prepare"); }
         }
         if (first) CK(cudaEventRecord(e1, cx->lanes[0].stream));
     }
@@ -976,6 +993,13 @@ struct DeviceJob {
             if (firstk < 0) firstk = k; last = k;
         }
         if (firstk >= 0 && n <= N_LANES) { float t = 0; CK(cudaEventElapsedTime(&t, pls[firstk].ln->ev[0], pls[last].ln->ev[7])); ms8[6] = t; }      // first kernel -> last kernel
+        if (getenv("AHS_TRACE") && n <= N_LANES)          // device timeline of the ranges, ms after the call's first event
+            for (int k = 0; k < n; k++) if (szs[k].C) {
+                auto at = [&](cudaEvent_t e) { float t = 0; CK(cudaEventElapsedTime(&t, e0, e)); return t; };
+                Lane* l = pls[k].ln;
+                fprintf(stderr, "[ahs timeline] dev %d range %d chains %lld: uploaded %.2f | phase1 start %.2f front %.2f rows+sync1 %.2f score %.2f cluster %.2f consensus %.2f thread %.2f end %.2f\n",
+                        device, k, (long long)szs[k].C, at(l->ev_up), at(l->ev[0]), at(l->ev[1]), at(l->ev[2]), at(l->ev[3]), at(l->ev[4]), at(l->ev[5]), at(l->ev[6]), at(l->ev[7]));
+            }
     }
 };
 

@@ -48,12 +48,12 @@ class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, all_gpus=False):
+        self.gpu, self.rows, self.proc, self.all_gpus = gpu_index, [], None, all_gpus
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi"] + ([] if self.all_gpus else ["-i", str(self.gpu)]) + ["--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -74,8 +74,17 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
+        by_gpu, pw_gpu = {}, {}
         for r in self.rows:
             try:
+                by_gpu.setdefault(int(r[0]), []).append(float(r[1])); pw_gpu.setdefault(int(r[0]), []).append(float(r[3]))
+            except Exception:
+                pass
+        self.per_gpu = {"sm_mhz": [statistics.median(by_gpu[g]) for g in sorted(by_gpu)], "power_w": [round(statistics.median(pw_gpu[g]), 1) for g in sorted(pw_gpu)]}
+        for r in self.rows:
+            try:
+                if int(r[0]) != self.gpu:
+                    continue
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
@@ -249,7 +258,7 @@ def main():
             import torch
             dist.barrier(); torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, all_gpus=world > 1)
     # ---- device-resident timing: W warm-up passes, K timed passes, CUDA events inside the library
     barrier()
     if rank == 0:
@@ -272,6 +281,17 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
+    ahead_ms = None
+    if os.environ.get("BENCH_AHEAD_LEG"):          # diagnostic: the same loop with the look-ahead upload order of the library
+        os.environ["AHS_UPLOAD_AHEAD"] = "1"
+        api.phase_batch(batch, device=local, copy=False).release()
+        barrier()
+        ta = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter(); api.phase_batch(batch, device=local, copy=False).release(); ta.append(time.perf_counter() - t0)
+        barrier()
+        os.environ["AHS_UPLOAD_AHEAD"] = "0"
+        ahead_ms = 1e3 * sum(ta) / len(ta)
     # ---- N > 1: the north-star split, checked once outside the timed regions.  Rank 0 deals ITS batch over all N
     # devices of the box inside one process (ahs_phase_batch_multi: heavy chains one by one, the tail in ranges of
     # consecutive chains, LPT; no inter-GPU traffic; every device writes its ranges straight into the output arrays)
@@ -330,8 +350,22 @@ def main():
 
     cells, chains_ok = res.n_cells, res.n_chains_ok
     cells_local = cells
+    per_rank = None
     if dist is not None:
         import torch
+        # every rank's own numbers (the line's times are the max over ranks): shows whether a drop in efficiency is one slow rank or all of them
+        mine = torch.tensor([ms_step, e2e_ms, float(cells), t["ms_cluster"], t["ms_project"], 1e3 * min(e2e_times), 1e3 * max(e2e_times), ahead_ms or 0.0],
+                            device=f"cuda:{local}", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        cols = ["ms_per_step", "e2e_ms_per_step", "cells", "ms_cluster", "ms_project", "e2e_ms_min", "e2e_ms_max", "e2e_ms_upload_ahead_leg"]
+        per_rank = {c: [round(float(a[i]), 3) for a in allr] for i, c in enumerate(cols)}
+        if clocks is not None and len(getattr(sampler, "per_gpu", {}).get("sm_mhz", [])) >= world:
+            per_rank["sm_mhz_median_by_gpu"] = sampler.per_gpu["sm_mhz"]; per_rank["power_w_median_by_gpu"] = sampler.per_gpu["power_w"]
+        try:
+            per_rank["cpus_rank0"] = sorted(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            pass
         v = torch.tensor([ms_step, e2e_ms], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(v[0]), float(v[1])
@@ -375,6 +409,8 @@ def main():
             "gpu_launches": int(t["n_launches"]) * args.steps, "roofline": roofline, "clocks": clocks}
     if multi is not None:
         line["multi"] = multi
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_port_baseline(batch)
     _emit(line)

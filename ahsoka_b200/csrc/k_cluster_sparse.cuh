@@ -46,15 +46,21 @@ struct SpBest {                                      // maxima over a set of slo
         if (o.maxPneg > maxPneg) maxPneg = o.maxPneg;
     }
 };
-__device__ __forceinline__ SpBest sp_shfl_xor(const SpBest& b, int o) {
-    SpBest r;
-    r.M = __shfl_xor_sync(0xffffffffu, b.M, o); r.maxP = __shfl_xor_sync(0xffffffffu, b.maxP, o); r.maxPpos = __shfl_xor_sync(0xffffffffu, b.maxPpos, o);
-    r.maxPneg = __shfl_xor_sync(0xffffffffu, b.maxPneg, o); r.kF = __shfl_xor_sync(0xffffffffu, b.kF, o); r.kP = __shfl_xor_sync(0xffffffffu, b.kP, o);
-    return r;
+// warp maxima with redux.sync: a 64-bit signed maximum is the maximum of the high words, then of the (unsigned) low words among the
+// lanes that hold it; a tie key is the smallest key among the lanes that hold the maximum.  ~35 instructions instead of the ~150
+// of a five-level shuffle tree over the six fields.
+__device__ __forceinline__ long long sp_warp_max_i64(long long v) {
+    const int hi = (int)(v >> 32); const unsigned lo = (unsigned)v;
+    const int mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return (long long)(((unsigned long long)(unsigned)mh << 32) | ml);
 }
 __device__ __forceinline__ SpBest sp_warp_reduce(SpBest b) {
-    for (int o = 16; o > 0; o >>= 1) { const SpBest t = sp_shfl_xor(b, o); b.merge(t); }
-    return b;
+    SpBest r;
+    r.M = sp_warp_max_i64(b.M); r.kF = __reduce_min_sync(0xffffffffu, b.M == r.M ? b.kF : SP_NONE);
+    r.maxP = sp_warp_max_i64(b.maxP); r.kP = __reduce_min_sync(0xffffffffu, b.maxP == r.maxP ? b.kP : SP_NONE);
+    r.maxPpos = sp_warp_max_i64(b.maxPpos); r.maxPneg = sp_warp_max_i64(b.maxPneg);
+    return r;
 }
 
 // one big chain: where its state lives (filled by the host, see phase_batch.cu)
@@ -275,30 +281,28 @@ __global__ void __launch_bounds__(NT) k_cluster_sparse(DB d, SpArrays sp, int c_
         // leaves of the changed slots, then their level-2 entries, then the block-wide maxima.  Three barriers.
         auto refresh = [&]() -> SpBest {
             __syncthreads();
-            for (int w = wid; w < w_leaf; w += NW) {
-                uint32_t bits = dleaf[w];
-                if (!bits) continue;
-                for (; bits; bits &= bits - 1) {
+            // dirty leaves come in runs (the slots of neighbouring nodes): bit j of every word goes to warp j % NW, so that a run is
+            // spread over all warps instead of landing on the one warp that owns its word
+            uint32_t mine_bits = 0;
+            for (int j = wid; j < 32; j += NW) mine_bits |= 1u << j;
+            for (int w = 0; w < w_leaf; w++) {
+                for (uint32_t bits = dleaf[w] & mine_bits; bits; bits &= bits - 1) {
                     const int l = w * 32 + __ffs(bits) - 1;
                     const SpBest b = sp_leaf_maxima(sp, ch, l, n_slots, lane);
                     if (lane == 0) { leaf[l] = b; atomicOr(&dsup[l >> 11], 1u << ((l >> 6) & 31)); }
                 }
-                __syncwarp();
-                if (lane == 0) dleaf[w] = 0;
             }
             __syncthreads();
-            for (int w = wid; w < w_sup; w += NW) {
-                uint32_t bits = dsup[w];
-                if (!bits) continue;
-                for (; bits; bits &= bits - 1) {
+            for (int w = tid; w < w_leaf; w += NT) dleaf[w] = 0;
+            for (int w = 0; w < w_sup; w++) {
+                for (uint32_t bits = dsup[w] & mine_bits; bits; bits &= bits - 1) {
                     const int su = w * 32 + __ffs(bits) - 1;
                     const SpBest b = sp_sup_maxima(sp, ch, su, lane);
                     if (lane == 0) sup[su] = b;
                 }
-                __syncwarp();
-                if (lane == 0) dsup[w] = 0;
             }
             __syncthreads();
+            for (int w = tid; w < w_sup; w += NT) dsup[w] = 0;
             SpBest b; b.clear();
             for (int su = tid; su < ch.n_sup; su += NT) b.merge(sup[su]);
             b = sp_warp_reduce(b);
@@ -427,20 +431,18 @@ __global__ void __launch_bounds__(NT) k_cluster_sparse(DB d, SpArrays sp, int c_
                 for (int su = tid; su < ch.n_sup; su += NT) if (sup[su].maxPneg > M) supq[atomicAdd(&scal[3], 1)] = (uint32_t)su;
                 __syncthreads();
                 const int n_q = scal[3];
-                for (int qi = wid; qi < n_q; qi += NW) {
-                    const int su = (int)supq[qi];
-                    for (int l = su * 64; l < min(ch.n_leaf, su * 64 + 64); l++) {
-                        if (leaf[l].maxPneg <= M) continue;              // warp-uniform
+                for (int idx = wid; idx < n_q * 64; idx += NW) {           // (level-2 entry, leaf) pairs dealt over the warps
+                    const int l = (int)supq[idx >> 6] * 64 + (idx & 63);
+                    if (l >= ch.n_leaf || leaf[l].maxPneg <= M) continue;      // warp-uniform
 #pragma unroll
-                        for (int u = 0; u < 2; u++) {
-                            const int s = l * 64 + u * 32 + lane;
-                            if (s >= n_slots) continue;
-                            const uint8_t fl = flag[s];
-                            if ((fl & (SPF_DEAD | SPF_FORB | SPF_POS)) || P[s] <= M) continue;
-                            const int q = atomicAdd(&scal[2], 1);              // never truncated: a partial round would not be exact
-                            flag[s] = fl | SPF_FLAG;
-                            fl_slot[q] = (uint32_t)s; fl_old[q] = W[(int64_t)(key[s] >> 16) * n + (key[s] & 0xffffu)];
-                        }
+                    for (int u = 0; u < 2; u++) {
+                        const int s = l * 64 + u * 32 + lane;
+                        if (s >= n_slots) continue;
+                        const uint8_t fl = flag[s];
+                        if ((fl & (SPF_DEAD | SPF_FORB | SPF_POS)) || P[s] <= M) continue;
+                        const int q = atomicAdd(&scal[2], 1);              // never truncated: a partial round would not be exact
+                        flag[s] = fl | SPF_FLAG;
+                        fl_slot[q] = (uint32_t)s; fl_old[q] = W[(int64_t)(key[s] >> 16) * n + (key[s] & 0xffffu)];
                     }
                 }
                 __syncthreads();

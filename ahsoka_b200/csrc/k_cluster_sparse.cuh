@@ -77,6 +77,7 @@ struct SpArrays {
     int64_t n_nodes, n_slot_cap, n_leaves, n_sups;   // totals over the chains (the chains' ranges are consecutive)
     uint32_t* fl_slot; int32_t* fl_old;              // per slot capacity: the edges flagged in a forbid round (never truncated)
     uint32_t* supq;                                  // per level-2 entry: the entries to visit in a round
+    uint32_t* leafq;                                 // per leaf: the dirty leaves of a refresh
     uint32_t* key; uint8_t* flag; long long *F, *P;  // slots
     uint32_t* pool;                                  // lists
     long long* lptr; uint32_t *llen, *sa, *sb, *up; int32_t *wa, *wb, *nw; long long *frF, *frP;      // per node
@@ -268,12 +269,12 @@ __global__ void __launch_bounds__(NT) k_cluster_sparse(DB d, SpArrays sp, int c_
         int32_t* wa = sp.wa + ch.node_off; int32_t* wb = sp.wb + ch.node_off; int32_t* nw = sp.nw + ch.node_off;
         long long* frF = sp.frF + ch.node_off; long long* frP = sp.frP + ch.node_off;
         SpBest* leaf = sp.leaf + ch.leaf_off; SpBest* sup = sp.sup + ch.sup_off;
-        uint32_t* fl_slot = sp.fl_slot + ch.slot_off; int32_t* fl_old = sp.fl_old + ch.slot_off; uint32_t* supq = sp.supq + ch.sup_off;
+        uint32_t* fl_slot = sp.fl_slot + ch.slot_off; int32_t* fl_old = sp.fl_old + ch.slot_off; uint32_t* supq = sp.supq + ch.sup_off; uint32_t* leafq = sp.leafq + ch.leaf_off;
         for (int x = tid; x < n; x += NT) label[x] = (uint16_t)x;
         for (int x = tid; x < w_ins; x += NT) inS[x] = 0;
         for (int x = tid; x < w_leaf; x += NT) dleaf[x] = 0;
         for (int x = tid; x < w_sup; x += NT) dsup[x] = 0;
-        if (tid == 0) { scal[1] = 0; scal[2] = 0; scal[3] = 0; scal[4] = 0; }
+        if (tid == 0) { scal[1] = 0; scal[2] = 0; scal[3] = 0; scal[4] = 0; scal[6] = 0; }
         int n_active = n;
         bool force_single = false;
         __syncthreads();
@@ -281,19 +282,26 @@ __global__ void __launch_bounds__(NT) k_cluster_sparse(DB d, SpArrays sp, int c_
         // leaves of the changed slots, then their level-2 entries, then the block-wide maxima.  Three barriers.
         auto refresh = [&]() -> SpBest {
             __syncthreads();
-            // dirty leaves come in runs (the slots of neighbouring nodes): bit j of every word goes to warp j % NW, so that a run is
-            // spread over all warps instead of landing on the one warp that owns its word
-            uint32_t mine_bits = 0;
-            for (int j = wid; j < 32; j += NW) mine_bits |= 1u << j;
-            for (int w = 0; w < w_leaf; w++) {
-                for (uint32_t bits = dleaf[w] & mine_bits; bits; bits &= bits - 1) {
-                    const int l = w * 32 + __ffs(bits) - 1;
-                    const SpBest b = sp_leaf_maxima(sp, ch, l, n_slots, lane);
-                    if (lane == 0) { leaf[l] = b; atomicOr(&dsup[l >> 11], 1u << ((l >> 6) & 31)); }
-                }
+            // dirty leaves come in runs (the slots of neighbouring nodes): they are queued first (a thread per 32-leaf word) and
+            // then dealt round-robin over the warps — a run would otherwise land on the one warp that owns its word
+            for (int w = tid; w < w_leaf; w += NT) {
+                uint32_t bits = dleaf[w];
+                if (!bits) continue;
+                int q = atomicAdd(&scal[6], __popc(bits));
+                for (; bits; bits &= bits - 1) leafq[q++] = (uint32_t)(w * 32 + __ffs(bits) - 1);
+                dleaf[w] = 0;
             }
             __syncthreads();
-            for (int w = tid; w < w_leaf; w += NT) dleaf[w] = 0;
+            const int n_lq = scal[6];
+            for (int qi = wid; qi < n_lq; qi += NW) {
+                const int l = (int)leafq[qi];
+                const SpBest b = sp_leaf_maxima(sp, ch, l, n_slots, lane);
+                if (lane == 0) { leaf[l] = b; atomicOr(&dsup[l >> 11], 1u << ((l >> 6) & 31)); }
+            }
+            __syncthreads();
+            if (tid == 0) scal[6] = 0;
+            uint32_t mine_bits = 0;
+            for (int j = wid; j < 32; j += NW) mine_bits |= 1u << j;
             for (int w = 0; w < w_sup; w++) {
                 for (uint32_t bits = dsup[w] & mine_bits; bits; bits &= bits - 1) {
                     const int su = w * 32 + __ffs(bits) - 1;

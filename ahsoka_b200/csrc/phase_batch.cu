@@ -668,7 +668,7 @@ struct Pipeline {
             }
             if (sp_smem_bytes(sp_nmax, sp_max_leaf) > cx->smem_optin) throw LimitFail{"a chain's cluster-editing state exceeds the shared memory of a block"};
             sp.n_chains = (int)chs.size(); sp.n_nodes = nodes; sp.n_slot_cap = slots; sp.n_leaves = leaves; sp.n_sups = sups;
-            sp.fl_slot = dalloc<uint32_t>(slots); sp.fl_old = dalloc<int32_t>(slots); sp.supq = dalloc<uint32_t>(sups);
+            sp.fl_slot = dalloc<uint32_t>(slots); sp.fl_old = dalloc<int32_t>(slots); sp.supq = dalloc<uint32_t>(sups); sp.leafq = dalloc<uint32_t>(leaves);
             sp.chains = up_pinned(chs.data(), (int64_t)chs.size());
             sp.key = dalloc<uint32_t>(slots); sp.flag = dalloc<uint8_t>(slots); sp.F = (long long*)dalloc<int64_t>(slots); sp.P = (long long*)dalloc<int64_t>(slots);
             sp.pool = dalloc<uint32_t>(pool);

@@ -545,7 +545,10 @@ struct Pipeline {
         s_frow[0] = 0; s_pos[0] = 0;
         int64_t nf_big = 0, cells_ok = 0; int n_max = 0;
         // chains above CC_MAXN reads: dense workspaces (k_cluster_big) up to dense_max reads, edge slots + lists (k_cluster_sparse) above
-        const int dense_max = getenv("AHS_CLUSTER_BIG") ? MAX_READS_CLUSTER_DENSE : getenv("AHS_CLUSTER_SPARSE") ? CC_MAXN : SP_SMALL_N;      // env: comparison runs
+        // chains above CC_MAXN reads take k_cluster_sparse (edge slots + lists).  AHS_CLUSTER_BIG=1 (comparison runs): its dense
+        // predecessor k_cluster_big up to 8,191 reads — slower since the sparse kernel balances its warps (cfg4 x 0.5: 599 vs 545 ms)
+        const int dense_max = (getenv("AHS_CLUSTER_BIG") && atoi(getenv("AHS_CLUSTER_BIG"))) ? MAX_READS_CLUSTER_DENSE : CC_MAXN;
+        const int sp_small_n = getenv("AHS_SP_SMALL_N") ? atoi(getenv("AHS_SP_SMALL_N")) : SP_SMALL_N;
         int max_reads = MAX_READS_CLUSTER;
         int64_t nf_dense = 0, nf_sparse = 0;
         if (const char* e = getenv("AHS_MAX_READS_CLUSTER")) max_reads = std::max(CC_MAXN, std::min(max_reads, atoi(e)));      // tests: exercise the limit cheaply
@@ -662,7 +665,7 @@ struct Pipeline {
                 ch.node_off = nodes; ch.leaf_off = leaves; ch.sup_off = sups;
                 slots += e0; pool += ch.list_cap; nodes += ch.n; leaves += ch.n_leaf; sups += ch.n_sup;
                 sp_nmax = std::max(sp_nmax, ch.n); sp_max_leaf = std::max(sp_max_leaf, ch.n_leaf);
-                if (ch.n > SP_SMALL_N) sp_n_large++;                               // the list is sorted by decreasing read count
+                if (ch.n > sp_small_n) sp_n_large++;                               // the list is sorted by decreasing read count
                 else { sp_nmax_small = std::max(sp_nmax_small, ch.n); sp_leaf_small = std::max(sp_leaf_small, ch.n_leaf); }
                 chs.push_back(ch);
             }

@@ -240,7 +240,7 @@ __host__ __device__ inline size_t sp_smem_bytes(int nmax, int max_leaf) {
 
 // chains [c_begin, c_end) of sp.chains (sorted by decreasing read count), one block of NT threads per chain at a time
 template <int NT>
-__global__ void __launch_bounds__(NT) k_cluster_sparse(DB d, SpArrays sp, int c_begin, int c_end, int nmax, int max_leaf, int32_t* __restrict__ work_counter) {
+__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 5) k_cluster_sparse(DB d, SpArrays sp, int c_begin, int c_end, int nmax, int max_leaf, int32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char sp_sm[];
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -355,18 +355,31 @@ __global__ void __launch_bounds__(NT) k_cluster_sparse(DB d, SpArrays sp, int c_
                     const int xa = wa[x], xb = wb[x], xn = nw[x];
                     const long long lp = lptr[x]; const int ll = (int)llen[x];
                     long long f = 0, p = 0;
-                    for (int i = lane; i < ll; i += 32) {
-                        const uint32_t s = pool[lp + i];
-                        const uint8_t fl = flag[s];
-                        if (fl & SPF_DEAD) continue;
-                        const int y = sp_other(key[s], x);
-                        if (y == a || y == b || !((inS[y >> 5] >> (y & 31)) & 1u)) continue;
-                        const int w_xy = W[(int64_t)x * n + y];
-                        const int ya = wa[y], yb = wb[y], yn = nw[y];
-                        f += sp_tf(yn, w_xy); p += sp_tp(yn, w_xy);
-                        if (x < y && !(fl & SPF_FORB)) {
-                            const long long df = sp_tf(xn, yn) - sp_tf(xa, ya) - sp_tf(xb, yb), dp = sp_tp(xn, yn) - sp_tp(xa, ya) - sp_tp(xb, yb);
-                            if (df != 0 || dp != 0) { F[s] += df; P[s] += dp; mark(s); }
+                    // four entries per lane in flight: the loads of a step (slot index -> flag, key -> weights -> costs) are issued for
+                    // all four before the first is used — the walk is a chain of dependent L2 accesses otherwise
+                    constexpr int U = NT >= 1024 ? 4 : 2;      // the 256-thread blocks run five to an SM: registers matter more there
+                    for (int i0 = lane; i0 < ll; i0 += 32 * U) {
+                        uint32_t s[U], ky[U]; uint8_t fl[U]; bool ok[U]; int y[U], w_xy[U], ya[U], yb[U], yn[U];
+#pragma unroll
+                        for (int u = 0; u < U; u++) { ok[u] = i0 + 32 * u < ll; s[u] = ok[u] ? pool[lp + i0 + 32 * u] : 0u; }
+#pragma unroll
+                        for (int u = 0; u < U; u++) { fl[u] = ok[u] ? flag[s[u]] : SPF_DEAD; ky[u] = ok[u] ? key[s[u]] : 0u; }
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            y[u] = sp_other(ky[u], x);
+                            ok[u] = !(fl[u] & SPF_DEAD) && y[u] != a && y[u] != b;
+                            ok[u] = ok[u] && ((inS[y[u] >> 5] >> (y[u] & 31)) & 1u);
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; u++) if (ok[u]) { w_xy[u] = W[(int64_t)x * n + y[u]]; ya[u] = wa[y[u]]; yb[u] = wb[y[u]]; yn[u] = nw[y[u]]; }
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            if (!ok[u]) continue;
+                            f += sp_tf(yn[u], w_xy[u]); p += sp_tp(yn[u], w_xy[u]);
+                            if (x < y[u] && !(fl[u] & SPF_FORB)) {
+                                const long long df = sp_tf(xn, yn[u]) - sp_tf(xa, ya[u]) - sp_tf(xb, yb[u]), dp = sp_tp(xn, yn[u]) - sp_tp(xa, ya[u]) - sp_tp(xb, yb[u]);
+                                if (df != 0 || dp != 0) { F[s[u]] += df; P[s[u]] += dp; mark(s[u]); }
+                            }
                         }
                     }
                     f = warp_sum_i64(f); p = warp_sum_i64(p);

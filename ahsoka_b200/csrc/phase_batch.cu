@@ -1013,6 +1013,15 @@ static std::vector<Range> ranges_single(const ahs_batch_in* in, const Sizes& sz,
     int n_chunks = 1;
     if (iters == 0 && C >= 4096 && sz.NEN >= (int64_t)16 << 20) {
         n_chunks = 3;
+        // ranges pay (tails of the cluster-editing launches, three host syncs) where there is an upload worth hiding: not when the
+        // estimated device time (ahs_chain_cost, ~7.4 us a unit on one B200) dwarfs the transfer (~55 GB/s)
+        double units = 0;
+        for (int64_t c = 0; c < C; c++) {
+            const int64_t e0 = in->entry_off[c], e1 = in->entry_off[c + 1];
+            if (e0 < 0 || e1 < e0 || e1 > sz.NE) throw ArgFail{"entry_off out of range"};
+            units += ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], e1 - e0, in->enode_off[e1] - in->enode_off[e0], in->ploidy);
+        }
+        if ((double)sz.NEN * 4.0 / 55e6 < 0.03 * units * 7.4e-3) n_chunks = 1;
         if (const char* e = getenv("AHS_CHUNKS")) n_chunks = std::max(1, std::min(N_LANES, atoi(e)));       // tuning / debugging
     }
     std::vector<int64_t> cut(n_chunks + 1, 0); cut[n_chunks] = C;

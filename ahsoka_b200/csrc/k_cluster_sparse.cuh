@@ -358,12 +358,16 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 5) k_cluster_sparse(DB d,
                     // four entries per lane in flight: the loads of a step (slot index -> flag, key -> weights -> costs) are issued for
                     // all four before the first is used — the walk is a chain of dependent L2 accesses otherwise
                     constexpr int U = NT >= 1024 ? 4 : 2;      // the 256-thread blocks run five to an SM: registers matter more there
-                    for (int i0 = lane; i0 < ll; i0 += 32 * U) {
-                        uint32_t s[U], ky[U]; uint8_t fl[U]; bool ok[U]; int y[U], w_xy[U], ya[U], yb[U], yn[U];
+                    // The walk also compacts the list: the slots of a node's partners die one by one as the partners merge into clusters,
+                    // and late in a long chain most entries of list(x) are dead — they are dropped here (live entries move down, in order)
+                    int kept = 0;                                          // warp-uniform: live entries written back so far
+                    for (int base = 0; base < ll; base += 32 * U) {
+                        const int i0 = base + lane;
+                        uint32_t s[U], ky[U]; uint8_t fl[U]; bool ok[U], in[U]; int y[U], w_xy[U], ya[U], yb[U], yn[U];
 #pragma unroll
-                        for (int u = 0; u < U; u++) { ok[u] = i0 + 32 * u < ll; s[u] = ok[u] ? pool[lp + i0 + 32 * u] : 0u; }
+                        for (int u = 0; u < U; u++) { in[u] = i0 + 32 * u < ll; s[u] = in[u] ? pool[lp + i0 + 32 * u] : 0u; }
 #pragma unroll
-                        for (int u = 0; u < U; u++) { fl[u] = ok[u] ? flag[s[u]] : SPF_DEAD; ky[u] = ok[u] ? key[s[u]] : 0u; }
+                        for (int u = 0; u < U; u++) { fl[u] = in[u] ? flag[s[u]] : SPF_DEAD; ky[u] = in[u] ? key[s[u]] : 0u; }
 #pragma unroll
                         for (int u = 0; u < U; u++) {
                             y[u] = sp_other(ky[u], x);
@@ -372,6 +376,15 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 5) k_cluster_sparse(DB d,
                         }
 #pragma unroll
                         for (int u = 0; u < U; u++) if (ok[u]) { w_xy[u] = W[(int64_t)x * n + y[u]]; ya[u] = wa[y[u]]; yb[u] = wb[y[u]]; yn[u] = nw[y[u]]; }
+                        __syncwarp();                                      // every lane has read its entries of this stretch
+#pragma unroll
+                        for (int u = 0; u < U; u++) {
+                            const bool live = !(fl[u] & SPF_DEAD);
+                            const unsigned bal = __ballot_sync(0xffffffffu, live);
+                            const int to = kept + __popc(bal & ((1u << lane) - 1u));
+                            if (live && to != i0 + 32 * u) pool[lp + to] = s[u];       // to <= the entry's own index: never ahead of a read
+                            kept += __popc(bal);
+                        }
 #pragma unroll
                         for (int u = 0; u < U; u++) {
                             if (!ok[u]) continue;
@@ -382,6 +395,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 5) k_cluster_sparse(DB d,
                             }
                         }
                     }
+                    if (lane == 0 && kept != ll) llen[x] = (uint32_t)kept;
                     f = warp_sum_i64(f); p = warp_sum_i64(p);
                     if (lane == 0) { frF[x] = f + max(xn, 0); frP[x] = p + max(-xn, 0); }
                 }

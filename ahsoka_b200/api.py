@@ -307,7 +307,7 @@ def phase_batch(batch: Batch, device: int = 0, devices=None, resident_iters: int
 
     copy=False returns zero-copy numpy views of the library-owned output buffers (the C ABI's own contract:
     valid until ahs_free_out); call .release() on the result before the next call on the same device.
-    devices: list of CUDA ordinals -> ahs_phase_batch_multi (chains dealt LPT across them).
+    devices: list of CUDA ordinals -> ahs_phase_batch_multi (one contiguous, cost-balanced share of the chains per device).
     resident_iters > 0 -> ahs_phase_batch_resident (device-only timing over resident inputs).
     """
     lib = load_library()

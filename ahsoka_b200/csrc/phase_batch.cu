@@ -922,7 +922,7 @@ struct DeviceJob {
             pl.alloc_phase1();
         };
         const bool ahead = getenv("AHS_UPLOAD_AHEAD") && atoi(getenv("AHS_UPLOAD_AHEAD")) != 0;
-        prepare(0);
+        if (n > 0) prepare(0);
         for (int k = 0; k < n; k++) {
             Pipeline& pl = pls[k];
             if (iters > 0) {
@@ -1006,25 +1006,35 @@ struct DeviceJob {
     }
 };
 
-// chains of one call on one device; iters > 0 = resident timing mode.  A call with host output (iters == 0) and a large
-// batch runs as three ranges of chains (equal shares of the alignment nodes, the bulk of the upload).
-static std::vector<Range> ranges_single(const ahs_batch_in* in, const Sizes& sz, int iters) {
-    const int64_t C = sz.C;
+// Ranges of the chains [cb, ce) of a call on one device; iters > 0 = resident timing mode.  A call with host output
+// (iters == 0) and a large share runs as three ranges of chains (12 % / 41 % / 47 % of the alignment nodes, the bulk of the
+// upload): range k+1 uploads under the clustering of range k.
+static std::vector<Range> ranges_of_share(const ahs_batch_in* in, const Sizes& sz, int64_t cb, int64_t ce, int iters) {
+    const int64_t C = ce - cb;
+    auto en_at = [&](int64_t c) -> int64_t {                 // alignment nodes before chain c
+        const int64_t e = in->entry_off[c];
+        if (e < 0 || e > sz.NE) throw ArgFail{"entry_off out of range"};
+        return in->enode_off[e];
+    };
+    const int64_t en0 = en_at(cb), NEN = en_at(ce) - en0;
     int n_chunks = 1;
-    if (iters == 0 && C >= 4096 && sz.NEN >= (int64_t)16 << 20) {
+    if (iters == 0 && C >= 4096 && NEN >= (int64_t)16 << 20) {
         n_chunks = 3;
-        // ranges pay (tails of the cluster-editing launches, three host syncs) where there is an upload worth hiding: not when the
-        // estimated device time (ahs_chain_cost, ~7.4 us a unit on one B200) dwarfs the transfer (~55 GB/s)
-        double units = 0;
-        for (int64_t c = 0; c < C; c++) {
+        // ranges pay (tails of the cluster-editing launches, three host syncs; the big chains of different ranges run one after
+        // the other) where there is an upload worth hiding: not when the estimated device time (ahs_chain_cost, ~7.4 us a unit
+        // on one B200) dwarfs the transfer (~55 GB/s), nor when one long chain's sequential merges (>= 30 us each) do
+        double units = 0; int64_t max_entries = 0;
+        for (int64_t c = cb; c < ce; c++) {
             const int64_t e0 = in->entry_off[c], e1 = in->entry_off[c + 1];
             if (e0 < 0 || e1 < e0 || e1 > sz.NE) throw ArgFail{"entry_off out of range"};
             units += ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], e1 - e0, in->enode_off[e1] - in->enode_off[e0], in->ploidy);
+            max_entries = std::max(max_entries, e1 - e0);
         }
-        if ((double)sz.NEN * 4.0 / 55e6 < 0.03 * units * 7.4e-3) n_chunks = 1;
+        const double upload_ms = (double)NEN * 4.0 / 55e6, nf_max = 0.7 * (double)max_entries;
+        if (upload_ms < 0.03 * units * 7.4e-3 || (nf_max > 160.0 && upload_ms < 0.1 * nf_max * 0.03)) n_chunks = 1;
         if (const char* e = getenv("AHS_CHUNKS")) n_chunks = std::max(1, std::min(N_LANES, atoi(e)));       // tuning / debugging
     }
-    std::vector<int64_t> cut(n_chunks + 1, 0); cut[n_chunks] = C;
+    std::vector<int64_t> cut(n_chunks + 1, cb); cut[n_chunks] = ce;
     // the first chunk is the smallest: nothing runs under its upload, and it only has to cover the next chunk's
     std::vector<double> frac(n_chunks + 1, 1.0);
     for (int k = 0; k <= n_chunks; k++) frac[k] = (double)k / n_chunks;
@@ -1034,13 +1044,9 @@ static std::vector<Range> ranges_single(const ahs_batch_in* in, const Sizes& sz,
         for (int k = 1; k < n_chunks && *q; k++) { frac[k] = std::min(1.0, std::max(frac[k - 1], atof(q))); while (*q && *q != ',') q++; if (*q == ',') q++; }
     }
     for (int k = 1; k < n_chunks; k++) {
-        const int64_t target = (int64_t)((double)sz.NEN * frac[k]);
-        int64_t lo = cut[k - 1], hi = C;                  // first chain whose entries start at or after the target
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) / 2, e = in->entry_off[mid];
-            if (e < 0 || e > sz.NE) throw ArgFail{"entry_off out of range"};
-            if (in->enode_off[e] >= target) hi = mid; else lo = mid + 1;
-        }
+        const int64_t target = en0 + (int64_t)((double)NEN * frac[k]);
+        int64_t lo = cut[k - 1], hi = ce;                 // first chain whose entries start at or after the target
+        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (en_at(mid) >= target) hi = mid; else lo = mid + 1; }
         cut[k] = lo;
     }
     std::vector<Range> r;
@@ -1048,39 +1054,41 @@ static std::vector<Range> ranges_single(const ahs_batch_in* in, const Sizes& sz,
     return r;
 }
 
-// Multi-device plan: the chains arrive largest first (size_sorting, polyassembly.cpp:135-140).  Heavy
-// chains are dealt one by one, the tail of light chains in blocks of consecutive chains, largest cost first onto the
-// least loaded device (LPT).  A device's share is therefore a handful of RANGES of the caller's arrays: they are
-// uploaded and downloaded in place, nothing is re-packed on the host.
+// Multi-device plan: every device gets ONE contiguous share of the chains, cut so that the largest estimated
+// share cost (ahs_chain_cost) is as small as contiguous cuts allow (binary search on the bound, greedy packing on prefix sums),
+// and runs it like a single-device call (ranges_of_share).  The chains arrive largest first (size_sorting,
+// polyassembly.cpp:135-140): the long chains of a share sit in one range and cluster side by side on different SMs.  (The first
+// version dealt heavy chains one by one, largest first onto the least loaded device: balanced on paper, but a device ran its
+// single-chain ranges one after the other — 1.49 s on two devices against 0.85 s on one for the Zipf-skewed batch.)
+// The shares are ranges of the caller's arrays: uploaded and downloaded in place, nothing is re-packed on the host.
 static std::vector<std::vector<Range>> plan_devices(const ahs_batch_in* in, const Sizes& sz, int G, std::vector<double>* load_out) {
     const int64_t C = sz.C; const int p = in->ploidy;
-    std::vector<double> cost(C); double T = 0;
+    std::vector<double> pre(C + 1, 0.0); double cmax = 0;
     for (int64_t c = 0; c < C; c++) {
         const int64_t e0 = in->entry_off[c], e1 = in->entry_off[c + 1];
-        if (e0 < 0 || e1 > sz.NE) throw ArgFail{"entry_off out of range"};
-        cost[c] = ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], e1 - e0, in->enode_off[e1] - in->enode_off[e0], p);
-        T += cost[c];
+        if (e0 < 0 || e1 < e0 || e1 > sz.NE) throw ArgFail{"entry_off out of range"};
+        const double k = ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], e1 - e0, in->enode_off[e1] - in->enode_off[e0], p);
+        pre[c + 1] = pre[c] + k; cmax = std::max(cmax, k);
     }
-    const double grain = T / (4.0 * G);                        // ~4 ranges per device: one per pipeline lane
-    struct Item { int64_t c0, c1; double cost; };
-    std::vector<Item> items;
-    for (int64_t c = 0; c < C;) {
-        if (cost[c] >= grain) { items.push_back(Item{c, c + 1, cost[c]}); c++; continue; }
-        Item it{c, c, 0.0};
-        while (c < C && cost[c] < grain && it.cost + cost[c] <= grain) { it.cost += cost[c]; c++; }
-        if (c == it.c0) { it.cost = cost[c]; c++; }              // (cannot happen: a chain below the grain always fits an empty block)
-        it.c1 = c;
-        items.push_back(it);
-    }
-    std::vector<int> order(items.size()); std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].cost > items[b].cost; });
-    std::vector<double> load(G, 0.0); std::vector<std::vector<Range>> plan(G);
-    for (int i : order) { const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin()); load[g] += items[i].cost; plan[g].push_back(Range{items[i].c0, items[i].c1}); }
-    for (auto& r : plan) {
-        std::sort(r.begin(), r.end(), [](const Range& a, const Range& b) { return a.c0 < b.c0; });
-        std::vector<Range> m;
-        for (auto& x : r) { if (!m.empty() && m.back().c1 == x.c0) m.back().c1 = x.c1; else m.push_back(x); }
-        r = m;
+    // shares under the bound M, packed greedily from the left; returns the cuts (G + 1 entries) or nothing if G shares do not suffice
+    auto pack = [&](double M, std::vector<int64_t>* cuts) {
+        int64_t c = 0; if (cuts) cuts->assign(1, 0);
+        for (int g = 0; g < G && c < C; g++) {
+            int64_t e = (int64_t)(std::upper_bound(pre.begin() + c + 1, pre.end(), pre[c] + M) - pre.begin()) - 1;     // last prefix <= pre[c] + M
+            e = std::max(e, c + 1);                              // a chain above the bound still goes somewhere
+            c = std::min(e, C);
+            if (cuts) cuts->push_back(c);
+        }
+        if (cuts) while ((int)cuts->size() < G + 1) cuts->push_back(c);
+        return c >= C;
+    };
+    double lo = std::max(cmax, pre[C] / G), hi = pre[C] + cmax;
+    for (int it = 0; it < 40 && hi - lo > 1e-6 * hi; it++) { const double mid = 0.5 * (lo + hi); if (pack(mid, nullptr)) hi = mid; else lo = mid; }
+    std::vector<int64_t> cuts; pack(hi, &cuts); cuts[G] = C;
+    std::vector<std::vector<Range>> plan(G); std::vector<double> load(G, 0.0);
+    for (int g = 0; g < G; g++) {
+        if (cuts[g + 1] > cuts[g]) plan[g] = ranges_of_share(in, sz, cuts[g], cuts[g + 1], 0);
+        load[g] = pre[cuts[g + 1]] - pre[cuts[g]];
     }
     if (load_out) *load_out = load;
     return plan;
@@ -1115,7 +1123,7 @@ static void phase_on_devices(const ahs_batch_in* in, ahs_batch_out* out, const i
     }
     std::vector<std::vector<Range>> plan;
     std::vector<double> load;
-    if (G == 1) plan.push_back(ranges_single(in, sz, iters)); else plan = plan_devices(in, sz, G, &load);
+    if (G == 1) plan.push_back(ranges_of_share(in, sz, 0, C, iters)); else plan = plan_devices(in, sz, G, &load);
     // every range of the call, in chain order: (device, index within the device)
     struct Place { int64_t c0; int g, k; };
     std::vector<Place> places;

@@ -293,8 +293,8 @@ def main():
         os.environ["AHS_UPLOAD_AHEAD"] = "0"
         ahead_ms = 1e3 * sum(ta) / len(ta)
     # ---- N > 1: the north-star split, checked once outside the timed regions.  Rank 0 deals ITS batch over all N
-    # devices of the box inside one process (ahs_phase_batch_multi: heavy chains one by one, the tail in ranges of
-    # consecutive chains, LPT; no inter-GPU traffic; every device writes its ranges straight into the output arrays)
+    # devices of the box inside one process (ahs_phase_batch_multi: one contiguous, cost-balanced share of the chains
+    # per device; no inter-GPU traffic; every device writes its ranges straight into the output arrays)
     # and compares every output array with the single-device result; the other ranks idle at the barrier.
     def multi_leg(single_ms):
         devs = list(range(world))

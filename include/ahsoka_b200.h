@@ -149,9 +149,10 @@ int  ahs_phase_batch(const ahs_batch_in *in, ahs_batch_out *out, int device);
 
 /*
  * Phase one batch across `n_devices` devices of this process (device_ids[0..n)).
- * Chains are independent (alignmentstoreadset.cpp:75): they are dealt to devices
- * largest-cost-first (LPT), each device runs on its own host thread and stream,
- * there is no inter-GPU traffic, results are gathered on the host in input order.
+ * Chains are independent (alignmentstoreadset.cpp:75): every device gets one
+ * contiguous share of them, balanced by ahs_chain_cost, and runs on its own host
+ * thread and streams; there is no inter-GPU traffic; every device writes its
+ * results straight into its slices of the output arrays, in input order.
  */
 int  ahs_phase_batch_multi(const ahs_batch_in *in, ahs_batch_out *out,
                            const int *device_ids, int n_devices);
@@ -191,7 +192,7 @@ const char *ahs_last_error(void);
  */
 int  ahs_debug_std_sort(int32_t *keys, int32_t *values, int32_t n, int descending, int device);
 
-/* Cost model used for LPT sharding (cells + pairs + DP work), exposed for the host tools. */
+/* Cost model used to balance the devices' shares (streaming + cluster editing + DP work), exposed for the host tools. */
 double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_nodes, int ploidy);
 
 #ifdef __cplusplus

@@ -1,5 +1,6 @@
 """One batch over 1..N devices of this process through ahs_phase_batch_multi: time per call (page-locked inputs), per-device
-kernel span, equality with the single-device result.  usage: python tools/multi_probe.py [workload] [scale]"""
+kernel span, equality with the single-device result, and the time of the largest chain alone (the lower bound of any
+split by chains).  usage: python tools/multi_probe.py [workload] [scale]"""
 import json
 import os
 import sys
@@ -30,6 +31,13 @@ def main():
             r.release()
         out["runs"].append({"devices": g, "ms_per_call": 1e3 * min(ts), "slowest_device_kernel_span_ms": span, "equal_to_single_device": same})
         g *= 2
+    import numpy as np
+    big = int(np.argmax(np.diff(b.read_off)))
+    one = b.select([big])
+    api.phase_batch(one, device=0, copy=False).release()
+    t0 = time.perf_counter(); api.phase_batch(one, device=0, copy=False).release()
+    out["largest_chain_alone_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["largest_chain_reads"] = int(np.diff(b.read_off).max())
     base = out["runs"][0]["ms_per_call"]
     for r in out["runs"]:
         r["speedup"] = base / r["ms_per_call"]

@@ -254,6 +254,8 @@ def load_library(path: str = LIB_PATH):
     lib.ahs_last_error.restype = C.c_char_p
     lib.ahs_chain_cost.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int]
     lib.ahs_chain_cost.restype = C.c_double
+    lib.ahs_plan_shares.argtypes = [C.POINTER(C.c_double), C.c_int64, C.c_int, C.POINTER(C.c_int64)]
+    lib.ahs_plan_shares.restype = C.c_int
     lib.ahs_warmup.argtypes = [C.c_int, C.c_uint64, C.c_uint64]
     lib.ahs_warmup.restype = C.c_int
     lib.ahs_pin_host.argtypes = [C.c_void_p, C.c_uint64]

@@ -25,6 +25,7 @@
 #include "k_chain.cuh"
 #include "k_cluster_big.cuh"
 #include "k_cluster_sparse.cuh"
+#include "host_plan.hpp"
 #include "k_thread.cuh"
 #include "k_thread_canon.cuh"
 
@@ -1063,28 +1064,14 @@ static std::vector<Range> ranges_of_share(const ahs_batch_in* in, const Sizes& s
 // The shares are ranges of the caller's arrays: uploaded and downloaded in place, nothing is re-packed on the host.
 static std::vector<std::vector<Range>> plan_devices(const ahs_batch_in* in, const Sizes& sz, int G, std::vector<double>* load_out) {
     const int64_t C = sz.C; const int p = in->ploidy;
-    std::vector<double> pre(C + 1, 0.0); double cmax = 0;
+    std::vector<double> pre(C + 1, 0.0);
     for (int64_t c = 0; c < C; c++) {
         const int64_t e0 = in->entry_off[c], e1 = in->entry_off[c + 1];
         if (e0 < 0 || e1 < e0 || e1 > sz.NE) throw ArgFail{"entry_off out of range"};
         const double k = ahs_chain_cost(in->bubble_off[c + 1] - in->bubble_off[c], e1 - e0, in->enode_off[e1] - in->enode_off[e0], p);
-        pre[c + 1] = pre[c] + k; cmax = std::max(cmax, k);
+        pre[c + 1] = pre[c] + k;
     }
-    // shares under the bound M, packed greedily from the left; returns the cuts (G + 1 entries) or nothing if G shares do not suffice
-    auto pack = [&](double M, std::vector<int64_t>* cuts) {
-        int64_t c = 0; if (cuts) cuts->assign(1, 0);
-        for (int g = 0; g < G && c < C; g++) {
-            int64_t e = (int64_t)(std::upper_bound(pre.begin() + c + 1, pre.end(), pre[c] + M) - pre.begin()) - 1;     // last prefix <= pre[c] + M
-            e = std::max(e, c + 1);                              // a chain above the bound still goes somewhere
-            c = std::min(e, C);
-            if (cuts) cuts->push_back(c);
-        }
-        if (cuts) while ((int)cuts->size() < G + 1) cuts->push_back(c);
-        return c >= C;
-    };
-    double lo = std::max(cmax, pre[C] / G), hi = pre[C] + cmax;
-    for (int it = 0; it < 40 && hi - lo > 1e-6 * hi; it++) { const double mid = 0.5 * (lo + hi); if (pack(mid, nullptr)) hi = mid; else lo = mid; }
-    std::vector<int64_t> cuts; pack(hi, &cuts); cuts[G] = C;
+    const std::vector<int64_t> cuts = balanced_contiguous_cuts(pre, G);                  // host_plan.hpp
     std::vector<std::vector<Range>> plan(G); std::vector<double> load(G, 0.0);
     for (int g = 0; g < G; g++) {
         if (cuts[g + 1] > cuts[g]) plan[g] = ranges_of_share(in, sz, cuts[g], cuts[g + 1], 0);
@@ -1228,6 +1215,19 @@ double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_node
     double S = 1; for (int i = 0; i < ploidy && i < 4; i++) S *= 2 * ploidy;
     if (ploidy > 4) S = 1716;
     return 1e-5 * (double)n_entry_nodes + cluster + 1e-7 * (double)n_bubbles * S;
+}
+
+int ahs_plan_shares(const double* chain_cost, int64_t n_chains, int n_parts, int64_t* cuts) {
+    return guarded("ahs_plan_shares", [&]() {
+        if (!cuts || n_parts < 1 || n_chains < 0 || (n_chains > 0 && !chain_cost)) throw ArgFail{"ahs_plan_shares: bad arguments"};
+        std::vector<double> pre((size_t)n_chains + 1, 0.0);
+        for (int64_t c = 0; c < n_chains; c++) {
+            if (!(chain_cost[c] >= 0.0)) throw ArgFail{"ahs_plan_shares: negative or NaN cost"};
+            pre[c + 1] = pre[c] + chain_cost[c];
+        }
+        const std::vector<int64_t> r = balanced_contiguous_cuts(pre, n_parts);
+        for (int g = 0; g <= n_parts; g++) cuts[g] = r[g];
+    });
 }
 
 int ahs_phase_batch(const ahs_batch_in* in, ahs_batch_out* out, int device) {

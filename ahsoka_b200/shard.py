@@ -2,8 +2,13 @@
 
 Bubble chains are independent (reference src/alignmentstoreadset.cpp:75), so N ranks phase N
 disjoint sets of chains with no data-path collective; the host gathers the per-chain results in
-input order.  The partition is the library's own rule (ahs_phase_batch_multi): chains by
-decreasing `ahs_chain_cost`, each onto the currently least loaded part (LPT)."""
+input order.
+
+`contiguous_partition` is the library's own rule (ahs_phase_batch_multi, through `ahs_plan_shares`): one contiguous
+share of the chains per part — they arrive largest first (polyassembly.cpp:135-140) — with the largest summed
+`ahs_chain_cost` as small as contiguous cuts allow; the long chains of a part stay together and cluster side by side.
+`lpt_partition` (chains by decreasing cost, each onto the least loaded part) balances arbitrary orders better and is
+kept for host tools that re-pack their parts anyway."""
 from __future__ import annotations
 
 import numpy as np
@@ -17,6 +22,25 @@ def chain_costs(batch: Batch) -> np.ndarray:
     ne = np.diff(batch.entry_off)
     nen = batch.enode_off[batch.entry_off[1:]] - batch.enode_off[batch.entry_off[:-1]]
     return np.array([lib.ahs_chain_cost(int(b), int(e), int(n), int(batch.ploidy)) for b, e, n in zip(nb, ne, nen)], dtype=np.float64)
+
+
+def plan_shares(cost: np.ndarray, n_parts: int) -> np.ndarray:
+    """cuts[0..n_parts] of the library's share rule for the given chain costs (host-only call)."""
+    import ctypes as C
+    lib = load_library()
+    cost = np.ascontiguousarray(cost, dtype=np.float64)
+    cuts = np.zeros(n_parts + 1, dtype=np.int64)
+    rc = lib.ahs_plan_shares(cost.ctypes.data_as(C.POINTER(C.c_double)), int(cost.shape[0]), int(n_parts),
+                             cuts.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc != 0:
+        raise ValueError(lib.ahs_last_error().decode())
+    return cuts
+
+
+def contiguous_partition(batch: Batch, n_parts: int) -> list[np.ndarray]:
+    """Chain indices of each part: part g = chains [cuts[g], cuts[g+1]) of `plan_shares` (a part may be empty)."""
+    cuts = plan_shares(chain_costs(batch), n_parts)
+    return [np.arange(cuts[g], cuts[g + 1], dtype=np.int64) for g in range(n_parts)]
 
 
 def lpt_partition(batch: Batch, n_parts: int) -> list[np.ndarray]:

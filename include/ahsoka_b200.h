@@ -195,6 +195,14 @@ int  ahs_debug_std_sort(int32_t *keys, int32_t *values, int32_t n, int descendin
 /* Cost model used to balance the devices' shares (streaming + cluster editing + DP work), exposed for the host tools. */
 double ahs_chain_cost(int64_t n_bubbles, int64_t n_entries, int64_t n_entry_nodes, int ploidy);
 
+/*
+ * The share rule of ahs_phase_batch_multi, for host tools that place chains themselves (one process per GPU):
+ * cuts[0..n_parts] with 0 = cuts[0] <= ... <= cuts[n_parts] = n_chains, part g = chains [cuts[g], cuts[g+1]),
+ * contiguous (the chains arrive largest first, polyassembly.cpp:135-140) and such that the largest summed cost is as
+ * small as contiguous cuts allow.  Host-only: needs no CUDA device.  Returns AHS_OK or AHS_ERR_ARG.
+ */
+int  ahs_plan_shares(const double *chain_cost, int64_t n_chains, int n_parts, int64_t *cuts);
+
 #ifdef __cplusplus
 }
 #endif

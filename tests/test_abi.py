@@ -23,7 +23,7 @@ def test_every_declared_symbol_is_exported():
     lib = api.load_library()
     names = _declared_functions()
     assert {"ahs_phase_batch", "ahs_phase_batch_multi", "ahs_phase_batch_resident", "ahs_free_out", "ahs_get_limits",
-            "ahs_device_count", "ahs_last_error", "ahs_chain_cost", "ahs_abi_version", "ahs_pin_host", "ahs_unpin_host", "ahs_warmup"} <= set(names)
+            "ahs_device_count", "ahs_last_error", "ahs_chain_cost", "ahs_plan_shares", "ahs_abi_version", "ahs_pin_host", "ahs_unpin_host", "ahs_warmup"} <= set(names)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
 

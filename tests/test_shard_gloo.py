@@ -1,4 +1,4 @@
-"""N>1 path on CPU: two gloo ranks shard the chains of one batch (LPT, no data-path collective), each phases
+"""N>1 path on CPU: two gloo ranks shard the chains of one batch (the library's share rule, no data-path collective), each phases
 its part, the host gathers in input order.  The phasing engine here is the CPU oracle (test infrastructure):
 what is under test is the sharding / gather logic and the torch.distributed plumbing bench.py uses."""
 import os
@@ -30,10 +30,49 @@ def test_lpt_partition_is_a_balanced_partition():
         assert loads.max() <= loads.mean() + cost.max() + 1e-6
 
 
+def _optimal_makespan(cost, n_parts):
+    # smallest possible largest share over all contiguous partitions into <= n_parts shares (dynamic programme)
+    pre = np.concatenate([[0.0], np.cumsum(cost)])
+    n = len(cost)
+    best = [pre[i] for i in range(n + 1)]                  # one share
+    for _ in range(1, n_parts):
+        nxt = list(best)
+        for i in range(1, n + 1):
+            nxt[i] = min(max(best[j], pre[i] - pre[j]) for j in range(i + 1))
+        best = nxt
+    return best[n]
+
+
+def test_share_rule_is_the_optimal_contiguous_partition():
+    rng = np.random.default_rng(20261019)
+    for trial in range(60):
+        n = int(rng.integers(1, 40)); g = int(rng.integers(1, 9))
+        cost = rng.pareto(1.2, n) + 0.01 if trial % 2 else rng.uniform(0.0, 1.0, n)
+        if trial % 5 == 0:
+            cost = np.sort(cost)[::-1].copy()              # largest first, as the chains arrive
+        cuts = shard.plan_shares(cost, g)
+        assert cuts[0] == 0 and cuts[-1] == n and np.all(np.diff(cuts) >= 0)
+        loads = np.array([cost[cuts[k]:cuts[k + 1]].sum() for k in range(g)])
+        assert loads.max() <= _optimal_makespan(cost, g) * (1 + 1e-5) + 1e-12
+    assert list(shard.plan_shares(np.zeros(0), 3)) == [0, 0, 0, 0]
+    with pytest.raises(ValueError):
+        shard.plan_shares(np.array([1.0, -1.0]), 2)
+
+
+def test_contiguous_partition_covers_every_chain_once():
+    b = synth.generate(synth.params(2, 200, 2, 60, 2, 400, 1.2, 2, depth=20.0, seed=7))
+    cost = shard.chain_costs(b)
+    for n in (1, 2, 3, 8):
+        parts = shard.contiguous_partition(b, n)
+        assert np.array_equal(np.concatenate(parts), np.arange(b.n_chains))
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() <= max(cost.max(), cost.sum() / n) + cost.max() + 1e-6
+
+
 def _worker(rank, world, initfile, outdir):
     dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
     b = synth.generate(_params())
-    parts = shard.lpt_partition(b, world)
+    parts = shard.contiguous_partition(b, world)
     mine = oracle_phase(b.select(parts[rank]))
     # the only collectives of the N>1 path: scalar reductions for the report (bench.py)
     s = torch.tensor([mine.n_cells, mine.n_chains_ok], dtype=torch.int64)

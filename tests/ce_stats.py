@@ -1,6 +1,6 @@
 """Step statistics of cluster editing (rule R2) on a cfg2 sample: merges, single forbids, batched
 rounds, failed rounds, candidate counts.  Design aid for the cluster-editing kernel; uses the CPU
-oracle only to obtain the pair weights (tools/, not product code)."""
+oracle only to obtain the pair weights (test infrastructure, not product code)."""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,5 +1,5 @@
 """Randomised parity stress: many seeded batches of varied shape (chain length, depth, ploidy, alleles, error rate)
-through the C ABI against the CPU oracle, each phased twice (determinism).  usage: python tools/stress_gpu.py [n_cases] [seed]"""
+through the C ABI against the CPU oracle, each phased twice (determinism).  usage: python tests/stress_gpu.py [n_cases] [seed]"""
 import os
 import sys
 import time

@@ -254,7 +254,7 @@ def test_randomised_shapes_twice_each():
     # every case bit-identical to the oracle, in two consecutive runs (a data race would show up as a flaky diff)
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(api.ROOT, "tools", "stress_gpu.py"), "30", "4242"], stdout=subprocess.PIPE, text=True)
+    r = subprocess.run([sys.executable, os.path.join(api.ROOT, "tests", "stress_gpu.py"), "30", "4242"], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
 
 

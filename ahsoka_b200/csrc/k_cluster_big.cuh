@@ -1,5 +1,6 @@
-// k_cluster_big.cuh — cluster editing (rule R2) of chains ABOVE CC_MAXN final reads, one block of 1024 threads per
-// chain, state in HBM / L2.
+// k_cluster_big.cuh — cluster editing (rule R2) of chains ABOVE CC_MAXN final reads, one block of 256 threads per
+// chain, state in HBM / L2.  The predecessor of k_cluster_sparse.cuh, which takes those chains now; selected
+// with AHS_CLUSTER_BIG=1 for comparison runs (chains of 161-8,191 reads) and kept under test.
 //
 // Replaces ClusterEditingSolver(sim,false).run() (call site reference src/alignmentstoreadset.cpp:312-315;
 // algorithm: oracle/core/phase_core.hpp rule R2) where the shared-memory kernel of k_chain.cuh does not fit.  Same

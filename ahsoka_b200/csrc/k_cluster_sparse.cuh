@@ -7,14 +7,17 @@
 // A long chain's graph is banded — a read overlaps ~2 x depth others — and stays local while clusters grow, so the work
 // of a step is bounded by the neighbourhoods of the two end nodes, not by the chain.
 //
-// State of one chain (HBM; one 1024-thread block runs its greedy loop):
+// State of one chain (HBM; one block runs its greedy loop: 1024 threads above SP_SMALL_N reads, 256 threads — five blocks to
+// an SM — below, where a batch has many such chains):
 //   W[n][n]      int32 dense weights (0 = no edge, CC_FORB = forbidden): O(1) third-side look-ups
 //   slots        one per edge that ever had a non-zero weight: key (a << 16 | b, a < b, CURRENT node ids), flags, icf, icp
 //                (int64).  A forbidden edge keeps its slot (flag SPF_FORB): it still counts in the icp of its neighbours.
-//   lists        list(x) = slot indices of the edges at node x, dead slots skipped on the way.  When b merges into a, the
-//                slot of (b,x) is relabelled (a,x) or dies in favour of (a,x), and list(a) is written afresh (bump pool).
+//   lists        list(x) = slot indices of the edges at node x; dead slots are skipped and dropped in place by the walk of a merge.
+//                When b merges into a, the slot of (b,x) is relabelled (a,x) or dies in favour of (a,x), and list(a) is
+//                written afresh (bump pool).
 //   tree         leaf = maxima of 64 consecutive slots, level 2 = maxima of 64 leaves; a step marks the leaves of the
-//                slots it changed and recomputes those, then their level-2 entries, then reduces level 2.
+//                slots it changed; they are queued, dealt round-robin over the warps and recomputed, then their level-2
+//                entries, then level 2 is reduced (warp maxima by redux.sync).
 // Same decisions as k_cluster_chain: merge the pair of largest icf if it is >= the largest icp, else forbid — runs of
 // forbids on negative edges batched exactly (validated against the sequential definition, rolled back otherwise).
 #pragma once

@@ -23,13 +23,23 @@ CASES = [
     ("dip_tiny", synth.params(2, 10, 1, 3, min_len=1, depth=12.0, seed=103), True),
     ("trip", synth.params(3, 3, 1, 12, depth=30.0, seed=104), False),
     ("tetra", synth.params(4, 2, 1, 10, depth=40.0, seed=105), False),
+    ("penta", synth.params(5, 2, 1, 9, depth=50.0, seed=106), False),        # rule R3c: canonical tuples over the first p + 2 clusters
+    ("hexa", synth.params(6, 2, 1, 8, depth=60.0, max_alleles=9, seed=107), False),
+    ("dip_200_reads", synth.params(2, 1, 0, 120, depth=40.0, seed=108), False),   # one chain above 160 final reads: the HBM-resident scoring / cluster-editing route
 ]
+ONLY = set(sys.argv[1:])          # names to (re)generate; none = all
 
 
 def main():
     index = {"cases": []}
+    old = {}
+    if ONLY and os.path.exists(os.path.join(HERE, "index.json")):
+        old = {c["name"]: c for c in json.load(open(os.path.join(HERE, "index.json")))["cases"]}
     ref = os.path.join(ROOT, "oracle", "_ref", "Ahsoka_ref")
     for name, prm, cli in CASES:
+        if ONLY and name not in ONLY and name in old:
+            index["cases"].append(old[name])
+            continue
         with tempfile.TemporaryDirectory() as td:
             b = synth.generate(prm, os.path.join(td, name))
             b.save(os.path.join(HERE, name + ".batch.npz"))

@@ -367,3 +367,18 @@ def test_cfg5_chain_of_five_thousand_bubbles_against_the_truth():
     # every read of the chain has a cluster, cluster ids are dense
     cl = r.read_cluster[int(r.read_off[c]):int(r.read_off[c + 1])]
     assert set(np.unique(cl).tolist()) == set(range(int(r.n_clusters[c])))
+
+
+def test_committed_golden_fixtures():
+    # tests/golden/*.batch.npz -> *.result.npz (written by tests/golden/make_golden.py from the CPU oracle; the same files pin
+    # the oracle itself in tests/test_oracle_cpu.py): ploidy 2-6, duplicated read names, a chain above 160 reads
+    import json
+    golden = os.path.join(api.ROOT, "tests", "golden")
+    cases = json.load(open(os.path.join(golden, "index.json")))["cases"]
+    assert len(cases) >= 8
+    for case in cases:
+        b = api.Batch.load(os.path.join(golden, case["batch"]))
+        want = np.load(os.path.join(golden, case["result"]))
+        got = api.phase_batch(b)
+        for k in got.ARRAYS:
+            assert np.array_equal(getattr(got, k), want[k]), (case["name"], k)
